@@ -1,0 +1,295 @@
+"""TEST INFRASTRUCTURE ONLY -- parity cases shared by the golden-vector generator and the tests.
+
+Every case is written ONCE against the reference's public API (`gpf.kernels.RBF(...)`,
+`gpf.models.GPR(...)`, `m.objective`, `m.predict_f(...)` -- examples/gpr.py:48-56,
+examples/svgp.py:142-160, README.md:17-30 of the reference).  `oracle/gen_golden.py` runs the
+cases against the UNMODIFIED reference package (over `oracle/tf_shim`); `tests/` runs the very
+same functions against the B200 package, which is only possible because that package is a
+drop-in for the reference API.  `conv(a)` turns a numpy array into the tensor type of the
+implementation under test (torch CPU for the shimmed reference, torch CUDA for the product).
+
+Each case function returns a dict  name -> tensor  of scalar/array outputs, and a list of
+(objective_name, model) for which gradients w.r.t. the unconstrained parameters are compared.
+"""
+import numpy as np
+
+
+def synth_gpr(n, d, seed=0):
+    """SURVEY.md section 8(d) synthetic GPR data: X~N(0,1), Y = sin(X.1/sqrt(D)) + 0.1 eps."""
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, d))
+    Y = np.sin(X.sum(1, keepdims=True) / np.sqrt(d)) + 0.1 * rng.standard_normal((n, 1))
+    return X, Y
+
+
+def synth_svgp(n, d, m, seed=0):
+    """SURVEY.md section 8(d) synthetic SVGP data: Y = sin(X.1/4) + 0.1 eps, Z = permuted rows."""
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, d))
+    Y = np.sin(X.sum(1, keepdims=True) / 4.0) + 0.1 * rng.standard_normal((n, 1))
+    Z = X[np.random.default_rng(2).permutation(n)[:m]].copy()
+    return X, Y, Z
+
+
+# --------------------------------------------------------------------------- kernels
+def _kernel_zoo(gpf, d):
+    k = gpf.kernels
+    ls = 0.7 + 0.15 * np.arange(d)
+    return [
+        ('rbf_iso', lambda: k.RBF(d, variance=1.3, lengthscales=0.9, name='a')),
+        ('rbf_ard', lambda: k.RBF(d, variance=0.8, lengthscales=ls, ARD=True, name='b')),
+        ('m12_ard', lambda: k.Matern12(d, variance=1.1, lengthscales=ls, ARD=True, name='c')),
+        ('m32_ard', lambda: k.Matern32(d, variance=0.6, lengthscales=ls, ARD=True, name='d')),
+        ('m52_iso', lambda: k.Matern52(d, variance=1.7, lengthscales=1.4, name='e')),
+        ('exp_ard', lambda: k.Exponential(d, variance=0.9, lengthscales=ls, ARD=True, name='f')),
+        ('lin_iso', lambda: k.Linear(d, variance=0.4, name='g')),
+        ('lin_ard', lambda: k.Linear(d, variance=0.3 + 0.1 * np.arange(d), ARD=True, name='h')),
+        ('periodic', lambda: k.Periodic(d, period=1.7, variance=1.2, lengthscales=0.8, name='i')),
+        ('rbf_active', lambda: k.RBF(2, variance=1.0, lengthscales=np.array([0.5, 1.5]), ARD=True,
+                                     active_dims=[2, 0], name='j')),
+        ('sum', lambda: k.RBF(d, lengthscales=ls, ARD=True, name='k1')
+            + k.Linear(d, variance=0.2, name='k2') + 0.37),
+        ('product', lambda: k.Matern32(d, lengthscales=1.2, name='k3')
+            * k.Periodic(d, period=2.1, name='k4') * 1.9),
+        ('sum_of_product', lambda: k.RBF(2, active_dims=[0, 1], name='k5')
+            * k.Linear(1, active_dims=[2], name='k6') + k.Matern52(d, name='k7')),
+    ]
+
+
+def case_kernels(gpf, conv):
+    """Gram matrices of every hot-path primitive and composition: K(X), K(X,X2), Kdiag(X)
+    (kernels.py:408-439, 499-510, 562-610, 806-819, 1000-1084)."""
+    d = 3
+    rng = np.random.default_rng(10)
+    X = rng.standard_normal((37, d)) * 1.3
+    X2 = rng.standard_normal((23, d)) * 1.3
+    out = {}
+    for name, make in _kernel_zoo(gpf, d):
+        kern = make()
+        out[name + '/K'] = kern.K(conv(X))
+        out[name + '/K2'] = kern.K(conv(X), conv(X2))
+        out[name + '/Kdiag'] = kern.Kdiag(conv(X))
+    return out, []
+
+
+def nkn_c3_kernel(gpf, d, weights=None):
+    """The section-8(d) NKN topology: k=6 primitives, Linear 6->8, Product 2, Linear 4->4,
+    Product 2, Linear 2->1 (neural_kernel_network_wrapper.py:38-40 hparams schema).  The
+    reference draws Linear weights from numpy's global RNG (wrapper.py:100-104), so it is
+    seeded here; an implementation may instead be handed `weights` explicitly."""
+    k = gpf.kernels
+    prims = [
+        k.RBF(d, ARD=True, name='p0'),
+        k.RBF(d, lengthscales=2.0, ARD=True, name='p1'),
+        k.Periodic(d, period=1.0, lengthscales=1.0, name='p2'),
+        k.Periodic(d, period=2.0, name='p3'),
+        k.Linear(d, ARD=True, name='p4'),
+        k.Linear(d, ARD=True, name='p5'),
+    ]
+    hparams = [
+        dict(name='Linear', params=dict(input_dim=6, output_dim=8, name='l0')),
+        dict(name='Product', params=dict(input_dim=8, step=2, name='l1')),
+        dict(name='Linear', params=dict(input_dim=4, output_dim=4, name='l2')),
+        dict(name='Product', params=dict(input_dim=4, step=2, name='l3')),
+        dict(name='Linear', params=dict(input_dim=2, output_dim=1, name='l4')),
+    ]
+    np.random.seed(0)
+    wrapper = gpf.neural_kernel_network.NKNWrapper(hparams)
+    return gpf.neural_kernel_network.NeuralKernelNetwork(d, prims, wrapper)
+
+
+def case_nkn(gpf, conv):
+    """NKN Gram + NKN-GPR objective, predict (neural_kernel_network.py:35-47)."""
+    d, n = 3, 150
+    X, Y = synth_gpr(n, d, seed=3)
+    Xs = np.random.default_rng(4).standard_normal((20, d))
+    kern = nkn_c3_kernel(gpf, d)
+    m = gpf.models.GPR(conv(X), conv(Y), kern=kern, name='nkn_gpr')
+    out = {'K': kern.K(conv(X[:30])), 'K2': kern.K(conv(X[:30]), conv(Xs)),
+           'Kdiag': kern.Kdiag(conv(X[:30])), 'objective': m.objective}
+    mu, var = m.predict_f(conv(Xs))
+    out['pred_mu'], out['pred_var'] = mu, var
+    return out, [('objective', m)]
+
+
+# --------------------------------------------------------------------------- GPR
+def _gpr(gpf, conv, n, d, ls, nstar, name):
+    X, Y = synth_gpr(n, d, seed=0)
+    Xs = np.random.default_rng(1).standard_normal((nstar, d))
+    kern = gpf.kernels.RBF(d, ARD=True, lengthscales=ls, name=name + '_k')
+    m = gpf.models.GPR(conv(X), conv(Y), kern=kern, name=name)
+    out = {'objective': m.objective}
+    mu, var = m.predict_f(conv(Xs))
+    out['pred_mu'], out['pred_var'] = mu, var
+    return out, [('objective', m)]
+
+
+def case_gpr_c1(gpf, conv):
+    """C1: GPR ARD-RBF N=1000 D=4, reference-default l=1 (examples/gpr.py:48-56)."""
+    return _gpr(gpf, conv, 1000, 4, None, 1024, 'c1')
+
+
+def case_gpr_c1_ls(gpf, conv):
+    """C1 with l = sqrt(D): non-trivial off-diagonals."""
+    return _gpr(gpf, conv, 1000, 4, 2.0, 64, 'c1b')
+
+
+def case_gpr_c2_small(gpf, conv):
+    """C2/C5 scaled down: GPR ARD-RBF N=2048 D=8, l = sqrt(8)."""
+    return _gpr(gpf, conv, 2048, 8, np.sqrt(8.0), 64, 'c2s')
+
+
+def case_gpr_misc(gpf, conv):
+    """GPR with R=3 output columns, Matern32+Linear kernel, full_cov predict, predict_y and
+    predict_density (models/gpr.py:118-131, models/model.py:121-166), N not a multiple of
+    any tile size."""
+    n, d = 301, 5
+    rng = np.random.default_rng(7)
+    X = rng.standard_normal((n, d))
+    Y = np.stack([np.sin(X[:, 0]), np.cos(X[:, 1]) * X[:, 2], X.sum(1) * 0.3], 1) \
+        + 0.05 * rng.standard_normal((n, 3))
+    Xs = rng.standard_normal((17, d))
+    Ys = rng.standard_normal((17, 3))
+    kern = gpf.kernels.Matern32(d, lengthscales=1.5, name='gm_a') \
+        + gpf.kernels.Linear(d, variance=0.1, name='gm_b')
+    m = gpf.models.GPR(conv(X), conv(Y), kern=kern, obs_var=0.05, name='gm')
+    out = {'objective': m.objective}
+    out['pred_mu'], out['pred_var'] = m.predict_f(conv(Xs))
+    out['full_mu'], out['full_cov'] = m.predict_f_full_cov(conv(Xs))
+    out['y_mu'], out['y_var'] = m.predict_y(conv(Xs))
+    out['density'] = m.predict_density(conv(Xs), conv(Ys))
+    return out, [('objective', m)]
+
+
+# --------------------------------------------------------------------------- SVGP / SGPR
+def _svgp(gpf, conv, n, d, minducing, batch, whiten, q_diag, latents, name, ls=None):
+    X, Y, Z = synth_svgp(n, d, minducing, seed=0)
+    if latents > 1:
+        Y = np.concatenate([Y * (1 + 0.3 * j) + 0.1 * j for j in range(latents)], 1)
+    rng = np.random.default_rng(5)
+    kern = gpf.kernels.RBF(d, ARD=True, lengthscales=ls if ls is not None else np.sqrt(d),
+                           name=name + '_k')
+    lik = gpf.likelihoods.Gaussian(var=0.1)
+    Xb, Yb = X[:batch], Y[:batch]
+    m = gpf.models.SVGP(conv(Xb), conv(Yb), kern, lik, Z=Z.copy(), whiten=whiten,
+                        q_diag=q_diag, num_data=n, name=name)
+    # move q_mu / q_sqrt off their trivial initial values (svgp.py:81-89) so every term of the
+    # bound and of base_conditional is exercised
+    import torch
+    with torch.no_grad():
+        qm = m._q_mu.unconstrained_tensor
+        qm.copy_(torch.as_tensor(0.3 * rng.standard_normal(tuple(qm.shape))).to(qm))
+        qs = m._q_sqrt.unconstrained_tensor
+        qs.add_(torch.as_tensor(0.05 * rng.standard_normal(tuple(qs.shape))).to(qs))
+    out = {'objective': m.objective, 'KL': m.build_prior_KL()}
+    Xs = rng.standard_normal((19, d))
+    out['pred_mu'], out['pred_var'] = m.predict_f(conv(Xs))
+    return out, [('objective', m)], m, Xs
+
+
+def case_svgp_white_full(gpf, conv):
+    """SVGP default config whiten=True, q_diag=False (svgp.py:45-130) at a scaled-down C4."""
+    o, g, m, Xs = _svgp(gpf, conv, 4000, 16, 256, 1024, True, False, 1, 'sv1', ls=4.0)
+    o['full_mu'], o['full_cov'] = m.predict_f_full_cov(conv(Xs))
+    return o, g
+
+
+def case_svgp_nonwhite_full(gpf, conv):
+    """whiten=False, q_diag=False, 2 latent GPs (conditionals.py:99-100, KL :92-103)."""
+    o, g, _, _ = _svgp(gpf, conv, 500, 4, 40, 200, False, False, 2, 'sv2')
+    return o, g
+
+
+def case_svgp_white_diag(gpf, conv):
+    """whiten=True, q_diag=True, 2 latent GPs (conditionals.py:106-107)."""
+    o, g, _, _ = _svgp(gpf, conv, 500, 4, 40, 200, True, True, 2, 'sv3')
+    return o, g
+
+
+def case_svgp_nonwhite_diag(gpf, conv):
+    """whiten=False, q_diag=True (kullback_leiblers.py:84-91)."""
+    o, g, _, _ = _svgp(gpf, conv, 500, 4, 40, 200, False, True, 1, 'sv4')
+    return o, g
+
+
+def case_sgpr(gpf, conv):
+    """SGPR collapsed bound and predictions (models/sgpr.py:121-189)."""
+    n, d, mi = 600, 4, 50
+    X, Y, Z = synth_svgp(n, d, mi, seed=8)
+    Xs = np.random.default_rng(9).standard_normal((21, d))
+    kern = gpf.kernels.RBF(d, ARD=True, lengthscales=2.0, name='sg_k')
+    m = gpf.models.SGPR(conv(X), conv(Y), kern, Z=Z.copy(), obs_var=0.1, name='sg')
+    out = {'objective': m.objective}
+    out['pred_mu'], out['pred_var'] = m.predict_f(conv(Xs))
+    out['full_mu'], out['full_cov'] = m.predict_f_full_cov(conv(Xs))
+    return out, [('objective', m)]
+
+
+# --------------------------------------------------------------------------- free functions
+def case_functions(gpf, conv):
+    """base_conditional (conditionals.py:81-121), conditional (:25-66), gauss_kl
+    (kullback_leiblers.py:26-105) and multivariate_normal (densities.py:73-95) called
+    directly, all q_sqrt / white / full_cov variants."""
+    rng = np.random.default_rng(11)
+    M, N, K, d = 24, 31, 2, 3
+    Xm = rng.standard_normal((M, d))
+    Xn = rng.standard_normal((N, d))
+    kern = gpf.kernels.Matern52(d, lengthscales=1.3, variance=1.4, name='fn_k')
+    f = rng.standard_normal((M, K))
+    qd = 0.5 + rng.random((M, K))
+    qf = np.stack([np.tril(rng.standard_normal((M, M))) * 0.3 + np.eye(M) for _ in range(K)], 2)
+    out = {}
+    for white in (False, True):
+        for full_cov in (False, True):
+            for qname, q in (('none', None), ('diag', qd), ('full', qf)):
+                mu, var = gpf.conditionals.conditional(
+                    conv(Xn), conv(Xm), kern, conv(f), full_cov=full_cov,
+                    q_sqrt=None if q is None else conv(q), white=white)
+                tag = 'cond/w%d_f%d_%s' % (white, full_cov, qname)
+                out[tag + '/mu'], out[tag + '/var'] = mu, var
+    Kmm = kern.K(conv(Xm)) + conv(np.eye(M) * 1e-6)
+    for qname, q in (('diag', qd), ('full', qf)):
+        out['kl/white_' + qname] = gpf.kullback_leiblers.gauss_kl(conv(f), conv(q))
+        out['kl/K_' + qname] = gpf.kullback_leiblers.gauss_kl(conv(f), conv(q), Kmm)
+    A = rng.standard_normal((M, M))
+    L = np.linalg.cholesky(A @ A.T + M * np.eye(M))
+    x = rng.standard_normal((M, 3))
+    mu = rng.standard_normal((M, 3))
+    out['mvn'] = gpf.densities.multivariate_normal(conv(x), conv(mu), conv(L))
+    return out, []
+
+
+CASES = {
+    'kernels': case_kernels,
+    'nkn': case_nkn,
+    'gpr_c1': case_gpr_c1,
+    'gpr_c1_ls': case_gpr_c1_ls,
+    'gpr_c2_small': case_gpr_c2_small,
+    'gpr_misc': case_gpr_misc,
+    'svgp_white_full': case_svgp_white_full,
+    'svgp_nonwhite_full': case_svgp_nonwhite_full,
+    'svgp_white_diag': case_svgp_white_diag,
+    'svgp_nonwhite_diag': case_svgp_nonwhite_diag,
+    'sgpr': case_sgpr,
+    'functions': case_functions,
+}
+
+
+def run_case(gpf, name, conv):
+    """Run one case; returns {key: numpy array} including 'grad/<objective>/<i>' entries, the
+    gradient of each listed objective w.r.t. the i-th entry of `model.parameters`
+    (unconstrained tensors, reference order: models/model.py:119, svgp.py:91)."""
+    import torch
+    out, grads = CASES[name](gpf, conv)
+    res = {}
+    for key, val in out.items():
+        res[key] = val.detach().cpu().numpy() if isinstance(val, torch.Tensor) else np.asarray(val)
+    for oname, model in grads:
+        params = [p.unconstrained_tensor for p in model.parameters]
+        obj = model.objective
+        gs = torch.autograd.grad(obj, params, allow_unused=True)
+        for i, (p, g) in enumerate(zip(params, gs)):
+            res['param/%s/%d' % (oname, i)] = p.detach().cpu().numpy()
+            res['grad/%s/%d' % (oname, i)] = (torch.zeros_like(p) if g is None else g) \
+                .detach().cpu().numpy()
+    return res

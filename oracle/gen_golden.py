@@ -1,0 +1,56 @@
+"""TEST INFRASTRUCTURE ONLY -- writes tests/golden/*.npz by running the UNMODIFIED reference.
+
+    python oracle/gen_golden.py            # needs /root/reference (this container only)
+
+The reference package (/root/reference/gpflowSlim) is imported as-is with `oracle/tf_shim`
+standing in for the absent TensorFlow 1.x (see tf_shim/tensorflow/__init__.py for what that
+does and does not pin) and float_type switched to float64 the way a cwd `gpflowrc` would
+(gpflowrc:7, _settings.py:159-181).  Each case in oracle/cases.py is evaluated through the
+reference's public API and its outputs + parameter gradients are stored.  The GPU box has no
+/root/reference; it only ever sees the committed .npz files.
+"""
+import collections
+import collections.abc
+import os
+import sys
+import warnings
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get('GPSLIM_REFERENCE', '/root/reference')
+
+collections.Mapping = collections.abc.Mapping      # _settings.py:147 predates Python 3.10
+sys.dont_write_bytecode = True
+sys.path.insert(0, os.path.join(HERE, 'tf_shim'))
+sys.path.insert(0, REF)
+sys.path.insert(0, ROOT)
+warnings.filterwarnings('ignore')
+
+import numpy as np                                  # noqa: E402
+import torch                                        # noqa: E402
+import tensorflow as tf                             # noqa: E402  (the shim)
+import gpflowSlim as gpf                            # noqa: E402  (the reference)
+
+assert os.path.realpath(gpf.__file__).startswith(os.path.realpath(REF)), gpf.__file__
+gpf.settings.dtypes.float_type = np.float64
+
+from oracle import cases                            # noqa: E402
+
+
+def conv(a):
+    return torch.as_tensor(np.asarray(a), dtype=torch.float64)
+
+
+def main(names):
+    outdir = os.path.join(ROOT, 'tests', 'golden')
+    os.makedirs(outdir, exist_ok=True)
+    for name in names:
+        tf.shim_reset()
+        res = cases.run_case(gpf, name, conv)
+        path = os.path.join(outdir, name + '.npz')
+        np.savez_compressed(path, **res)
+        print('%-22s %3d arrays  %8.1f KiB' % (name, len(res), os.path.getsize(path) / 1024.0))
+
+
+if __name__ == '__main__':
+    main(sys.argv[1:] or list(cases.CASES))
