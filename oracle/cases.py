@@ -286,6 +286,11 @@ def run_case(gpf, name, conv):
         res[key] = val.detach().cpu().numpy() if isinstance(val, torch.Tensor) else np.asarray(val)
     for oname, model in grads:
         params = [p.unconstrained_tensor for p in model.parameters]
+        if hasattr(model, 'feature'):
+            # the reference keeps the inducing inputs Z out of `model.parameters`
+            # (svgp.py:91, sgpr.py:116) although Z is a trainable variable (features.py:65);
+            # its gradient is part of the hot path, so it is appended as the last entry.
+            params.append(model.feature._Z.unconstrained_tensor)
         obj = model.objective
         gs = torch.autograd.grad(obj, params, allow_unused=True)
         for i, (p, g) in enumerate(zip(params, gs)):

@@ -1,0 +1,248 @@
+"""Pins oracle/ref_torch.py to the golden vectors the UNMODIFIED reference produced
+(oracle/gen_golden.py).  CPU only.  Tolerance 1e-10 relative: both sides are float64 LAPACK
+arithmetic of the same op sequence."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases
+from oracle import ref_torch as R
+
+RTOL = 1e-10
+
+
+def close(a, b, rtol=RTOL, what=''):
+    a = np.asarray(a.detach().numpy() if isinstance(a, torch.Tensor) else a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    scale = max(np.abs(b).max(), 1e-300)
+    err = np.abs(a - b).max() / scale
+    assert err < rtol, '%s: rel err %.3e' % (what, err)
+
+
+def sp(raw):
+    return R.softplus_fwd(torch.tensor(raw, requires_grad=False))
+
+
+def leaf(a):
+    return torch.tensor(np.asarray(a), dtype=torch.float64, requires_grad=True)
+
+
+def grads_wrt(obj, leaves):
+    return torch.autograd.grad(obj, leaves, allow_unused=True)
+
+
+def test_transforms_roundtrip():
+    y = np.array([1e-5, 0.1, 1.0, 30.0, 800.0])
+    raw = R.softplus_inv(y)
+    close(R.softplus_fwd(raw), y, 1e-12, 'softplus roundtrip')
+    v = np.arange(1.0, 13.0).reshape(2, 6)
+    tri = R.vec_to_tri(v, 3)
+    assert tri.shape == (3, 3, 2)
+    assert tri[1, 0, 0] == 2.0 and tri[2, 2, 1] == 12.0 and tri[0, 1, 0] == 0.0
+
+
+def _zoo_specs(d):
+    ls = torch.tensor(0.7 + 0.15 * np.arange(d))
+    t = lambda v: torch.tensor(v, dtype=torch.float64)
+    st = lambda typ, v, l, ad=None, dim=d: dict(type=typ, variance=t(v), lengthscales=l,
+                                                active_dims=ad, input_dim=dim)
+    return {
+        'rbf_iso': st('rbf', 1.3, t(0.9)),
+        'rbf_ard': st('rbf', 0.8, ls),
+        'm12_ard': st('matern12', 1.1, ls),
+        'm32_ard': st('matern32', 0.6, ls),
+        'm52_iso': st('matern52', 1.7, t(1.4)),
+        'exp_ard': st('exponential', 0.9, ls),
+        'lin_iso': dict(type='linear', variance=t(0.4), input_dim=d),
+        'lin_ard': dict(type='linear', variance=t(0.3 + 0.1 * np.arange(d)), input_dim=d),
+        'periodic': dict(type='periodic', variance=t(1.2), lengthscales=t(0.8), period=t(1.7),
+                         input_dim=d),
+        'rbf_active': st('rbf', 1.0, t([0.5, 1.5]), [2, 0], 2),
+        'sum': dict(type='sum', children=[st('rbf', 1.0, ls),
+                                          dict(type='linear', variance=t(0.2), input_dim=d), 0.37]),
+        'product': dict(type='product', children=[
+            st('matern32', 1.0, t(1.2)),
+            dict(type='periodic', variance=t(1.0), lengthscales=t(1.0), period=t(2.1), input_dim=d),
+            1.9]),
+        'sum_of_product': dict(type='sum', children=[
+            dict(type='product', children=[st('rbf', 1.0, t(1.0), [0, 1], 2),
+                                           dict(type='linear', variance=t(1.0), active_dims=[2])]),
+            st('matern52', 1.0, t(1.0))]),
+    }
+
+
+def test_kernels(golden):
+    g = golden('kernels')
+    d = 3
+    rng = np.random.default_rng(10)
+    X = torch.tensor(rng.standard_normal((37, d)) * 1.3)
+    X2 = torch.tensor(rng.standard_normal((23, d)) * 1.3)
+    for name, spec in _zoo_specs(d).items():
+        # constrained values went through softplus_inv -> softplus in the reference: 1e-12 ok
+        close(R.K(spec, X), g[name + '/K'], 1e-9, name + '/K')
+        close(R.K(spec, X, X2), g[name + '/K2'], 1e-9, name + '/K2')
+        close(R.Kdiag(spec, X), g[name + '/Kdiag'], 1e-9, name + '/Kdiag')
+
+
+def _gpr_from_golden(g, d):
+    raw = [leaf(g['param/objective/%d' % i]) for i in range(3)]
+    spec = dict(type='rbf', variance=R.softplus_fwd(raw[0]), lengthscales=R.softplus_fwd(raw[1]))
+    return raw, spec, R.softplus_fwd(raw[2])
+
+
+@pytest.mark.parametrize('name,n,d,nstar', [('gpr_c1', 1000, 4, 1024), ('gpr_c1_ls', 1000, 4, 64),
+                                            ('gpr_c2_small', 2048, 8, 64)])
+def test_gpr(golden, name, n, d, nstar):
+    g = golden(name)
+    X, Y = cases.synth_gpr(n, d, seed=0)
+    Xs = np.random.default_rng(1).standard_normal((nstar, d))
+    X, Y, Xs = map(torch.tensor, (X, Y, Xs))
+    raw, spec, noise = _gpr_from_golden(g, d)
+    obj = R.gpr_nlml(spec, X, Y, noise)
+    close(obj, g['objective'], RTOL, 'objective')
+    for i, gr in enumerate(grads_wrt(obj, raw)):
+        close(gr, g['grad/objective/%d' % i], 1e-9, 'grad %d' % i)
+    mu, var = R.gpr_predict(spec, X, Y, noise, Xs)
+    close(mu, g['pred_mu'], 1e-9, 'pred_mu')
+    close(var, g['pred_var'], 1e-9, 'pred_var')
+    # independent LAPACK + analytic-gradient route (the algebra the CUDA backward uses)
+    nl, gv, gl, gn = R.gpr_nlml_grad_lapack(X.numpy(), Y.numpy(), spec['variance'].item(),
+                                            spec['lengthscales'].detach().numpy(), noise.item())
+    close(nl, g['objective'], RTOL, 'lapack nlml')
+    sig = lambda r: torch.sigmoid(r).detach().numpy()       # d softplus / d raw
+    close(gv * sig(raw[0]), g['grad/objective/0'], 1e-8, 'lapack g_var')
+    close(gl * sig(raw[1]), g['grad/objective/1'], 1e-8, 'lapack g_ls')
+    close(gn * sig(raw[2]), g['grad/objective/2'], 1e-8, 'lapack g_noise')
+
+
+def test_nkn(golden):
+    g = golden('nkn')
+    d, n = 3, 150
+    X, Y = cases.synth_gpr(n, d, seed=3)
+    Xs = np.random.default_rng(4).standard_normal((20, d))
+    X, Y, Xs = map(torch.tensor, (X, Y, Xs))
+    raw = [leaf(g['param/objective/%d' % i]) for i in range(19)]
+    c = [R.softplus_fwd(r) for r in raw]
+    # parameter order: wrapper (W0,b0,W2,b2,W4,b4) then primitives (neural_kernel_network.py:31-33)
+    layers = [('linear', c[0], c[1]), ('product', 2), ('linear', c[2], c[3]), ('product', 2),
+              ('linear', c[4], c[5])]
+    prims = [dict(type='rbf', variance=c[6], lengthscales=c[7]),
+             dict(type='rbf', variance=c[8], lengthscales=c[9]),
+             dict(type='periodic', variance=c[10], lengthscales=c[11], period=c[12]),
+             dict(type='periodic', variance=c[13], lengthscales=c[14], period=c[15]),
+             dict(type='linear', variance=c[16]), dict(type='linear', variance=c[17])]
+    # NeuralKernelNetwork itself has no active_dims restriction on primitives
+    spec = dict(type='nkn', prims=prims, layers=layers)
+    noise = c[18]
+    assert len([k for k in g if k.startswith('param/objective/')]) == 19
+    close(R.K(spec, X[:30]), g['K'], RTOL, 'K')
+    close(R.K(spec, X[:30], Xs), g['K2'], RTOL, 'K2')
+    close(R.Kdiag(spec, X[:30]), g['Kdiag'], RTOL, 'Kdiag')
+    obj = R.gpr_nlml(spec, X, Y, noise)
+    close(obj, g['objective'], RTOL, 'objective')
+    for i, gr in enumerate(grads_wrt(obj, raw[:19])):
+        close(gr, g['grad/objective/%d' % i], 1e-8, 'grad %d' % i)
+    mu, var = R.gpr_predict(spec, X, Y, noise, Xs)
+    close(mu, g['pred_mu'], 1e-9, 'pred_mu')
+    close(var, g['pred_var'], 1e-8, 'pred_var')
+
+
+def _svgp_inputs(n, d, m, batch, latents):
+    X, Y, Z = cases.synth_svgp(n, d, m, seed=0)
+    if latents > 1:
+        Y = np.concatenate([Y * (1 + 0.3 * j) + 0.1 * j for j in range(latents)], 1)
+    return torch.tensor(X[:batch]), torch.tensor(Y[:batch])
+
+
+@pytest.mark.parametrize('name,n,d,m,batch,whiten,q_diag,latents', [
+    ('svgp_white_full', 4000, 16, 256, 1024, True, False, 1),
+    ('svgp_nonwhite_full', 500, 4, 40, 200, False, False, 2),
+    ('svgp_white_diag', 500, 4, 40, 200, True, True, 2),
+    ('svgp_nonwhite_diag', 500, 4, 40, 200, False, True, 1)])
+def test_svgp(golden, name, n, d, m, batch, whiten, q_diag, latents):
+    g = golden(name)
+    Xb, Yb = _svgp_inputs(n, d, m, batch, latents)
+    # parameters: kern.variance, kern.ls, likelihood.variance, q_mu, q_sqrt, then Z
+    raw = [leaf(g['param/objective/%d' % i]) for i in range(6)]
+    spec = dict(type='rbf', variance=R.softplus_fwd(raw[0]), lengthscales=R.softplus_fwd(raw[1]))
+    noise = R.softplus_fwd(raw[2])
+    q_mu = raw[3]
+    q_sqrt = R.softplus_fwd(raw[4]) if q_diag else R.vec_to_tri(raw[4], m)
+    Z = raw[5]
+    obj = R.svgp_objective(spec, Xb, Yb, Z, q_mu, q_sqrt, noise, n, whiten=whiten)
+    close(obj, g['objective'], RTOL, 'objective')
+    Kuu = None if whiten else R.K(spec, Z) + torch.eye(m, dtype=torch.float64) * 1e-6
+    close(R.gauss_kl(q_mu, q_sqrt, Kuu), g['KL'], 1e-9, 'KL')
+    for i, gr in enumerate(grads_wrt(obj, raw)):
+        close(gr, g['grad/objective/%d' % i], 1e-8, 'grad %d' % i)
+    Xs = None
+    rng = np.random.default_rng(5)
+    rng.standard_normal(tuple(g['param/objective/3'].shape))
+    rng.standard_normal(tuple(g['param/objective/4'].shape))
+    Xs = torch.tensor(rng.standard_normal((19, d)))
+    mu, var = R.conditional(spec, Xs, Z, q_mu, q_sqrt=q_sqrt, white=whiten)
+    close(mu, g['pred_mu'], 1e-9, 'pred_mu')
+    close(var, g['pred_var'], 1e-8, 'pred_var')
+
+
+def test_sgpr(golden):
+    g = golden('sgpr')
+    n, d, mi = 600, 4, 50
+    X, Y, _ = cases.synth_svgp(n, d, mi, seed=8)
+    Xs = torch.tensor(np.random.default_rng(9).standard_normal((21, d)))
+    X, Y = torch.tensor(X), torch.tensor(Y)
+    raw = [leaf(g['param/objective/%d' % i]) for i in range(4)]
+    spec = dict(type='rbf', variance=R.softplus_fwd(raw[0]), lengthscales=R.softplus_fwd(raw[1]))
+    noise = R.softplus_fwd(raw[2])
+    Z = raw[3]
+    obj = R.sgpr_objective(spec, X, Y, Z, noise)
+    close(obj, g['objective'], RTOL, 'objective')
+    for i, gr in enumerate(grads_wrt(obj, raw)):
+        close(gr, g['grad/objective/%d' % i], 1e-8, 'grad %d' % i)
+    mu, var = R.sgpr_predict(spec, X, Y, Z, noise, Xs)
+    close(mu, g['pred_mu'], 1e-9, 'pred_mu')
+    close(var, g['pred_var'], 1e-8, 'pred_var')
+    mu, cov = R.sgpr_predict(spec, X, Y, Z, noise, Xs, full_cov=True)
+    close(cov, g['full_cov'], 1e-8, 'full_cov')
+
+
+def test_functions(golden):
+    g = golden('functions')
+    rng = np.random.default_rng(11)
+    M, N, K, d = 24, 31, 2, 3
+    Xm = torch.tensor(rng.standard_normal((M, d)))
+    Xn = torch.tensor(rng.standard_normal((N, d)))
+    spec = dict(type='matern52', variance=torch.tensor(1.4, dtype=torch.float64),
+                lengthscales=torch.tensor(1.3, dtype=torch.float64))
+    f = torch.tensor(rng.standard_normal((M, K)))
+    qd = torch.tensor(0.5 + rng.random((M, K)))
+    qf = torch.tensor(np.stack([np.tril(rng.standard_normal((M, M))) * 0.3 + np.eye(M)
+                                for _ in range(K)], 2))
+    for white in (False, True):
+        for full_cov in (False, True):
+            for qname, q in (('none', None), ('diag', qd), ('full', qf)):
+                mu, var = R.conditional(spec, Xn, Xm, f, full_cov=full_cov, q_sqrt=q, white=white)
+                tag = 'cond/w%d_f%d_%s' % (white, full_cov, qname)
+                close(mu, g[tag + '/mu'], 1e-9, tag + '/mu')
+                close(var, g[tag + '/var'], 1e-9, tag + '/var')
+    Kmm = R.K(spec, Xm) + torch.eye(M, dtype=torch.float64) * 1e-6
+    for qname, q in (('diag', qd), ('full', qf)):
+        close(R.gauss_kl(f, q), g['kl/white_' + qname], 1e-10, 'kl white ' + qname)
+        close(R.gauss_kl(f, q, Kmm), g['kl/K_' + qname], 1e-9, 'kl K ' + qname)
+    A = rng.standard_normal((M, M))
+    L = np.linalg.cholesky(A @ A.T + M * np.eye(M))
+    x = rng.standard_normal((M, 3))
+    mu = rng.standard_normal((M, 3))
+    close(R.multivariate_normal(torch.tensor(x), torch.tensor(mu), torch.tensor(L)), g['mvn'],
+          1e-10, 'mvn')
+
+
+def test_tf_adam_first_step():
+    """First TF-Adam step moves every coordinate by lr*g/(|g| + eps*sqrt(1-b2)) ~= lr*sign(g)."""
+    p = [torch.tensor([1.0, -2.0], dtype=torch.float64)]
+    gr = [torch.tensor([0.5, -3.0], dtype=torch.float64)]
+    new = R.tf_adam_step(p, gr, {}, lr=1e-3)
+    close(new[0], np.array([1.0 - 1e-3, -2.0 + 1e-3]), 1e-6, 'adam')
