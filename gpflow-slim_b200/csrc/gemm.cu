@@ -1,0 +1,298 @@
+// FP64 tensor-core GEMM family:  C = alpha * A * B^T + beta * C,  all row-major, both operands
+// with K contiguous ("NT").  This one kernel carries every O(n^3) flop of the hot path: the
+// SYRK/GEMM trailing updates and panel updates of the blocked Cholesky (tf.cholesky call
+// sites, see gpslim_b200.h), the triangular inverse, K^-1 = U U^T, and the conditional /
+// predictive products.
+//
+// Blackwell note: tcgen05.mma has no f64 kind; FP64 tensor work on sm_100a is the warp-level
+// DMMA (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4) with register accumulators, so this is a
+// warp-MMA kernel: 128x128 CTA tile, 8 warps of 64x32, BK=16, 4-stage cp.async pipeline into
+// padded shared memory (row stride 20 doubles -> conflict-free fragment loads).
+//
+// Triangular operands: a_tri / b_tri restrict the K range per output tile so that all-zero
+// 128-wide operand tiles are never loaded or multiplied (this is what makes TRMM-, TRTRI- and
+// LAUUM-shaped products cost their true flop count).  c_uplo = lower computes only tiles that
+// intersect the lower triangle and masks stores above the diagonal.
+#include "internal.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4;
+constexpr int LDS = BK + 4;                       // padded smem row stride (doubles)
+constexpr int STAGE_ELEMS = (BM + BN) * LDS;      // doubles per stage
+constexpr int GEMM_SMEM = STAGES * STAGE_ELEMS * (int)sizeof(double);  // 163840 B
+constexpr int GEMM_THREADS = 256;
+
+struct GemmArgs {
+  const double* A;
+  const double* B;
+  double* C;
+  int64_t lda, ldb, ldc;
+  int M, N, K;
+  double alpha, beta;
+  int a_tri, b_tri, c_uplo;
+  int tiles_m, tiles_n;
+};
+
+__device__ __forceinline__ void tile_coords(const GemmArgs& g, int bid, int& ti, int& tj) {
+  // grouped ordering: GROUP tile-rows are walked column by column so that concurrently
+  // resident CTAs share A row-panels and B row-panels in L2.
+  constexpr int GROUP = 8;
+  int per_group = GROUP * g.tiles_n;
+  int grp = bid / per_group;
+  int first = grp * GROUP;
+  int gsize = min(GROUP, g.tiles_m - first);
+  int rem = bid - grp * per_group;
+  ti = first + rem % gsize;
+  tj = rem / gsize;
+}
+
+__device__ __forceinline__ void k_range(const GemmArgs& g, int ti, int tj, int& klo, int& khi) {
+  klo = 0;
+  khi = g.K;
+  if (g.a_tri == TRI_LOWER) khi = min(khi, (ti + 1) * BM);
+  if (g.a_tri == TRI_UPPER) klo = max(klo, ti * BM);
+  if (g.b_tri == TRI_LOWER) khi = min(khi, (tj + 1) * BN);
+  if (g.b_tri == TRI_UPPER) klo = max(klo, tj * BN);
+}
+
+// VEC16: operands are 16-byte aligned with even leading dimensions -> 16 B cp.async
+template <bool VEC16>
+__device__ __forceinline__ void load_stage(const GemmArgs& g, double* stage, int m0, int n0, int k0,
+                                           int khi, int tid) {
+  double* As = stage;
+  double* Bs = stage + BM * LDS;
+  if (VEC16) {
+    // 128 rows x 8 chunks of 2 doubles per operand; 256 threads x 4 chunks
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int c = tid + i * GEMM_THREADS;
+      int row = c >> 3, kc = (c & 7) * 2;
+      int k = k0 + kc;
+      int kb = (k + 1 < khi) ? 16 : (k < khi ? 8 : 0);
+      {
+        int r = m0 + row;
+        int nb = (r < g.M) ? kb : 0;
+        const double* src = nb ? g.A + (int64_t)r * g.lda + k : g.A;
+        cp_async16(As + row * LDS + kc, src, nb);
+      }
+      {
+        int r = n0 + row;
+        int nb = (r < g.N) ? kb : 0;
+        const double* src = nb ? g.B + (int64_t)r * g.ldb + k : g.B;
+        cp_async16(Bs + row * LDS + kc, src, nb);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int c = tid + i * GEMM_THREADS;
+      int row = c >> 4, kc = c & 15;
+      int k = k0 + kc;
+      int kb = (k < khi) ? 8 : 0;
+      {
+        int r = m0 + row;
+        int nb = (r < g.M) ? kb : 0;
+        const double* src = nb ? g.A + (int64_t)r * g.lda + k : g.A;
+        cp_async8(As + row * LDS + kc, src, nb);
+      }
+      {
+        int r = n0 + row;
+        int nb = (r < g.N) ? kb : 0;
+        const double* src = nb ? g.B + (int64_t)r * g.ldb + k : g.B;
+        cp_async8(Bs + row * LDS + kc, src, nb);
+      }
+    }
+  }
+}
+
+template <bool VEC16>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_dmma_kernel(const GemmArgs g) {
+  extern __shared__ __align__(16) double smem[];
+  int ti, tj;
+  tile_coords(g, blockIdx.x, ti, tj);
+  const int m0 = ti * BM, n0 = tj * BN;
+  if (g.c_uplo == C_LOWER && m0 + BM - 1 < n0) return;  // tile entirely above the diagonal
+
+  int klo, khi;
+  k_range(g, ti, tj, klo, khi);
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps, warp tile 64 x 32
+  const int lr = lane >> 2, lc = lane & 3;
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int nk = (khi > klo) ? (khi - klo + BK - 1) / BK : 0;
+
+  // prologue
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nk) load_stage<VEC16>(g, smem + s * STAGE_ELEMS, m0, n0, klo + s * BK, khi, tid);
+    cp_async_commit();
+  }
+
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      int nxt = kt + STAGES - 1;
+      if (nxt < nk)
+        load_stage<VEC16>(g, smem + (nxt % STAGES) * STAGE_ELEMS, m0, n0, klo + nxt * BK, khi, tid);
+      cp_async_commit();
+    }
+    const double* As = smem + (kt % STAGES) * STAGE_ELEMS + (wm * 64 + lr) * LDS + lc;
+    const double* Bs = smem + (kt % STAGES) * STAGE_ELEMS + BM * LDS + (wn * 32 + lr) * LDS + lc;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+      double a[8], b[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = As[i * 8 * LDS + kk * 4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[j * 8 * LDS + kk * 4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue
+  const bool vec_ok = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+  const bool diag_tile = (g.c_uplo == C_LOWER) && (n0 + BN - 1 > m0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int row = m0 + wm * 64 + i * 8 + lr;
+    if (row >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int col = n0 + wn * 32 + j * 8 + lc * 2;
+      if (col >= g.N) continue;
+      bool ok0 = !diag_tile || col <= row;
+      bool ok1 = (col + 1 < g.N) && (!diag_tile || col + 1 <= row);
+      double* cp = g.C + (int64_t)row * g.ldc + col;
+      double v0 = g.alpha * acc[i][j][0], v1 = g.alpha * acc[i][j][1];
+      if (vec_ok && ok0 && ok1) {
+        if (g.beta != 0.0) {
+          double2 old = *reinterpret_cast<const double2*>(cp);
+          v0 = fma(g.beta, old.x, v0);
+          v1 = fma(g.beta, old.y, v1);
+        }
+        *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
+      } else {
+        if (ok0) cp[0] = (g.beta != 0.0) ? fma(g.beta, cp[0], v0) : v0;
+        if (ok1) cp[1] = (g.beta != 0.0) ? fma(g.beta, cp[1], v1) : v1;
+      }
+    }
+  }
+}
+
+// plain-FMA check kernel with identical semantics (gps_set_option("gemm_impl", 1)); used by
+// the GPU tests to validate the DMMA kernel independently of the oracle.
+__global__ void gemm_nt_naive_kernel(const GemmArgs g) {
+  int col = blockIdx.x * 16 + threadIdx.x;
+  int row = blockIdx.y * 16 + threadIdx.y;
+  if (row >= g.M || col >= g.N) return;
+  if (g.c_uplo == C_LOWER && col > row) return;
+  int klo = 0, khi = g.K;
+  if (g.a_tri == TRI_LOWER) khi = min(khi, row + 1);
+  if (g.a_tri == TRI_UPPER) klo = max(klo, row);
+  if (g.b_tri == TRI_LOWER) khi = min(khi, col + 1);
+  if (g.b_tri == TRI_UPPER) klo = max(klo, col);
+  const double* a = g.A + (int64_t)row * g.lda;
+  const double* b = g.B + (int64_t)col * g.ldb;
+  double s = 0;
+  for (int k = klo; k < khi; ++k) s = fma(a[k], b[k], s);
+  double* cp = g.C + (int64_t)row * g.ldc + col;
+  *cp = (g.beta != 0.0) ? fma(g.beta, *cp, g.alpha * s) : g.alpha * s;
+}
+
+double gemm_flops(const GemmArgs& g) {
+  // algorithmic flops honouring the triangular structure (tile granularity is not counted)
+  double full = 2.0 * (double)g.M * (double)g.N * (double)g.K;
+  double f = full;
+  if (g.c_uplo == C_LOWER && g.M == g.N) f *= 0.5;
+  if (g.a_tri != TRI_NONE && g.b_tri != TRI_NONE)
+    f = (g.c_uplo == C_LOWER) ? full / 6.0 : full / 3.0;
+  else if (g.a_tri != TRI_NONE || g.b_tri != TRI_NONE)
+    f *= 0.5;
+  return f;
+}
+
+}  // namespace
+
+int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, Mat C, int a_tri,
+                       int b_tri, int c_uplo) {
+  if (A.cols != B.cols) return gps_fail(h, -3, "gemm_nt: K mismatch (%lld vs %lld)",
+                                        (long long)A.cols, (long long)B.cols);
+  if (C.rows != A.rows || C.cols != B.rows) return gps_fail(h, -6, "gemm_nt: C shape mismatch");
+  if (C.rows == 0 || C.cols == 0) return 0;
+  if (A.rows > INT32_MAX || B.rows > INT32_MAX || A.cols > INT32_MAX)
+    return gps_fail(h, -3, "gemm_nt: dimension too large");
+  GemmArgs g;
+  g.A = A.p; g.B = B.p; g.C = C.p;
+  g.lda = A.ld; g.ldb = B.ld; g.ldc = C.ld;
+  g.M = (int)A.rows; g.N = (int)B.rows; g.K = (int)A.cols;
+  g.alpha = alpha; g.beta = beta;
+  g.a_tri = a_tri; g.b_tri = b_tri; g.c_uplo = c_uplo;
+  g.tiles_m = (g.M + BM - 1) / BM;
+  g.tiles_n = (g.N + BN - 1) / BN;
+
+  GemmEvent* ev = nullptr;
+  if (h->profile) {
+    if (h->events_used == h->events.size()) {
+      GemmEvent e;
+      if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess)
+        return gps_fail(h, -100, "cudaEventCreate failed");
+      e.flops = 0;
+      h->events.push_back(e);
+    }
+    ev = &h->events[h->events_used++];
+    ev->flops = gemm_flops(g);
+    cudaEventRecord(ev->a, h->stream);
+  }
+
+  if (h->gemm_impl == 1) {
+    dim3 grid((g.N + 15) / 16, (g.M + 15) / 16);
+    gemm_nt_naive_kernel<<<grid, dim3(16, 16), 0, h->stream>>>(g);
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(gemm_nt_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           GEMM_SMEM);
+      cudaFuncSetAttribute(gemm_nt_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           GEMM_SMEM);
+      attr_set = true;
+    }
+    bool vec16 = ((A.ld & 1) == 0) && ((B.ld & 1) == 0) &&
+                 ((reinterpret_cast<uintptr_t>(A.p) & 15) == 0) &&
+                 ((reinterpret_cast<uintptr_t>(B.p) & 15) == 0);
+    unsigned grid = (unsigned)(g.tiles_m * g.tiles_n);
+    if (vec16)
+      gemm_nt_dmma_kernel<true><<<grid, GEMM_THREADS, GEMM_SMEM, h->stream>>>(g);
+    else
+      gemm_nt_dmma_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM, h->stream>>>(g);
+  }
+  if (ev) cudaEventRecord(ev->b, h->stream);
+  GPS_LAUNCH_CHECK(h);
+  return 0;
+}
+
+extern "C" int gps_gemm_nt(gps_handle* h, double alpha, const DLTensor* A, const DLTensor* B,
+                           double beta, DLTensor* C, int a_tri, int b_tri, int c_uplo) {
+  if (!h) return -1;
+  Mat a, b, c;
+  int rc;
+  if ((rc = gps_as_mat(h, A, 3, "A", &a, false))) return rc;
+  if ((rc = gps_as_mat(h, B, 4, "B", &b, false))) return rc;
+  if ((rc = gps_as_mat(h, C, 6, "C", &c, false))) return rc;
+  if (a_tri < 0 || a_tri > 2 || b_tri < 0 || b_tri > 2 || c_uplo < 0 || c_uplo > 1)
+    return gps_fail(h, -7, "gemm_nt: bad tri/uplo flag");
+  GPS_CUDA(h, cudaSetDevice(h->device));
+  return gps_gemm_nt_launch(h, alpha, a, b, beta, c, a_tri, b_tri, c_uplo);
+}

@@ -1,0 +1,823 @@
+// Fused Gram-matrix kernels.
+//
+// Forward: K[i,j] = program(prim_0(x_i,x'_j), ..., prim_{P-1}(x_i,x'_j)) -- the scaled squared
+// distance / dot products, the exp / Matern / periodic bodies and the Sum / Product / Neural-
+// Kernel-Network composition are evaluated per element in registers; neither the distance
+// matrix nor any per-primitive Gram is ever written to memory (the reference materialises
+// k + #layers full N x M temporaries, Periodic even an N x M x D one: kernels.py:806-819,
+// neural_kernel_network.py:41-47).
+//
+// Every primitive is reduced to inner products of per-point FEATURES computed once per call
+// (O(N D) work):
+//   stationary (kernels.py:408-421): f = [x/l (nd), |x/l|^2]; d2 = s_i + s_j - 2 <f_i,f_j>,
+//                                    clipped at 0 exactly like the reference;
+//   linear     (kernels.py:499-505): f = x;  k = sum_d (x_d v_d) x'_d;
+//   periodic   (kernels.py:806-819): f = [cos a, sin a, a], a = 2 pi x / p, using
+//        sum_d sin^2(pi (x_d-x'_d)/p) = (nd - sum_d cos(a_d - a'_d)) / 2   (exact identity),
+//        so the N x M x D sin() evaluations of the reference become N x D.
+//
+// Backward: dtheta[t] = sum_ij W_ij dK_ij/dtheta_t (and optionally the gradient w.r.t. the rows
+// of X), recomputing K tile by tile; W is either a dense matrix or, for the fused GPR
+// objective, formed on the fly as 1/2 (R K^-1 - beta beta^T) from the lower triangle of K^-1.
+// Reductions are deterministic (per-CTA partials + a fixed-order second pass).
+#include <math.h>
+#include <string.h>
+
+#include "internal.cuh"
+
+namespace {
+
+constexpr int TILE = 64;
+constexpr int GRAM_THREADS = 256;
+constexpr int MAX_ACC = 192;     // per-thread gradient accumulators (n_theta + 1)
+constexpr int MAX_FEAT = 160;    // features per point
+constexpr int MAX_R = 16;        // output columns in the fused GPR weight
+
+struct PrimC {
+  int16_t type, ard, ndims, theta_off, feat_off, feat_cnt;
+};
+struct OpC {
+  int16_t op, dst, a, b, c, d, n, pad;
+};
+struct Plan {
+  int n_prims, n_ops, n_theta, out_slot, FT, S;   // S = padded (odd) feature row stride
+  PrimC prims[GPS_MAX_PRIMS];
+  OpC ops[GPS_MAX_OPS];
+};
+struct PlanDims {
+  uint8_t dims[GPS_MAX_PRIMS][GPS_MAX_DIMS];
+};
+
+__host__ __device__ inline bool is_stationary(int t) { return t <= GPS_MATERN52; }
+
+int build_plan(gps_handle* h, const gps_kernel_desc* d, int64_t xcols, Plan* pl, PlanDims* pd) {
+  if (!d) return gps_fail(h, -2, "null kernel descriptor");
+  if (d->n_prims < 1 || d->n_prims > GPS_MAX_PRIMS) return gps_fail(h, -2, "desc: n_prims out of range");
+  if (d->n_ops < 0 || d->n_ops > GPS_MAX_OPS) return gps_fail(h, -2, "desc: n_ops out of range");
+  if (d->n_theta < 1 || d->n_theta + 1 > MAX_ACC) return gps_fail(h, -2, "desc: n_theta out of range (max %d)", MAX_ACC - 1);
+  memset(pl, 0, sizeof(*pl));
+  memset(pd, 0, sizeof(*pd));
+  pl->n_prims = d->n_prims; pl->n_ops = d->n_ops; pl->n_theta = d->n_theta; pl->out_slot = d->out_slot;
+  int ft = 0;
+  for (int p = 0; p < d->n_prims; ++p) {
+    const gps_prim& q = d->prims[p];
+    if (q.type < GPS_RBF || q.type > GPS_PERIODIC) return gps_fail(h, -2, "desc: primitive %d has unknown type %d", p, q.type);
+    if (q.ndims < 1 || q.ndims > GPS_MAX_DIMS) return gps_fail(h, -2, "desc: primitive %d ndims out of range", p);
+    int np = is_stationary(q.type) ? 1 + (q.ard ? q.ndims : 1)
+             : q.type == GPS_LINEAR ? (q.ard ? q.ndims : 1) : 3;
+    if (q.theta_off < 0 || q.theta_off + np > d->n_theta) return gps_fail(h, -2, "desc: primitive %d theta range", p);
+    for (int k = 0; k < q.ndims; ++k) {
+      if (q.dims[k] < 0 || q.dims[k] >= xcols || q.dims[k] > 255)
+        return gps_fail(h, -2, "desc: primitive %d uses column %d but X has %lld columns", p, q.dims[k], (long long)xcols);
+      pd->dims[p][k] = (uint8_t)q.dims[k];
+    }
+    PrimC& c = pl->prims[p];
+    c.type = (int16_t)q.type; c.ard = (int16_t)(q.ard ? 1 : 0); c.ndims = (int16_t)q.ndims;
+    c.theta_off = (int16_t)q.theta_off; c.feat_off = (int16_t)ft;
+    c.feat_cnt = (int16_t)(is_stationary(q.type) ? q.ndims + 1 : q.type == GPS_LINEAR ? q.ndims : 3 * q.ndims);
+    ft += c.feat_cnt;
+  }
+  if (ft > MAX_FEAT) return gps_fail(h, -2, "desc: %d features per point exceed the limit %d", ft, MAX_FEAT);
+  pl->FT = ft;
+  pl->S = ft | 1;
+  int nslots = d->n_prims;
+  for (int i = 0; i < d->n_ops; ++i) {
+    const gps_op& o = d->ops[i];
+    OpC& c = pl->ops[i];
+    c.op = (int16_t)o.op; c.dst = (int16_t)o.dst; c.a = (int16_t)o.a; c.b = (int16_t)o.b;
+    c.c = (int16_t)o.c; c.d = (int16_t)o.d; c.n = (int16_t)o.n; c.pad = 0;
+    int nout = 1;
+    bool ok = o.dst >= 0;
+    switch (o.op) {
+      case GPS_OP_CONST: ok = ok && o.a >= 0 && o.a < d->n_theta; break;
+      case GPS_OP_ADD: case GPS_OP_MUL: ok = ok && o.a >= 0 && o.a < nslots && o.b >= 0 && o.b < nslots; break;
+      case GPS_OP_COPY: ok = ok && o.a >= 0 && o.a < nslots; break;
+      case GPS_OP_LINEAR:
+        nout = o.n;
+        ok = ok && o.b >= 1 && o.n >= 1 && o.a >= 0 && o.a + o.b <= nslots && o.c >= 0 &&
+             o.c + o.n * o.b <= d->n_theta && o.d >= 0 && o.d + o.n <= d->n_theta;
+        break;
+      case GPS_OP_PRODUCT:
+        nout = o.n;
+        ok = ok && o.b >= 1 && o.n >= 1 && o.a >= 0 && o.a + o.b * o.n <= nslots;
+        break;
+      default: ok = false;
+    }
+    // ops append slots in order: dst must be the next free slot
+    if (!ok || o.dst != nslots || o.dst + nout > GPS_MAX_SLOTS)
+      return gps_fail(h, -2, "desc: op %d is malformed (op=%d dst=%d, next free slot %d)", i, o.op, o.dst, nslots);
+    nslots += nout;
+  }
+  if (d->out_slot < 0 || d->out_slot >= nslots) return gps_fail(h, -2, "desc: out_slot out of range");
+  return 0;
+}
+
+// --------------------------------------------------------------------------- features
+__global__ void feature_kernel(const Plan pl, const PlanDims pd, const double* __restrict__ theta,
+                               const double* __restrict__ X, int64_t ldx, int64_t N,
+                               double* __restrict__ F) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const double* x = X + i * ldx;
+  double* f = F + i * pl.FT;
+  for (int p = 0; p < pl.n_prims; ++p) {
+    const PrimC P = pl.prims[p];
+    double* fp = f + P.feat_off;
+    const double* th = theta + P.theta_off;
+    if (is_stationary(P.type)) {
+      double s = 0.0;
+      for (int k = 0; k < P.ndims; ++k) {
+        double v = x[pd.dims[p][k]] / th[1 + (P.ard ? k : 0)];   // X / lengthscales (kernels.py:409)
+        fp[k] = v;
+        s += v * v;                                              // reduce_sum(square(X)) (:410)
+      }
+      fp[P.ndims] = s;
+    } else if (P.type == GPS_LINEAR) {
+      for (int k = 0; k < P.ndims; ++k) fp[k] = x[pd.dims[p][k]];
+    } else {
+      const double per = th[2];
+      for (int k = 0; k < P.ndims; ++k) {
+        double a = 2.0 * M_PI * x[pd.dims[p][k]] / per;
+        double sn, cs;
+        sincos(a, &sn, &cs);
+        fp[k] = cs;
+        fp[P.ndims + k] = sn;
+        fp[2 * P.ndims + k] = a;
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------- primitive bodies
+struct PrimEval {
+  double k;     // value
+  double dk;    // stationary: dk/d(d2) (0 where clipped); periodic: r = sum sin^2/l^2
+  double d2;    // stationary: unclipped-side squared distance (after clip)
+};
+
+__device__ __forceinline__ PrimEval prim_eval(const PrimC& P, const double* __restrict__ th,
+                                              const double* __restrict__ fi,
+                                              const double* __restrict__ fj) {
+  PrimEval e;
+  e.k = 0; e.dk = 0; e.d2 = 0;
+  const double* t = th + P.theta_off;
+  if (is_stationary(P.type)) {
+    double dot = 0.0;
+    for (int k = 0; k < P.ndims; ++k) dot = fma(fi[k], fj[k], dot);
+    double raw = -2.0 * dot + (fi[P.ndims] + fj[P.ndims]);      // kernels.py:413-414 / 419-420
+    bool live = raw >= 0.0;                                      // clip_by_value(dist, 0, inf)
+    double d2 = live ? raw : 0.0;
+    const double var = t[0];
+    e.d2 = d2;
+    if (P.type == GPS_RBF) {
+      double ex = exp(-0.5 * d2);
+      e.k = var * ex;
+      e.dk = live ? -0.5 * var * ex : 0.0;
+    } else {
+      double r = sqrt(d2 + 1e-12);                               // kernels.py:424-426
+      double drd2 = live ? 0.5 / r : 0.0;
+      if (P.type == GPS_EXPONENTIAL) {
+        double ex = exp(-0.5 * r);
+        e.k = var * ex;
+        e.dk = -0.5 * var * ex * drd2;
+      } else if (P.type == GPS_MATERN12) {
+        double ex = exp(-r);
+        e.k = var * ex;
+        e.dk = -var * ex * drd2;
+      } else if (P.type == GPS_MATERN32) {
+        const double s3 = 1.7320508075688772;
+        double ex = exp(-s3 * r);
+        e.k = var * (1.0 + s3 * r) * ex;
+        e.dk = var * (-3.0 * r) * ex * drd2;                     // d/dr[(1+s3 r)e^{-s3 r}] = -3 r e^{-s3 r}
+      } else {
+        const double s5 = 2.23606797749979;
+        double ex = exp(-s5 * r);
+        e.k = var * (1.0 + s5 * r + (5.0 / 3.0) * r * r) * ex;
+        e.dk = var * (-(5.0 / 3.0) * r * (1.0 + s5 * r)) * ex * drd2;
+      }
+    }
+  } else if (P.type == GPS_LINEAR) {
+    double dot = 0.0;
+    for (int k = 0; k < P.ndims; ++k) dot = fma(fi[k] * t[P.ard ? k : 0], fj[k], dot);
+    e.k = dot;
+  } else {
+    const int nd = P.ndims;
+    double cs = 0.0;
+    for (int k = 0; k < nd; ++k) cs += fi[k] * fj[k] + fi[nd + k] * fj[nd + k];
+    double ls = t[1];
+    double r = 0.5 * ((double)nd - cs) / (ls * ls);
+    e.k = t[0] * exp(-0.5 * r);
+    e.dk = r;
+  }
+  return e;
+}
+
+__device__ __forceinline__ void program_fwd(const Plan& pl, const double* __restrict__ th, double* v) {
+  for (int q = 0; q < pl.n_ops; ++q) {
+    const OpC o = pl.ops[q];
+    switch (o.op) {
+      case GPS_OP_CONST: v[o.dst] = th[o.a]; break;
+      case GPS_OP_ADD: v[o.dst] = v[o.a] + v[o.b]; break;
+      case GPS_OP_MUL: v[o.dst] = v[o.a] * v[o.b]; break;
+      case GPS_OP_COPY: v[o.dst] = v[o.a]; break;
+      case GPS_OP_LINEAR:
+        for (int r = 0; r < o.n; ++r) {
+          double s = 0.0;
+          for (int c = 0; c < o.b; ++c) s = fma(v[o.a + c], th[o.c + r * o.b + c], s);
+          v[o.dst + r] = s + th[o.d + r];
+        }
+        break;
+      case GPS_OP_PRODUCT:
+        for (int g = 0; g < o.n; ++g) {
+          double s = v[o.a + g * o.b];
+          for (int c = 1; c < o.b; ++c) s *= v[o.a + g * o.b + c];
+          v[o.dst + g] = s;
+        }
+        break;
+    }
+  }
+}
+
+// reverse sweep; vb = adjoints of the slots, acc = gradient accumulators over theta
+__device__ __forceinline__ void program_bwd(const Plan& pl, const double* __restrict__ th,
+                                            const double* v, double* vb, double* acc) {
+  for (int q = pl.n_ops - 1; q >= 0; --q) {
+    const OpC o = pl.ops[q];
+    switch (o.op) {
+      case GPS_OP_CONST: acc[o.a] += vb[o.dst]; break;
+      case GPS_OP_ADD: vb[o.a] += vb[o.dst]; vb[o.b] += vb[o.dst]; break;
+      case GPS_OP_MUL: {
+        double g = vb[o.dst];
+        double va = v[o.a], vbv = v[o.b];
+        vb[o.a] += g * vbv;
+        vb[o.b] += g * va;
+      } break;
+      case GPS_OP_COPY: vb[o.a] += vb[o.dst]; break;
+      case GPS_OP_LINEAR:
+        for (int r = 0; r < o.n; ++r) {
+          double g = vb[o.dst + r];
+          acc[o.d + r] += g;
+          for (int c = 0; c < o.b; ++c) {
+            acc[o.c + r * o.b + c] = fma(g, v[o.a + c], acc[o.c + r * o.b + c]);
+            vb[o.a + c] = fma(g, th[o.c + r * o.b + c], vb[o.a + c]);
+          }
+        }
+        break;
+      case GPS_OP_PRODUCT:
+        for (int g = 0; g < o.n; ++g) {
+          double gg = vb[o.dst + g];
+          for (int c = 0; c < o.b; ++c) {
+            double s = gg;
+            for (int c2 = 0; c2 < o.b; ++c2)
+              if (c2 != c) s *= v[o.a + g * o.b + c2];
+            vb[o.a + g * o.b + c] += s;
+          }
+        }
+        break;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------- forward
+__global__ void __launch_bounds__(GRAM_THREADS)
+gram_fwd_kernel(const Plan pl, const double* __restrict__ theta, const double* __restrict__ FL,
+                const double* __restrict__ FR, int64_t N, int64_t M, double diag_add, int sym,
+                int uplo, double* __restrict__ K, int64_t ldk) {
+  extern __shared__ double sm[];
+  double* th = sm;
+  double* sl = th + pl.n_theta;
+  double* sr = sl + TILE * pl.S;
+  const int64_t i0 = (int64_t)blockIdx.y * TILE, j0 = (int64_t)blockIdx.x * TILE;
+  if (sym && uplo && j0 > i0 + TILE - 1) return;
+  const int tid = threadIdx.x;
+  for (int t = tid; t < pl.n_theta; t += GRAM_THREADS) th[t] = theta[t];
+  for (int idx = tid; idx < TILE * pl.FT; idx += GRAM_THREADS) {
+    int r = idx / pl.FT, c = idx - r * pl.FT;
+    sl[r * pl.S + c] = (i0 + r < N) ? FL[(i0 + r) * pl.FT + c] : 0.0;
+    sr[r * pl.S + c] = (j0 + r < M) ? FR[(j0 + r) * pl.FT + c] : 0.0;
+  }
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  double v[GPS_MAX_SLOTS];
+  for (int a = 0; a < 4; ++a) {
+    const int il = ty + 16 * a;
+    const int64_t gi = i0 + il;
+    if (gi >= N) continue;
+    for (int b = 0; b < 4; ++b) {
+      const int jl = tx + 16 * b;
+      const int64_t gj = j0 + jl;
+      if (gj >= M) continue;
+      if (sym && uplo && gj > gi) continue;
+      for (int p = 0; p < pl.n_prims; ++p) {
+        const PrimC P = pl.prims[p];
+        v[p] = prim_eval(P, th, sl + il * pl.S + P.feat_off, sr + jl * pl.S + P.feat_off).k;
+      }
+      program_fwd(pl, th, v);
+      double out = v[pl.out_slot];
+      if (sym && gi == gj) out += diag_add;
+      K[gi * ldk + gj] = out;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------- backward
+struct BwdArgs {
+  int mode;               // W_DENSE / W_GPR
+  const double* W;        // dense weights or K^-1 (lower)
+  int64_t ldw;
+  const double* beta;     // [R][N]
+  int R;
+  int sym_lower;          // iterate lower tiles only, off-diagonal elements weigh double
+  int want_dx;
+  int xcols;
+  double dx_scale;        // 2 for the symmetric problem (row + column role of X)
+  int njc;                // column chunks
+};
+
+__global__ void __launch_bounds__(GRAM_THREADS)
+gram_bwd_kernel(const Plan pl, const PlanDims pd, const double* __restrict__ theta,
+                const double* __restrict__ FL, const double* __restrict__ FR, int64_t N, int64_t M,
+                const BwdArgs w, double* __restrict__ part_theta, double* __restrict__ part_dx) {
+  extern __shared__ double sm[];
+  const int nacc = pl.n_theta + 1;
+  double* th = sm;                                 // [n_theta]
+  double* sl = th + pl.n_theta;                    // [TILE][S]
+  double* sr = sl + TILE * pl.S;                   // [TILE][S]
+  double* bi = sr + TILE * pl.S;                   // [MAX_R][TILE]   beta rows (i side)
+  double* bj = bi + (w.mode == W_GPR ? w.R * TILE : 0);
+  double* red = bj + (w.mode == W_GPR ? w.R * TILE : 0);   // [8][nacc]
+  double* dxs = red + 8 * nacc;                    // [TILE][xcols]
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t i0 = (int64_t)blockIdx.y * TILE;
+  const int64_t jtiles = (M + TILE - 1) / TILE;
+
+  double acc[MAX_ACC];
+  for (int t = 0; t < nacc; ++t) acc[t] = 0.0;
+  for (int t = tid; t < pl.n_theta; t += GRAM_THREADS) th[t] = theta[t];
+  for (int idx = tid; idx < TILE * pl.FT; idx += GRAM_THREADS) {
+    int r = idx / pl.FT, c = idx - r * pl.FT;
+    sl[r * pl.S + c] = (i0 + r < N) ? FL[(i0 + r) * pl.FT + c] : 0.0;
+  }
+  if (w.mode == W_GPR)
+    for (int idx = tid; idx < w.R * TILE; idx += GRAM_THREADS) {
+      int r = idx / TILE, c = idx - r * TILE;
+      bi[idx] = (i0 + c < N) ? w.beta[(int64_t)r * N + i0 + c] : 0.0;
+    }
+  if (w.want_dx)
+    for (int idx = tid; idx < TILE * w.xcols; idx += GRAM_THREADS) dxs[idx] = 0.0;
+
+  double v[GPS_MAX_SLOTS], vb[GPS_MAX_SLOTS];
+  double dxr[GPS_MAX_DIMS];
+
+  for (int64_t jt = blockIdx.x; jt < jtiles; jt += w.njc) {
+    const int64_t j0 = jt * TILE;
+    if (w.sym_lower && j0 > i0 + TILE - 1) break;
+    __syncthreads();   // previous tile fully consumed
+    for (int idx = tid; idx < TILE * pl.FT; idx += GRAM_THREADS) {
+      int r = idx / pl.FT, c = idx - r * pl.FT;
+      sr[r * pl.S + c] = (j0 + r < M) ? FR[(j0 + r) * pl.FT + c] : 0.0;
+    }
+    if (w.mode == W_GPR)
+      for (int idx = tid; idx < w.R * TILE; idx += GRAM_THREADS) {
+        int r = idx / TILE, c = idx - r * TILE;
+        bj[idx] = (j0 + c < M) ? w.beta[(int64_t)r * N + j0 + c] : 0.0;
+      }
+    __syncthreads();
+    for (int a = 0; a < 4; ++a) {
+      const int il = ty + 16 * a;
+      const int64_t gi = i0 + il;
+      const bool rowok = gi < N;
+      if (w.want_dx)
+        for (int d = 0; d < w.xcols; ++d) dxr[d] = 0.0;
+      for (int b = 0; b < 4; ++b) {
+        const int jl = tx + 16 * b;
+        const int64_t gj = j0 + jl;
+        if (!rowok || gj >= M) continue;
+        if (w.sym_lower && gj > gi) continue;
+        double wij;
+        if (w.mode == W_GPR) {
+          double bb = 0.0;
+          for (int r = 0; r < w.R; ++r) bb = fma(bi[r * TILE + il], bj[r * TILE + jl], bb);
+          wij = 0.5 * ((double)w.R * w.W[gi * w.ldw + gj] - bb);
+          if (gi == gj) acc[pl.n_theta] += wij;          // tr W = d nlml / d noise
+        } else {
+          wij = w.W[gi * w.ldw + gj];
+        }
+        if (w.sym_lower && gj != gi) wij *= 2.0;
+        const double* fi = sl + il * pl.S;
+        const double* fj = sr + jl * pl.S;
+        PrimEval ev[GPS_MAX_PRIMS];
+        for (int p = 0; p < pl.n_prims; ++p) {
+          const PrimC P = pl.prims[p];
+          ev[p] = prim_eval(P, th, fi + P.feat_off, fj + P.feat_off);
+          v[p] = ev[p].k;
+        }
+        int nslots_used = pl.n_prims;
+        if (pl.n_ops) {
+          program_fwd(pl, th, v);
+          const OpC last = pl.ops[pl.n_ops - 1];
+          nslots_used = last.dst + ((last.op == GPS_OP_LINEAR || last.op == GPS_OP_PRODUCT) ? last.n : 1);
+        }
+        for (int s = 0; s < nslots_used; ++s) vb[s] = 0.0;
+        vb[pl.out_slot] = wij;
+        program_bwd(pl, th, v, vb, acc);
+        for (int p = 0; p < pl.n_prims; ++p) {
+          const PrimC P = pl.prims[p];
+          const double g = vb[p];
+          const double* t = th + P.theta_off;
+          const double* fip = fi + P.feat_off;
+          const double* fjp = fj + P.feat_off;
+          if (is_stationary(P.type)) {
+            acc[P.theta_off] += g * ev[p].k / t[0];
+            const double G = g * ev[p].dk;               // dObj / d(d2)
+            if (P.ard) {
+              for (int k = 0; k < P.ndims; ++k) {
+                double df = fip[k] - fjp[k];
+                acc[P.theta_off + 1 + k] += G * (-2.0) * df * df / t[1 + k];
+                if (w.want_dx) dxr[pd.dims[p][k]] += 2.0 * G * df / t[1 + k];
+              }
+            } else {
+              acc[P.theta_off + 1] += G * (-2.0) * ev[p].d2 / t[1];
+              if (w.want_dx)
+                for (int k = 0; k < P.ndims; ++k)
+                  dxr[pd.dims[p][k]] += 2.0 * G * (fip[k] - fjp[k]) / t[1];
+            }
+          } else if (P.type == GPS_LINEAR) {
+            for (int k = 0; k < P.ndims; ++k) {
+              acc[P.theta_off + (P.ard ? k : 0)] += g * fip[k] * fjp[k];
+              if (w.want_dx) dxr[pd.dims[p][k]] += g * t[P.ard ? k : 0] * fjp[k];
+            }
+          } else {
+            const int nd = P.ndims;
+            const double kk = ev[p].k, r = ev[p].dk, ls = t[1], per = t[2];
+            acc[P.theta_off] += g * kk / t[0];
+            acc[P.theta_off + 1] += g * kk * r / ls;
+            double dcs = 0.0;   // d(sum cos)/dp
+            for (int k = 0; k < nd; ++k) {
+              double sind = fip[nd + k] * fjp[k] - fip[k] * fjp[nd + k];   // sin(a_i - a_j)
+              dcs += sind * (fip[2 * nd + k] - fjp[2 * nd + k]) / per;
+              if (w.want_dx) dxr[pd.dims[p][k]] += -g * kk * sind * M_PI / (2.0 * per * ls * ls);
+            }
+            acc[P.theta_off + 2] += g * kk * dcs / (4.0 * ls * ls);
+          }
+        }
+      }
+      if (w.want_dx) {
+        // the 16 tx-lanes of a half warp share row il
+        for (int d = 0; d < w.xcols; ++d) {
+          double s = dxr[d];
+          s += __shfl_xor_sync(0xffffffffu, s, 8);
+          s += __shfl_xor_sync(0xffffffffu, s, 4);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          if (tx == 0) dxs[il * w.xcols + d] += s;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // deterministic CTA reduction of the theta accumulators
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int t = 0; t < nacc; ++t) {
+    double s = warp_sum(acc[t]);
+    if (lane == 0) red[warp * nacc + t] = s;
+  }
+  __syncthreads();
+  const int64_t cta = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+  for (int t = tid; t < nacc; t += GRAM_THREADS) {
+    double s = 0.0;
+    for (int wq = 0; wq < GRAM_THREADS / 32; ++wq) s += red[wq * nacc + t];
+    part_theta[cta * nacc + t] = s;
+  }
+  if (w.want_dx) {
+    for (int idx = tid; idx < TILE * w.xcols; idx += GRAM_THREADS) {
+      int r = idx / w.xcols;
+      if (i0 + r < N)
+        part_dx[((int64_t)blockIdx.x * N + i0 + r) * w.xcols + (idx - r * w.xcols)] = dxs[idx];
+    }
+  }
+}
+
+// out[t] = sum_c part[c][t] (fixed order)
+__global__ void reduce_cols_kernel(const double* __restrict__ part, int64_t nrows, int64_t ncols,
+                                   double scale, double* __restrict__ out, int64_t out_stride_skip,
+                                   int accumulate) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncols) return;
+  double s = 0.0;
+  for (int64_t c = 0; c < nrows; ++c) s += part[c * ncols + t];
+  (void)out_stride_skip;
+  out[t] = (accumulate ? out[t] : 0.0) + scale * s;
+}
+
+// dX[i][d] = scale * sum_jc part[jc][i][d]
+__global__ void reduce_dx_kernel(const double* __restrict__ part, int njc, int64_t N, int xcols,
+                                 double scale, double* __restrict__ dX, int64_t lddx) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * xcols) return;
+  double s = 0.0;
+  for (int c = 0; c < njc; ++c) s += part[(int64_t)c * N * xcols + idx];
+  int64_t i = idx / xcols;
+  dX[i * lddx + (idx - i * xcols)] = scale * s;
+}
+
+// --------------------------------------------------------------------------- Kdiag
+__global__ void kdiag_kernel(const Plan pl, const PlanDims pd, const double* __restrict__ theta,
+                             const double* __restrict__ X, int64_t ldx, int64_t N,
+                             double* __restrict__ out, const double* __restrict__ wvec,
+                             double* __restrict__ part_theta, double* __restrict__ dX, int64_t lddx,
+                             int xcols) {
+  // forward (wvec == nullptr): out[i] = Kdiag(x_i).  backward: accumulates sum_i w_i dKdiag_i/dtheta
+  // into per-thread partials and writes dX rows.
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool bwd = wvec != nullptr;
+  double acc[MAX_ACC];
+  const int nacc = pl.n_theta;
+  if (bwd)
+    for (int t = 0; t < nacc; ++t) acc[t] = 0.0;
+  if (i < N) {
+    const double* x = X + i * ldx;
+    double v[GPS_MAX_SLOTS], vb[GPS_MAX_SLOTS];
+    for (int p = 0; p < pl.n_prims; ++p) {
+      const PrimC P = pl.prims[p];
+      const double* t = theta + P.theta_off;
+      if (P.type == GPS_LINEAR) {                    // kernels.py:507-510
+        double s = 0.0;
+        for (int k = 0; k < P.ndims; ++k) {
+          double xv = x[pd.dims[p][k]];
+          s += xv * xv * t[P.ard ? k : 0];
+        }
+        v[p] = s;
+      } else {
+        v[p] = t[0];                                 // kernels.py:428-429, :803-804
+      }
+    }
+    program_fwd(pl, theta, v);
+    if (!bwd) {
+      out[i] = v[pl.out_slot];
+    } else {
+      int nslots_used = pl.n_prims;
+      if (pl.n_ops) {
+        const OpC last = pl.ops[pl.n_ops - 1];
+        nslots_used = last.dst + ((last.op == GPS_OP_LINEAR || last.op == GPS_OP_PRODUCT) ? last.n : 1);
+      }
+      for (int s = 0; s < nslots_used; ++s) vb[s] = 0.0;
+      vb[pl.out_slot] = wvec[i];
+      program_bwd(pl, theta, v, vb, acc);
+      if (dX)
+        for (int d = 0; d < xcols; ++d) dX[i * lddx + d] = 0.0;
+      for (int p = 0; p < pl.n_prims; ++p) {
+        const PrimC P = pl.prims[p];
+        const double* t = theta + P.theta_off;
+        if (P.type == GPS_LINEAR) {
+          for (int k = 0; k < P.ndims; ++k) {
+            double xv = x[pd.dims[p][k]];
+            acc[P.theta_off + (P.ard ? k : 0)] += vb[p] * xv * xv;
+            if (dX) dX[i * lddx + pd.dims[p][k]] += vb[p] * 2.0 * xv * t[P.ard ? k : 0];
+          }
+        } else {
+          acc[P.theta_off] += vb[p];
+        }
+      }
+    }
+  }
+  if (bwd) {
+    __shared__ double red[GRAM_THREADS / 32][MAX_ACC];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int t = 0; t < nacc; ++t) {
+      double s = warp_sum(acc[t]);
+      if (lane == 0) red[warp][t] = s;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nacc; t += blockDim.x) {
+      double s = 0.0;
+      for (int wq = 0; wq < GRAM_THREADS / 32; ++wq) s += red[wq][t];
+      part_theta[(int64_t)blockIdx.x * nacc + t] = s;
+    }
+  }
+}
+
+int features(gps_handle* h, const Plan& pl, const PlanDims& pd, const double* theta, Mat X, int slot,
+             double** out) {
+  double* F = (double*)gps_ws(h, slot, (size_t)X.rows * pl.FT * sizeof(double));
+  if (!F) return -102;
+  if (X.rows > 0) {
+    feature_kernel<<<(unsigned)((X.rows + 127) / 128), 128, 0, h->stream>>>(pl, pd, theta, X.p, X.ld,
+                                                                           X.rows, F);
+    GPS_LAUNCH_CHECK(h);
+  }
+  *out = F;
+  return 0;
+}
+
+bool g_gram_attr = false;
+void gram_attrs() {
+  if (g_gram_attr) return;
+  cudaFuncSetAttribute(gram_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(gram_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  g_gram_attr = true;
+}
+
+}  // namespace
+
+int gps_gram_fwd_mat(gps_handle* h, const gps_kernel_desc* desc, const double* theta, Mat X,
+                     const Mat* X2, double diag_add, int uplo, Mat K) {
+  Plan pl;
+  PlanDims pd;
+  int rc;
+  if ((rc = build_plan(h, desc, X.cols, &pl, &pd))) return rc;
+  if (X2 && X2->cols != X.cols) return gps_fail(h, -5, "gram: X2 has %lld columns, X has %lld", (long long)X2->cols, (long long)X.cols);
+  const int64_t N = X.rows, M = X2 ? X2->rows : X.rows;
+  if (K.rows != N || K.cols != M) return gps_fail(h, -8, "gram: K_out must be %lld x %lld", (long long)N, (long long)M);
+  if (N == 0 || M == 0) return 0;
+  double *FL, *FR;
+  if ((rc = features(h, pl, pd, theta, X, WS_FEAT_L, &FL))) return rc;
+  FR = FL;
+  if (X2 && (rc = features(h, pl, pd, theta, *X2, WS_FEAT_R, &FR))) return rc;
+  gram_attrs();
+  size_t smem = (size_t)(pl.n_theta + 2 * TILE * pl.S) * sizeof(double);
+  dim3 grid((unsigned)((M + TILE - 1) / TILE), (unsigned)((N + TILE - 1) / TILE));
+  if (grid.y > 65535) return gps_fail(h, -4, "gram: too many rows");
+  gram_fwd_kernel<<<grid, GRAM_THREADS, smem, h->stream>>>(pl, theta, FL, FR, N, M, diag_add,
+                                                           X2 ? 0 : 1, X2 ? 0 : uplo, K.p, K.ld);
+  GPS_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int gps_gram_bwd_mat(gps_handle* h, const gps_kernel_desc* desc, const double* theta, Mat X,
+                     const Mat* X2, GramW w, double* dtheta_out, Mat* dX, double* trace_out) {
+  Plan pl;
+  PlanDims pd;
+  int rc;
+  if ((rc = build_plan(h, desc, X.cols, &pl, &pd))) return rc;
+  const int64_t N = X.rows, M = X2 ? X2->rows : X.rows;
+  if (X2 && X2->cols != X.cols) return gps_fail(h, -5, "gram_bwd: X2 column mismatch");
+  if (w.W.rows != N || w.W.cols != M) return gps_fail(h, -6, "gram_bwd: W must be %lld x %lld", (long long)N, (long long)M);
+  if (w.mode == W_GPR && (w.R < 1 || w.R > MAX_R)) return gps_fail(h, -6, "gram_bwd: R out of range (max %d)", MAX_R);
+  if (dX && w.sym_lower) return gps_fail(h, -8, "gram_bwd: dX needs the full weight matrix");
+  if (dX && (dX->rows != N || dX->cols != X.cols)) return gps_fail(h, -8, "gram_bwd: dX shape mismatch");
+  if (X.cols > GPS_MAX_DIMS && dX) return gps_fail(h, -4, "gram_bwd: dX supports at most %d columns", GPS_MAX_DIMS);
+  const int nacc = pl.n_theta + 1;
+  if (N == 0 || M == 0) {
+    GPS_CUDA(h, cudaMemsetAsync(dtheta_out, 0, pl.n_theta * sizeof(double), h->stream));
+    if (trace_out) GPS_CUDA(h, cudaMemsetAsync(trace_out, 0, sizeof(double), h->stream));
+    return 0;
+  }
+  double *FL, *FR;
+  if ((rc = features(h, pl, pd, theta, X, WS_FEAT_L, &FL))) return rc;
+  FR = FL;
+  if (X2 && (rc = features(h, pl, pd, theta, *X2, WS_FEAT_R, &FR))) return rc;
+  gram_attrs();
+  const int64_t itiles = (N + TILE - 1) / TILE, jtiles = (M + TILE - 1) / TILE;
+  int64_t njc = (4 * h->sm_count + itiles - 1) / itiles;
+  if (njc < 1) njc = 1;
+  if (njc > jtiles) njc = jtiles;
+  if (itiles > 65535) return gps_fail(h, -4, "gram_bwd: too many rows");
+  BwdArgs a;
+  a.mode = w.mode; a.W = w.W.p; a.ldw = w.W.ld; a.beta = w.beta; a.R = w.R;
+  a.sym_lower = w.sym_lower; a.want_dx = dX ? 1 : 0; a.xcols = (int)X.cols;
+  a.dx_scale = X2 ? 1.0 : 2.0; a.njc = (int)njc;
+  const int64_t nctas = itiles * njc;
+  double* part = (double*)gps_ws(h, WS_PARTIAL, (size_t)nctas * nacc * sizeof(double));
+  if (!part) return -102;
+  double* pdx = nullptr;
+  if (dX) {
+    pdx = (double*)gps_ws(h, WS_PARTIAL2, (size_t)njc * N * X.cols * sizeof(double));
+    if (!pdx) return -102;
+  }
+  size_t smem = (size_t)(pl.n_theta + 2 * TILE * pl.S + (w.mode == W_GPR ? 2 * w.R * TILE : 0) +
+                         8 * nacc + (dX ? TILE * X.cols : 0)) * sizeof(double);
+  if (smem > 220 * 1024) return gps_fail(h, -2, "gram_bwd: kernel too large for shared memory");
+  gram_bwd_kernel<<<dim3((unsigned)njc, (unsigned)itiles), GRAM_THREADS, smem, h->stream>>>(
+      pl, pd, theta, FL, FR, N, M, a, part, pdx);
+  GPS_LAUNCH_CHECK(h);
+  // theta gradient
+  reduce_cols_kernel<<<(nacc + 127) / 128, 128, 0, h->stream>>>(part, nctas, nacc, 1.0, part, 0, 0);
+  GPS_LAUNCH_CHECK(h);
+  // (the reduction wrote row 0 of `part` in place: column t only reads rows of column t)
+  GPS_CUDA(h, cudaMemcpyAsync(dtheta_out, part, pl.n_theta * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if (trace_out)
+    GPS_CUDA(h, cudaMemcpyAsync(trace_out, part + pl.n_theta, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if (dX) {
+    int64_t tot = N * X.cols;
+    reduce_dx_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(pdx, (int)njc, N, (int)X.cols,
+                                                                          a.dx_scale, dX->p, dX->ld);
+    GPS_LAUNCH_CHECK(h);
+  }
+  return 0;
+}
+
+int gps_kdiag_fwd_vec(gps_handle* h, const gps_kernel_desc* desc, const double* theta, Mat X,
+                      double* out) {
+  Plan pl;
+  PlanDims pd;
+  int rc;
+  if ((rc = build_plan(h, desc, X.cols, &pl, &pd))) return rc;
+  if (X.rows == 0) return 0;
+  kdiag_kernel<<<(unsigned)((X.rows + GRAM_THREADS - 1) / GRAM_THREADS), GRAM_THREADS, 0, h->stream>>>(
+      pl, pd, theta, X.p, X.ld, X.rows, out, nullptr, nullptr, nullptr, 0, (int)X.cols);
+  GPS_LAUNCH_CHECK(h);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------- C ABI
+namespace {
+int theta_ptr(gps_handle* h, const gps_kernel_desc* desc, const DLTensor* theta, int argidx,
+              const double** out) {
+  Mat t;
+  int rc;
+  if ((rc = gps_as_mat(h, theta, argidx, "theta", &t))) return rc;
+  if (!desc) return gps_fail(h, -2, "null kernel descriptor");
+  if (t.rows * t.cols < desc->n_theta)
+    return gps_fail(h, -argidx, "theta has %lld entries, descriptor needs %d", (long long)(t.rows * t.cols), desc->n_theta);
+  *out = t.p;
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int gps_gram_fwd(gps_handle* h, const gps_kernel_desc* desc, const DLTensor* theta, const DLTensor* X,
+                 const DLTensor* X2, double diag_add, int uplo, DLTensor* K_out) {
+  if (!h) return -1;
+  const double* th;
+  Mat x, x2, k;
+  int rc;
+  if ((rc = theta_ptr(h, desc, theta, 3, &th))) return rc;
+  if ((rc = gps_as_mat(h, X, 4, "X", &x, false))) return rc;
+  if (X2 && (rc = gps_as_mat(h, X2, 5, "X2", &x2, false))) return rc;
+  if ((rc = gps_as_mat(h, K_out, 8, "K_out", &k, false))) return rc;
+  GPS_CUDA(h, cudaSetDevice(h->device));
+  return gps_gram_fwd_mat(h, desc, th, x, X2 ? &x2 : nullptr, diag_add, uplo, k);
+}
+
+int gps_gram_bwd(gps_handle* h, const gps_kernel_desc* desc, const DLTensor* theta, const DLTensor* X,
+                 const DLTensor* X2, const DLTensor* W, DLTensor* dtheta_out, DLTensor* dX_out) {
+  if (!h) return -1;
+  const double* th;
+  Mat x, x2, w, dth, dx;
+  int rc;
+  if ((rc = theta_ptr(h, desc, theta, 3, &th))) return rc;
+  if ((rc = gps_as_mat(h, X, 4, "X", &x, false))) return rc;
+  if (X2 && (rc = gps_as_mat(h, X2, 5, "X2", &x2, false))) return rc;
+  if ((rc = gps_as_mat(h, W, 6, "W", &w, false))) return rc;
+  if ((rc = gps_as_mat(h, dtheta_out, 7, "dtheta_out", &dth))) return rc;
+  if (dth.rows * dth.cols < desc->n_theta) return gps_fail(h, -7, "dtheta_out too small");
+  if (dX_out && (rc = gps_as_mat(h, dX_out, 8, "dX_out", &dx, false))) return rc;
+  GPS_CUDA(h, cudaSetDevice(h->device));
+  GramW gw;
+  gw.mode = W_DENSE; gw.W = w; gw.beta = nullptr; gw.R = 0; gw.sym_lower = 0;
+  return gps_gram_bwd_mat(h, desc, th, x, X2 ? &x2 : nullptr, gw, dth.p, dX_out ? &dx : nullptr, nullptr);
+}
+
+int gps_kdiag_fwd(gps_handle* h, const gps_kernel_desc* desc, const DLTensor* theta, const DLTensor* X,
+                  DLTensor* out) {
+  if (!h) return -1;
+  const double* th;
+  Mat x, o;
+  int rc;
+  if ((rc = theta_ptr(h, desc, theta, 3, &th))) return rc;
+  if ((rc = gps_as_mat(h, X, 4, "X", &x, false))) return rc;
+  if ((rc = gps_as_mat(h, out, 5, "out", &o))) return rc;
+  if (o.rows * o.cols != x.rows) return gps_fail(h, -5, "kdiag: out must have %lld entries", (long long)x.rows);
+  GPS_CUDA(h, cudaSetDevice(h->device));
+  return gps_kdiag_fwd_vec(h, desc, th, x, o.p);
+}
+
+int gps_kdiag_bwd(gps_handle* h, const gps_kernel_desc* desc, const DLTensor* theta, const DLTensor* X,
+                  const DLTensor* wv, DLTensor* dtheta_out, DLTensor* dX_out) {
+  if (!h) return -1;
+  const double* th;
+  Mat x, w, dth, dx;
+  int rc;
+  if ((rc = theta_ptr(h, desc, theta, 3, &th))) return rc;
+  if ((rc = gps_as_mat(h, X, 4, "X", &x, false))) return rc;
+  if ((rc = gps_as_mat(h, wv, 5, "w", &w))) return rc;
+  if (w.rows * w.cols != x.rows) return gps_fail(h, -5, "kdiag_bwd: w must have %lld entries", (long long)x.rows);
+  if ((rc = gps_as_mat(h, dtheta_out, 6, "dtheta_out", &dth))) return rc;
+  if (dth.rows * dth.cols < desc->n_theta) return gps_fail(h, -6, "dtheta_out too small");
+  if (dX_out) {
+    if ((rc = gps_as_mat(h, dX_out, 7, "dX_out", &dx, false))) return rc;
+    if (dx.rows != x.rows || dx.cols != x.cols) return gps_fail(h, -7, "kdiag_bwd: dX shape mismatch");
+  }
+  GPS_CUDA(h, cudaSetDevice(h->device));
+  Plan pl;
+  PlanDims pd;
+  if ((rc = build_plan(h, desc, x.cols, &pl, &pd))) return rc;
+  if (x.rows == 0) {
+    GPS_CUDA(h, cudaMemsetAsync(dth.p, 0, pl.n_theta * sizeof(double), h->stream));
+    return 0;
+  }
+  unsigned nblk = (unsigned)((x.rows + GRAM_THREADS - 1) / GRAM_THREADS);
+  double* part = (double*)gps_ws(h, WS_PARTIAL, (size_t)nblk * pl.n_theta * sizeof(double));
+  if (!part) return -102;
+  kdiag_kernel<<<nblk, GRAM_THREADS, 0, h->stream>>>(pl, pd, th, x.p, x.ld, x.rows, nullptr, w.p, part,
+                                                     dX_out ? dx.p : nullptr, dX_out ? dx.ld : 0, (int)x.cols);
+  GPS_LAUNCH_CHECK(h);
+  reduce_cols_kernel<<<(pl.n_theta + 127) / 128, 128, 0, h->stream>>>(part, nblk, pl.n_theta, 1.0, dth.p, 0, 0);
+  GPS_LAUNCH_CHECK(h);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,422 @@
+// Blocked recursive FP64 Cholesky, triangular solves and triangular inverse.
+//
+// Replaces tf.cholesky / tf.matrix_triangular_solve of the reference (call sites listed in
+// include/gpslim_b200.h).  Row-major, lower.  Structure:
+//   * leaves: one CTA factors a 128x128 diagonal block in shared memory AND inverts it
+//     (T = L_kk^-1); the rows beneath the block are then solved in place against T^T by
+//     64-row strips on the FP64 tensor cores (trsm_strip_kernel);
+//   * inner nodes: the trailing update  A22 -= A21 A21^T  (including all rows beneath, so the
+//     recursive TRSM updates are the same launch) is one lower-masked DMMA GEMM whose K is the
+//     size of the left half -- half of all flops run with K >= N/4.
+// The same leaves/inner-node split gives B L^-T (gps_trsm_rec) and U = L^-T
+// (gps_inv_upper_rec); K^-1 = U U^T is a single triangular-aware GEMM.
+#include "internal.cuh"
+
+namespace {
+
+constexpr int NB = GPS_NB;        // 128
+constexpr int SLD = 130;          // smem row stride of the base kernel (see bank analysis below)
+constexpr int BASE_THREADS = 256;
+constexpr int BASE_SMEM = (NB * SLD + 3 * NB) * (int)sizeof(double);
+
+// ------------------------------------------------------------------ 128x128 leaf
+// Thread pair (2i, 2i+1) owns row i; each half-sums the odd / even k terms of the dot
+// products.  SLD = 130: for a half-warp (8 rows x 2 parities) the 8-byte words
+// (i*130 + k + h) mod 16 are all distinct -> conflict-free.
+template <bool DO_CHOL>
+__global__ void __launch_bounds__(BASE_THREADS, 1)
+potrf_base_kernel(double* __restrict__ Abase, int64_t lda, int n_total, double* __restrict__ tinv,
+                  double* __restrict__ logdet, int* __restrict__ info, int row0,
+                  double* __restrict__ Ubase, int64_t ldu) {
+  extern __shared__ __align__(16) double sm[];
+  double* S = sm;                 // [NB][SLD]; lower: L, strict upper (transposed): T
+  double* rinv = sm + NB * SLD;   // 1 / L_ii
+  double* piv = rinv + NB;        // raw pivots
+  double* red = piv + NB;         // scratch for the log-det reduction
+  const int blk = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int n = min(NB, n_total - blk * NB);
+  double* A = Abase + (int64_t)blk * NB * (lda + 1);
+
+  for (int idx = tid; idx < NB * NB; idx += BASE_THREADS) {
+    int i = idx >> 7, j = idx & (NB - 1);
+    double v = (i == j) ? 1.0 : 0.0;          // identity padding for a partial last block
+    if (i < n && j <= i) v = A[(int64_t)i * lda + j];
+    S[i * SLD + j] = v;
+  }
+  __syncthreads();
+
+  const int i = tid >> 1, hh = tid & 1;
+  if (DO_CHOL) {
+    int bad = 0;
+    for (int j = 0; j < NB; ++j) {
+      double p0 = 0.0, p1 = 0.0;
+      if (i >= j) {
+        const double* ri = S + i * SLD;
+        const double* rj = S + j * SLD;
+        int k = hh;
+        for (; k + 2 < j; k += 4) {
+          p0 = fma(ri[k], rj[k], p0);
+          p1 = fma(ri[k + 2], rj[k + 2], p1);
+        }
+        if (k < j) p0 = fma(ri[k], rj[k], p0);
+      }
+      double part = p0 + p1;
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      double s = 0.0;
+      if (i >= j) s = S[i * SLD + j] - part;
+      if (i == j && hh == 0) piv[j] = s;             // raw pivot
+      __syncthreads();
+      double d = piv[j];
+      if (!(d > 0.0)) {                              // also catches NaN
+        if (!bad && tid == 0 && j < n) {
+          int val = row0 + blk * NB + j + 1;
+          int old = atomicCAS(info, 0, val);
+          if (old != 0 && old > val) atomicMin(info, val);
+        }
+        bad = 1;
+      }
+      double r = sqrt(d);
+      if (hh == 0) {
+        if (i == j) {
+          S[j * SLD + j] = r;
+          rinv[j] = 1.0 / r;
+        } else if (i > j) {
+          S[i * SLD + j] = s / r;
+        }
+      }
+      __syncthreads();
+    }
+  } else {
+    if (tid < NB) rinv[tid] = 1.0 / S[tid * SLD + tid];
+    __syncthreads();
+  }
+
+  // T = L^-1, column c by thread pair c (forward substitution down the rows); T[i][c] (i > c)
+  // is kept at S[c][i], i.e. in the unused strict upper triangle.
+  {
+    const int c = i;
+    const int tmax = NB - 1 - (tid >> 5) * 16;   // warp-uniform trip count (16 columns / warp)
+    const double* tc = S + c * SLD;
+    for (int t = 0; t < tmax; ++t) {
+      const int r = c + 1 + t;
+      const bool act = r < NB;
+      const double* lr = S + (act ? r : c) * SLD;
+      double p0 = 0.0, p1 = 0.0;
+      // the k = c term uses T[c][c] = rinv[c] and is added below
+      int k = c + 1 + hh;
+      const int kend = act ? r : 0;
+      for (; k + 2 < kend; k += 4) {
+        p0 = fma(lr[k], tc[k], p0);
+        p1 = fma(lr[k + 2], tc[k + 2], p1);
+      }
+      if (k < kend) p0 = fma(lr[k], tc[k], p0);
+      double part = p0 + p1;
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      if (act && hh == 0) S[c * SLD + r] = -(part + lr[c] * rinv[c]) * rinv[r];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  // write back: L (lower part of A), T (dense, zero upper), U diag tile = T^T (zero lower)
+  if (DO_CHOL) {
+    for (int idx = tid; idx < NB * NB; idx += BASE_THREADS) {
+      int r = idx >> 7, cc = idx & (NB - 1);
+      if (r < n && cc <= r) A[(int64_t)r * lda + cc] = S[r * SLD + cc];
+    }
+  }
+  if (tinv) {
+    double* T = tinv + (int64_t)blk * NB * NB;
+    for (int idx = tid; idx < NB * NB; idx += BASE_THREADS) {
+      int r = idx >> 7, cc = idx & (NB - 1);
+      double v = 0.0;
+      if (cc < r) v = S[cc * SLD + r];
+      else if (cc == r) v = rinv[r];
+      T[idx] = v;
+    }
+  }
+  if (Ubase) {
+    double* U = Ubase + (int64_t)blk * NB * (ldu + 1);
+    for (int idx = tid; idx < NB * NB; idx += BASE_THREADS) {
+      int r = idx >> 7, cc = idx & (NB - 1);
+      if (r < n && cc < n) {
+        double v = 0.0;
+        if (cc > r) v = S[r * SLD + cc];
+        else if (cc == r) v = rinv[r];
+        U[(int64_t)r * ldu + cc] = v;
+      }
+    }
+  }
+  if (logdet) {
+    double s = 0.0;
+    if (tid < n) s = -log(rinv[tid]);
+    s = warp_sum(s);
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < BASE_THREADS / 32; ++w) t += red[w];
+      logdet[blk] = t;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ strip TRSM on DMMA
+// B[r0:r0+64, 0:n] <- B[r0:r0+64, 0:n] * T^T   (T = 128x128 dense inverse of the diagonal
+// block, lower triangular with explicit zeros above the diagonal).  In place: a CTA reads
+// only the strip it overwrites.
+constexpr int TS_LD = 132;   // 132 = 4 mod 16 -> conflict-free DMMA fragment loads
+constexpr int STRIP = 64;
+constexpr int STRIP_SMEM = (NB + STRIP) * TS_LD * (int)sizeof(double);
+
+__global__ void __launch_bounds__(256, 1)
+trsm_strip_kernel(double* __restrict__ B, int64_t ldb, int m, int n, const double* __restrict__ T) {
+  extern __shared__ __align__(16) double sm[];
+  double* Ts = sm;                  // [NB][TS_LD]
+  double* Bs = sm + NB * TS_LD;     // [STRIP][TS_LD]
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.x * STRIP;
+  for (int idx = tid; idx < NB * NB / 2; idx += 256) {
+    int r = idx >> 6, c2 = (idx & 63) * 2;
+    double2 v = *reinterpret_cast<const double2*>(T + r * NB + c2);
+    Ts[r * TS_LD + c2] = v.x;
+    Ts[r * TS_LD + c2 + 1] = v.y;
+  }
+  for (int idx = tid; idx < STRIP * NB; idx += 256) {
+    int r = idx >> 7, c = idx & (NB - 1);
+    double v = 0.0;
+    if (r0 + r < m && c < n) v = B[(int64_t)(r0 + r) * ldb + c];
+    Bs[r * TS_LD + c] = v;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int mrow = (warp & 3) * 16;     // 2 m-subtiles of 8 rows
+  const int nbase = (warp >> 2) * 64;   // 8 n-subtiles of 8 columns
+  double acc[2][8][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[a][j][0] = acc[a][j][1] = 0.0;
+  const int kend = min(n, nbase + 64);  // T[c][k] == 0 for k > c
+  for (int k0 = 0; k0 < kend; k0 += 4) {
+    double a0 = Bs[(mrow + lr) * TS_LD + k0 + lc];
+    double a1 = Bs[(mrow + 8 + lr) * TS_LD + k0 + lc];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (k0 <= nbase + j * 8 + 7) {     // warp-uniform
+        double b = Ts[(nbase + j * 8 + lr) * TS_LD + k0 + lc];
+        dmma884(acc[0][j][0], acc[0][j][1], a0, b);
+        dmma884(acc[1][j][0], acc[1][j][1], a1, b);
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    int row = r0 + mrow + a * 8 + lr;
+    if (row >= m) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int col = nbase + j * 8 + lc * 2;
+      double* bp = B + (int64_t)row * ldb + col;
+      if (col < n) bp[0] = acc[a][j][0];
+      if (col + 1 < n) bp[1] = acc[a][j][1];
+    }
+  }
+}
+
+bool g_attr_set = false;
+void set_attrs() {
+  if (g_attr_set) return;
+  cudaFuncSetAttribute(potrf_base_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BASE_SMEM);
+  cudaFuncSetAttribute(potrf_base_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BASE_SMEM);
+  cudaFuncSetAttribute(trsm_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STRIP_SMEM);
+  g_attr_set = true;
+}
+
+int64_t split_point(int64_t n) {
+  int64_t nb = (n + NB - 1) / NB;
+  return (nb / 2) * NB;
+}
+
+int strip_launch(gps_handle* h, Mat B, int64_t n, const double* T) {
+  if (B.rows <= 0) return 0;
+  set_attrs();
+  unsigned grid = (unsigned)((B.rows + STRIP - 1) / STRIP);
+  trsm_strip_kernel<<<grid, 256, STRIP_SMEM, h->stream>>>(B.p, B.ld, (int)B.rows, (int)n, T);
+  GPS_LAUNCH_CHECK(h);
+  return 0;
+}
+
+}  // namespace
+
+int gps_potrf_rec(gps_handle* h, Mat A, int64_t n, int64_t below, int64_t blk0, double* tinv,
+                  double* logdet, int* info_dev, int64_t row0) {
+  int rc;
+  if (n <= 0) return 0;
+  if (n <= NB) {
+    set_attrs();
+    potrf_base_kernel<true><<<1, BASE_THREADS, BASE_SMEM, h->stream>>>(
+        A.p, A.ld, (int)n, tinv + blk0 * NB * NB, logdet ? logdet + blk0 : nullptr, info_dev,
+        (int)row0, nullptr, 0);
+    GPS_LAUNCH_CHECK(h);
+    if (below > 0) {
+      if ((rc = strip_launch(h, A.sub(n, 0, below, n), n, tinv + blk0 * NB * NB))) return rc;
+    }
+    return 0;
+  }
+  int64_t n1 = split_point(n), n2 = n - n1;
+  if ((rc = gps_potrf_rec(h, A, n1, n2 + below, blk0, tinv, logdet, info_dev, row0))) return rc;
+  // trailing update incl. the rows beneath:  C -= P * P[0:n2]^T  (lower-masked)
+  Mat P = A.sub(n1, 0, n2 + below, n1);
+  Mat Pb = A.sub(n1, 0, n2, n1);
+  Mat C = A.sub(n1, n1, n2 + below, n2);
+  if ((rc = gps_gemm_nt_launch(h, -1.0, P, Pb, 1.0, C, TRI_NONE, TRI_NONE, C_LOWER))) return rc;
+  return gps_potrf_rec(h, A.sub(n1, n1, n2 + below, n2), n2, below, blk0 + n1 / NB, tinv, logdet,
+                       info_dev, row0 + n1);
+}
+
+int gps_trsm_rec(gps_handle* h, Mat L, Mat B, int64_t blk0, const double* tinv) {
+  int rc;
+  int64_t n = L.rows;
+  if (n <= 0 || B.rows <= 0) return 0;
+  if (n <= NB) return strip_launch(h, B, n, tinv + blk0 * NB * NB);
+  int64_t n1 = split_point(n), n2 = n - n1;
+  Mat B1 = B.sub(0, 0, B.rows, n1), B2 = B.sub(0, n1, B.rows, n2);
+  if ((rc = gps_trsm_rec(h, L.sub(0, 0, n1, n1), B1, blk0, tinv))) return rc;
+  if ((rc = gps_gemm_nt_launch(h, -1.0, B1, L.sub(n1, 0, n2, n1), 1.0, B2, TRI_NONE, TRI_NONE,
+                               C_ALL)))
+    return rc;
+  return gps_trsm_rec(h, L.sub(n1, n1, n2, n2), B2, blk0 + n1 / NB, tinv);
+}
+
+int gps_block_inverses(gps_handle* h, Mat L, double* tinv) {
+  if (L.rows <= 0) return 0;
+  set_attrs();
+  unsigned nblk = (unsigned)((L.rows + NB - 1) / NB);
+  potrf_base_kernel<false><<<nblk, BASE_THREADS, BASE_SMEM, h->stream>>>(
+      L.p, L.ld, (int)L.rows, tinv, nullptr, nullptr, 0, nullptr, 0);
+  GPS_LAUNCH_CHECK(h);
+  return 0;
+}
+
+// diagonal tiles of U from the block inverses (U_kk = T_kk^T)
+__global__ void u_diag_kernel(const double* __restrict__ tinv, double* __restrict__ U, int64_t ldu,
+                              int n_total) {
+  __shared__ double tile[32][33];
+  const int blk = blockIdx.z;
+  const int n = min(NB, n_total - blk * NB);
+  const double* T = tinv + (int64_t)blk * NB * NB;
+  double* Ub = U + (int64_t)blk * NB * (ldu + 1);
+  int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;  // tile of T
+  for (int i = threadIdx.y; i < 32; i += 8) tile[i][threadIdx.x] = T[(r0 + i) * NB + c0 + threadIdx.x];
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int r = c0 + i, c = r0 + threadIdx.x;  // U[r][c] = T[c][r]
+    if (r < n && c < n) Ub[(int64_t)r * ldu + c] = tile[threadIdx.x][i];
+  }
+}
+
+int gps_inv_upper_rec(gps_handle* h, Mat L, Mat U, int64_t blk0, const double* tinv) {
+  int rc;
+  int64_t n = L.rows;
+  if (n <= NB) return 0;  // diagonal tiles are written up front by the caller
+  int64_t n1 = split_point(n), n2 = n - n1;
+  if ((rc = gps_inv_upper_rec(h, L.sub(0, 0, n1, n1), U.sub(0, 0, n1, n1), blk0, tinv))) return rc;
+  if ((rc = gps_inv_upper_rec(h, L.sub(n1, n1, n2, n2), U.sub(n1, n1, n2, n2), blk0 + n1 / NB, tinv)))
+    return rc;
+  // U12 = -U11 * L21^T, then U12 <- U12 * L22^-T
+  Mat U12 = U.sub(0, n1, n1, n2);
+  if ((rc = gps_gemm_nt_launch(h, -1.0, U.sub(0, 0, n1, n1), L.sub(n1, 0, n2, n1), 0.0, U12,
+                               TRI_UPPER, TRI_NONE, C_ALL)))
+    return rc;
+  return gps_trsm_rec(h, L.sub(n1, n1, n2, n2), U12, blk0 + n1 / NB, tinv);
+}
+
+static int u_diag_launch(gps_handle* h, const double* tinv, Mat U) {
+  unsigned nblk = (unsigned)((U.rows + NB - 1) / NB);
+  u_diag_kernel<<<dim3(NB / 32, NB / 32, nblk), dim3(32, 8), 0, h->stream>>>(tinv, U.p, U.ld,
+                                                                           (int)U.rows);
+  GPS_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int gps_inv_upper_full(gps_handle* h, Mat L, Mat U, const double* tinv) {
+  int rc;
+  if ((rc = u_diag_launch(h, tinv, U))) return rc;
+  return gps_inv_upper_rec(h, L, U, 0, tinv);
+}
+
+// ------------------------------------------------------------------------- C ABI
+extern "C" {
+
+int gps_potrf(gps_handle* h, DLTensor* A_inout, int zero_upper, int* info_host) {
+  if (!h) return -1;
+  Mat A;
+  int rc;
+  if ((rc = gps_as_mat(h, A_inout, 2, "A_inout", &A, false))) return rc;
+  if (A.rows != A.cols) return gps_fail(h, -2, "potrf: matrix must be square");
+  GPS_CUDA(h, cudaSetDevice(h->device));
+  int64_t n = A.rows;
+  if (n == 0) {
+    if (info_host) *info_host = 0;
+    return 0;
+  }
+  int64_t nblk = (n + NB - 1) / NB;
+  double* tinv = (double*)gps_ws(h, WS_TINV, (size_t)nblk * NB * NB * sizeof(double));
+  int* info_dev = (int*)gps_ws(h, WS_INFO, 64);
+  if (!tinv || !info_dev) return -102;
+  GPS_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int), h->stream));
+  if ((rc = gps_potrf_rec(h, A, n, 0, 0, tinv, nullptr, info_dev, 0))) return rc;
+  if (zero_upper && (rc = gps_zero_upper_launch(h, A))) return rc;
+  if (info_host) {
+    GPS_CUDA(h, cudaMemcpyAsync(info_host, info_dev, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    GPS_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (*info_host > 0) {
+      gps_fail(h, *info_host, "potrf: leading minor of order %d is not positive definite", *info_host);
+      return *info_host;
+    }
+  }
+  return 0;
+}
+
+int gps_trsm_rlt(gps_handle* h, const DLTensor* Lt, DLTensor* B_inout) {
+  if (!h) return -1;
+  Mat L, B;
+  int rc;
+  if ((rc = gps_as_mat(h, Lt, 2, "L", &L, false))) return rc;
+  if ((rc = gps_as_mat(h, B_inout, 3, "B_inout", &B, false))) return rc;
+  if (L.rows != L.cols) return gps_fail(h, -2, "trsm: L must be square");
+  if (B.cols != L.rows) return gps_fail(h, -3, "trsm: B has %lld columns, L is %lld x %lld",
+                                        (long long)B.cols, (long long)L.rows, (long long)L.rows);
+  GPS_CUDA(h, cudaSetDevice(h->device));
+  if (L.rows == 0 || B.rows == 0) return 0;
+  int64_t nblk = (L.rows + NB - 1) / NB;
+  double* tinv = (double*)gps_ws(h, WS_TINV, (size_t)nblk * NB * NB * sizeof(double));
+  if (!tinv) return -102;
+  if ((rc = gps_block_inverses(h, L, tinv))) return rc;
+  return gps_trsm_rec(h, L, B, 0, tinv);
+}
+
+int gps_tri_inv_t(gps_handle* h, const DLTensor* Lt, DLTensor* U_out) {
+  if (!h) return -1;
+  Mat L, U;
+  int rc;
+  if ((rc = gps_as_mat(h, Lt, 2, "L", &L, false))) return rc;
+  if ((rc = gps_as_mat(h, U_out, 3, "U_out", &U, false))) return rc;
+  if (L.rows != L.cols || U.rows != L.rows || U.cols != L.cols)
+    return gps_fail(h, -3, "tri_inv_t: shape mismatch");
+  GPS_CUDA(h, cudaSetDevice(h->device));
+  if (L.rows == 0) return 0;
+  int64_t nblk = (L.rows + NB - 1) / NB;
+  double* tinv = (double*)gps_ws(h, WS_TINV, (size_t)nblk * NB * NB * sizeof(double));
+  if (!tinv) return -102;
+  // strict lower part of U is defined to be zero
+  GPS_CUDA(h, cudaMemset2DAsync(U.p, U.ld * sizeof(double), 0, U.cols * sizeof(double), U.rows,
+                                h->stream));
+  if ((rc = gps_block_inverses(h, L, tinv))) return rc;
+  return gps_inv_upper_full(h, L, U, tinv);
+}
+
+}  // extern "C"

@@ -1,0 +1,401 @@
+"""torch.autograd plumbing over the C ABI.
+
+Each Function forwards to one or a few library calls; all O(n^2) / O(n^3) arithmetic --
+forward and backward -- runs in the hand-written CUDA kernels.  torch only supplies memory,
+the autograd tape and a handful of O(n^2) elementwise masks.
+"""
+import ctypes
+import weakref
+
+import torch
+
+from . import lib as _L
+from .lib import TRI_LOWER, TRI_NONE, TRI_UPPER, handle_for, ref, view
+
+F64 = torch.float64
+
+
+def _prep(t):
+    if t.dtype != F64:
+        t = t.to(F64)
+    if t.dim() == 2 and t.shape[1] > 1 and t.stride(1) != 1:
+        t = t.contiguous()
+    elif t.dim() == 2 and t.shape[0] > 1 and t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    elif t.dim() == 1 and t.numel() > 1 and t.stride(0) != 1:
+        t = t.contiguous()
+    return t
+
+
+# ------------------------------------------------------------------------- raw (no autograd)
+def gemm_nt(A, B, alpha=1.0, beta=0.0, out=None, a_tri=TRI_NONE, b_tri=TRI_NONE, c_uplo=0):
+    """out = alpha * A @ B.T + beta * out  (FP64 tensor-core GEMM)."""
+    A, B = _prep(A), _prep(B)
+    h = handle_for(A)
+    if out is None:
+        out = torch.empty((A.shape[0], B.shape[0]), dtype=F64, device=A.device)
+        if c_uplo:
+            out.zero_()
+        beta = 0.0
+    va, vb, vc = view(A), view(B), view(out)
+    h.check(h.lib.gps_gemm_nt(h.ptr, float(alpha), va.ref, vb.ref, float(beta), vc.ref, a_tri,
+                              b_tri, c_uplo))
+    return out
+
+
+def transpose(A):
+    A = _prep(A)
+    h = handle_for(A)
+    out = torch.empty((A.shape[1], A.shape[0]), dtype=F64, device=A.device)
+    if A.numel():
+        va, vo = view(A), view(out)
+        h.check(h.lib.gps_transpose(h.ptr, va.ref, vo.ref))
+    return out
+
+
+def potrf(K, zero_upper=True, check=True):
+    """Returns the lower Cholesky factor of K (K is not modified)."""
+    L = _prep(K).clone()
+    h = handle_for(L)
+    info = ctypes.c_int(0)
+    vl = view(L)
+    h.check(h.lib.gps_potrf(h.ptr, vl.ref, int(zero_upper), ctypes.byref(info) if check else None))
+    return L
+
+
+def trsm_rlt_(L, B):
+    """In place B <- B L^-T."""
+    h = handle_for(B)
+    vl, vb = view(_prep(L)), view(B)
+    h.check(h.lib.gps_trsm_rlt(h.ptr, vl.ref, vb.ref))
+    return B
+
+
+_U_CACHE = {}
+
+
+def tri_inv_t(L):
+    """U = L^-T (upper triangular).  Cached per factor: backward passes reuse it."""
+    L = _prep(L)
+    key = (L.data_ptr(), L._version, tuple(L.shape))
+    hit = _U_CACHE.get(key)
+    if hit is not None and hit[0]() is L:
+        return hit[1]
+    h = handle_for(L)
+    U = torch.empty_like(L, memory_format=torch.contiguous_format)
+    vl, vu = view(L), view(U)
+    h.check(h.lib.gps_tri_inv_t(h.ptr, vl.ref, vu.ref))
+    if len(_U_CACHE) > 8:
+        _U_CACHE.clear()
+    _U_CACHE[key] = (weakref.ref(L), U)
+    return U
+
+
+def row_sumsq(A):
+    A = _prep(A)
+    h = handle_for(A)
+    out = torch.empty(A.shape[0], dtype=F64, device=A.device)
+    if A.shape[0]:
+        va, vo = view(A), view(out)
+        h.check(h.lib.gps_row_sumsq(h.ptr, 1.0, va.ref, 0.0, vo.ref))
+    return out
+
+
+# ------------------------------------------------------------------------- autograd Functions
+class _MatmulNT(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, A, B, a_tri, b_tri):
+        A, B = _prep(A), _prep(B)
+        ctx.save_for_backward(A, B)
+        ctx.tri = (a_tri, b_tri)
+        return gemm_nt(A, B, a_tri=a_tri, b_tri=b_tri)
+
+    @staticmethod
+    def backward(ctx, G):
+        A, B = ctx.saved_tensors
+        a_tri, b_tri = ctx.tri
+        G = _prep(G)
+        dA = dB = None
+        if ctx.needs_input_grad[0]:
+            # dA = G B   ==  G (B^T)^T
+            dA = gemm_nt(G, transpose(B))
+            if a_tri == TRI_LOWER:
+                dA = torch.tril(dA)
+            elif a_tri == TRI_UPPER:
+                dA = torch.triu(dA)
+        if ctx.needs_input_grad[1]:
+            # dB = G^T A  ==  (G^T) (A^T)^T
+            dB = gemm_nt(transpose(G), transpose(A))
+            if b_tri == TRI_LOWER:
+                dB = torch.tril(dB)
+            elif b_tri == TRI_UPPER:
+                dB = torch.triu(dB)
+        return dA, dB, None, None
+
+
+def matmul_nt(A, B, a_tri=TRI_NONE, b_tri=TRI_NONE):
+    """A @ B.T; a_tri / b_tri declare A / B triangular (zero tiles are skipped)."""
+    return _MatmulNT.apply(A, B, a_tri, b_tri)
+
+
+def matmul(A, B):
+    """A @ B through the NT tensor-core kernel (B is transposed by a device kernel)."""
+    return matmul_nt(A, _Transpose.apply(B))
+
+
+class _Transpose(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, A):
+        return transpose(A)
+
+    @staticmethod
+    def backward(ctx, G):
+        return transpose(_prep(G))
+
+
+def t(A):
+    return _Transpose.apply(A)
+
+
+class _Cholesky(torch.autograd.Function):
+    """L = chol(K) (tf.cholesky).  Backward: Kbar = sym(L^-T Phi(L^T Lbar) L^-1) (Murray 2016),
+    evaluated with U = L^-T and triangular-aware tensor-core GEMMs."""
+
+    @staticmethod
+    def forward(ctx, K):
+        L = potrf(K)
+        ctx.save_for_backward(L)
+        return L
+
+    @staticmethod
+    def backward(ctx, Lbar):
+        (L,) = ctx.saved_tensors
+        Lbar = torch.tril(_prep(Lbar))
+        U = tri_inv_t(L)
+        # P = Phi(L^T Lbar):  (L^T Lbar)[m,n] = sum_k Lt[m,k] Lbar_t[n,k]
+        P = gemm_nt(transpose(L), transpose(Lbar), a_tri=TRI_UPPER, b_tri=TRI_UPPER)
+        P = torch.tril(P)
+        P.diagonal().mul_(0.5)
+        # S = U P U^T:  Qt = U P^T ; S = U Qt^T ... with NT products: Qt[m,n] = sum_k U[m,k] P[n,k]
+        Qt = gemm_nt(U, P, a_tri=TRI_UPPER, b_tri=TRI_LOWER)
+        S = gemm_nt(U, Qt, a_tri=TRI_UPPER)
+        return 0.5 * (S + S.t())
+
+
+def cholesky(K):
+    return _Cholesky.apply(K)
+
+
+class _TrsmRLT(torch.autograd.Function):
+    """X = B L^-T  (the row-major form of tf.matrix_triangular_solve(L, B^T, lower=True)^T)."""
+
+    @staticmethod
+    def forward(ctx, B, L):
+        L = _prep(L)
+        X = _prep(B).clone()
+        trsm_rlt_(L, X)
+        ctx.save_for_backward(X, L)
+        return X
+
+    @staticmethod
+    def backward(ctx, Xbar):
+        X, L = ctx.saved_tensors
+        Xbar = _prep(Xbar)
+        U = tri_inv_t(L)
+        # Bbar = Xbar L^-1 = Xbar U^T
+        Bbar = gemm_nt(Xbar, U, b_tri=TRI_UPPER)
+        dL = None
+        if ctx.needs_input_grad[1]:
+            # Lbar = -tril(Bbar^T X)
+            dL = gemm_nt(transpose(Bbar), transpose(X), alpha=-1.0, c_uplo=1)
+        return (Bbar if ctx.needs_input_grad[0] else None), dL
+
+
+def trsm_rlt(B, L):
+    return _TrsmRLT.apply(B, L)
+
+
+def solve_lower(L, B):
+    """tf.matrix_triangular_solve(L, B, lower=True) for column-layout B [n, m]."""
+    return t(trsm_rlt(t(B), L))
+
+
+def solve_upper_t(L, B):
+    """tf.matrix_triangular_solve(tf.transpose(L), B, lower=False) = L^-T B  (conditionals.py:100):
+    (L^-T B)^T = B^T L^-1 = B^T U^T with U = L^-T."""
+    return t(matmul_nt(t(B), _TriInvT.apply(L), b_tri=TRI_UPPER))
+
+
+class _TriInvT(torch.autograd.Function):
+    """U = L^-T.  Backward: Lbar = -tril((U Ubar^T U)^T)... derived from dU = -U dL^T U."""
+
+    @staticmethod
+    def forward(ctx, L):
+        L = _prep(L)
+        U = tri_inv_t(L)
+        ctx.save_for_backward(U)
+        return U
+
+    @staticmethod
+    def backward(ctx, Ubar):
+        (U,) = ctx.saved_tensors
+        Ubar = torch.triu(_prep(Ubar))
+        # dU = -U dL^T U  =>  Lbar = -(U^T Ubar U^T)^T = -U Ubar^T U  (lower part)
+        T1 = gemm_nt(U, Ubar, a_tri=TRI_UPPER, b_tri=TRI_UPPER)        # U Ubar^T
+        Lbar = gemm_nt(T1, transpose(U), alpha=-1.0)                   # (U Ubar^T) U
+        return torch.tril(Lbar)
+
+
+# ------------------------------------------------------------------------- Gram
+class KernelProgram(object):
+    """A compiled covariance function: ctypes descriptor + the list of constrained parameter
+    tensors whose concatenation is `theta`."""
+
+    def __init__(self, desc, pieces, n_theta):
+        self.desc = desc
+        self.pieces = pieces          # callables returning tensors (constrained values)
+        self.n_theta = n_theta
+
+    def theta(self, device):
+        vals = []
+        for p in self.pieces:
+            v = p() if callable(p) else p
+            if not isinstance(v, torch.Tensor):
+                v = torch.as_tensor(v, dtype=F64, device=device)
+            vals.append(v.to(device=device, dtype=F64).reshape(-1))
+        return torch.cat(vals)
+
+
+class _Gram(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, theta, X, X2, prog, diag_add):
+        X = _prep(X)
+        X2 = None if X2 is None else _prep(X2)
+        theta = _prep(theta)
+        h = handle_for(X)
+        n, m = X.shape[0], (X.shape[0] if X2 is None else X2.shape[0])
+        K = torch.empty((n, m), dtype=F64, device=X.device)
+        vt, vx, vx2, vk = view(theta), view(X), view(X2), view(K)
+        h.check(h.lib.gps_gram_fwd(h.ptr, ctypes.byref(prog.desc), vt.ref, vx.ref, ref(vx2),
+                                   float(diag_add), 0, vk.ref))
+        ctx.save_for_backward(theta, X, X2 if X2 is not None else torch.empty(0))
+        ctx.prog = prog
+        ctx.has_x2 = X2 is not None
+        return K
+
+    @staticmethod
+    def backward(ctx, W):
+        theta, X, X2 = ctx.saved_tensors
+        X2 = X2 if ctx.has_x2 else None
+        prog = ctx.prog
+        W = _prep(W)
+        h = handle_for(X)
+        need_dx = ctx.needs_input_grad[1]
+        need_dx2 = ctx.has_x2 and ctx.needs_input_grad[2]
+        dtheta = torch.empty(prog.n_theta, dtype=F64, device=X.device)
+        dX = torch.empty_like(X) if need_dx else None
+        if not ctx.has_x2:
+            # the library treats W as symmetric in the one-argument case
+            W = 0.5 * (W + W.t())
+            W = W.contiguous()
+        vt, vx, vx2, vw, vd, vdx = view(theta), view(X), view(X2), view(W), view(dtheta), view(dX)
+        h.check(h.lib.gps_gram_bwd(h.ptr, ctypes.byref(prog.desc), vt.ref, vx.ref, ref(vx2),
+                                   vw.ref, vd.ref, ref(vdx)))
+        dX2 = None
+        if need_dx2:
+            # gradient w.r.t. the second argument: swap roles, transpose the weights
+            dX2 = torch.empty_like(X2)
+            Wt = transpose(W)
+            scratch = torch.empty(prog.n_theta, dtype=F64, device=X.device)
+            vwt, vs, vdx2 = view(Wt), view(scratch), view(dX2)
+            h.check(h.lib.gps_gram_bwd(h.ptr, ctypes.byref(prog.desc), vt.ref, vx2.ref, vx.ref,
+                                       vwt.ref, vs.ref, vdx2.ref))
+        return dtheta, dX, dX2, None, None
+
+
+def gram(prog, X, X2=None, diag_add=0.0):
+    theta = prog.theta(X.device)
+    return _Gram.apply(theta, X, X2, prog, diag_add)
+
+
+class _Kdiag(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, theta, X, prog):
+        X, theta = _prep(X), _prep(theta)
+        h = handle_for(X)
+        out = torch.empty(X.shape[0], dtype=F64, device=X.device)
+        vt, vx, vo = view(theta), view(X), view(out)
+        h.check(h.lib.gps_kdiag_fwd(h.ptr, ctypes.byref(prog.desc), vt.ref, vx.ref, vo.ref))
+        ctx.save_for_backward(theta, X)
+        ctx.prog = prog
+        return out
+
+    @staticmethod
+    def backward(ctx, w):
+        theta, X = ctx.saved_tensors
+        prog = ctx.prog
+        w = _prep(w)
+        h = handle_for(X)
+        dtheta = torch.empty(prog.n_theta, dtype=F64, device=X.device)
+        dX = torch.empty_like(X) if ctx.needs_input_grad[1] else None
+        vt, vx, vw, vd, vdx = view(theta), view(X), view(w), view(dtheta), view(dX)
+        h.check(h.lib.gps_kdiag_bwd(h.ptr, ctypes.byref(prog.desc), vt.ref, vx.ref, vw.ref, vd.ref,
+                                    ref(vdx)))
+        return dtheta, dX, None
+
+
+def kdiag(prog, X):
+    return _Kdiag.apply(prog.theta(X.device), X, prog)
+
+
+# ------------------------------------------------------------------------- fused GPR
+class _GprLogLik(torch.autograd.Function):
+    """log p(Y) of GPR (models/gpr.py:55-72) with its gradient, one library call."""
+
+    @staticmethod
+    def forward(ctx, theta, noise, Yc, X, prog):
+        X, Yc, theta = _prep(X), _prep(Yc), _prep(theta)
+        h = handle_for(X)
+        want_grad = bool(theta.requires_grad or noise.requires_grad or Yc.requires_grad)
+        # torch clears requires_grad inside Function.forward; use the ctx flags instead
+        want_grad = any(ctx.needs_input_grad[:3])
+        scal = torch.zeros(2, dtype=F64, device=X.device)
+        dtheta = torch.empty(prog.n_theta, dtype=F64, device=X.device) if want_grad else None
+        dY = torch.empty_like(Yc) if (want_grad and ctx.needs_input_grad[2]) else None
+        info = ctypes.c_int(0)
+        vt, vx, vy, vs, vd, vdy = view(theta), view(X), view(Yc), view(scal), view(dtheta), view(dY)
+        h.check(h.lib.gps_gpr_nlml_fwd_bwd(h.ptr, ctypes.byref(prog.desc), vt.ref, vx.ref, vy.ref,
+                                           float(noise), int(want_grad), vs.ref, ref(vd), ref(vdy),
+                                           ctypes.byref(info)))
+        ctx.grads = (dtheta, scal[1] if want_grad else None, dY)
+        return -scal[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        dtheta, dnoise, dY = ctx.grads
+        # stored gradients are those of the NEGATIVE log likelihood
+        gt = -g * dtheta if ctx.needs_input_grad[0] else None
+        gn = -g * dnoise if ctx.needs_input_grad[1] else None
+        gy = -g * dY if (ctx.needs_input_grad[2] and dY is not None) else None
+        return gt, gn, gy, None, None
+
+
+def gpr_loglik(prog, X, Yc, noise):
+    noise = noise if isinstance(noise, torch.Tensor) else torch.as_tensor(noise, dtype=F64,
+                                                                          device=X.device)
+    return _GprLogLik.apply(prog.theta(X.device), noise.reshape(()), Yc, X, prog)
+
+
+def gpr_predict(prog, X, Yc, noise, Xnew, full_cov=False):
+    X, Yc, Xnew = _prep(X), _prep(Yc), _prep(Xnew)
+    theta = _prep(prog.theta(X.device).detach())
+    h = handle_for(X)
+    ns, r = Xnew.shape[0], Yc.shape[1]
+    mean = torch.empty((ns, r), dtype=F64, device=X.device)
+    var = torch.empty((ns, ns) if full_cov else (ns,), dtype=F64, device=X.device)
+    info = ctypes.c_int(0)
+    vt, vx, vy, vn, vm, vv = view(theta), view(X), view(Yc), view(Xnew), view(mean), view(var)
+    h.check(h.lib.gps_gpr_predict(h.ptr, ctypes.byref(prog.desc), vt.ref, vx.ref, vy.ref,
+                                  float(noise), vn.ref, int(full_cov), vm.ref, vv.ref,
+                                  ctypes.byref(info)))
+    return mean, var

@@ -1,0 +1,114 @@
+"""Host-side logic (no GPU): transforms / parameters against the oracle and the golden
+initial states, kernel-expression compilation, settings."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases
+from oracle import ref_torch as R
+
+
+def gpf():
+    import gpflowSlim
+    return gpflowSlim
+
+
+def test_settings_surface():
+    s = gpf().settings
+    assert s.float_type is np.float64 and s.dtypes.float_type is np.float64
+    assert s.numerics.jitter_level == 1e-6 and s.jitter == 1e-6
+    s.set_jitter(1e-5)
+    assert s.jitter == 1e-5
+    s.set_jitter(1e-6)
+    tmp = s.get_settings()
+    tmp.numerics.jitter_level = 1e-3
+    with s.temp_settings(tmp):
+        assert s.numerics.jitter_level == 1e-3
+    assert s.numerics.jitter_level == 1e-6
+
+
+def test_log1pe_matches_oracle_and_is_exact_for_large_inputs():
+    t = gpf().transforms.Log1pe()
+    y = np.array([1e-5, 0.3, 1.0, 25.0, 900.0])
+    raw = t.backward(y)
+    np.testing.assert_allclose(raw, R.softplus_inv(y), rtol=0, atol=0)
+    np.testing.assert_allclose(t.forward_tensor(torch.tensor(raw)).numpy(), y, rtol=1e-14)
+    np.testing.assert_allclose(t.forward(raw), y, rtol=1e-14)
+    # torch's softplus linearises above 20; ours (like tf.nn.softplus) must not
+    x = torch.tensor([21.0], dtype=torch.float64)
+    assert float(t.forward_tensor(x)) == pytest.approx(21.0 + np.log1p(np.exp(-21.0)) + 1e-6, rel=1e-15)
+
+
+def test_lower_triangular_transform_matches_oracle():
+    T = gpf().transforms.LowerTriangular(4, num_matrices=3)
+    rng = np.random.default_rng(0)
+    mats = np.stack([np.tril(rng.standard_normal((4, 4))) for _ in range(3)], 2)
+    free = T.backward(mats)
+    assert free.shape == (3, 10)
+    np.testing.assert_array_equal(T.forward(free), mats)
+    np.testing.assert_array_equal(T.forward_tensor(torch.tensor(free)).numpy(), mats)
+    np.testing.assert_array_equal(R.vec_to_tri(free, 4).numpy(), mats)
+
+
+def test_parameter_order_and_initial_state_match_reference(golden):
+    """Same construction code as the reference => same parameter list, shapes and values."""
+    g = gpf()
+    X, Y = cases.synth_gpr(50, 4)
+    m = g.models.GPR(X, Y, kern=g.kernels.RBF(4, ARD=True))
+    gold = golden('gpr_c1')
+    assert len(m.parameters) == 3
+    for i, p in enumerate(m.parameters):
+        np.testing.assert_allclose(p.unconstrained_tensor.detach().cpu().numpy(),
+                                   gold['param/objective/%d' % i], rtol=1e-15)
+    Xs, Ys, Z = cases.synth_svgp(100, 3, 7)
+    sv = g.models.SVGP(Xs, Ys, g.kernels.RBF(3), g.likelihoods.Gaussian(), Z=Z, num_latent=2)
+    assert [tuple(p.shape) for p in sv.parameters] == [(), (), (), (7, 2), (2, 28)]
+    assert tuple(sv.q_sqrt.shape) == (7, 7, 2)
+    np.testing.assert_array_equal(sv.q_sqrt[:, :, 1].detach().cpu().numpy(), np.eye(7))
+    assert len(sv.trainable_tensors) == 6
+
+
+def test_kernel_expression_compiles_to_descriptor():
+    g = gpf()
+    from gpflowSlim._backend import lib
+    k = g.kernels
+    kern = k.RBF(2, active_dims=[0, 1]) * k.Linear(1, active_dims=[2]) + k.Matern52(3) + 0.5
+    prog = kern.program()
+    d = prog.desc
+    assert (d.n_prims, d.n_ops, d.n_theta) == (3, 4, 2 + 1 + 2 + 1)
+    assert [d.prims[i].type for i in range(3)] == [lib.GPS_RBF, lib.GPS_LINEAR, lib.GPS_MATERN52]
+    assert list(d.prims[1].dims[:1]) == [2] and list(d.prims[0].dims[:2]) == [0, 1]
+    ops = [(d.ops[i].op, d.ops[i].dst, d.ops[i].a, d.ops[i].b) for i in range(4)]
+    assert ops == [(lib.GPS_OP_MUL, 3, 0, 1), (lib.GPS_OP_CONST, 4, 5, 0), (lib.GPS_OP_ADD, 5, 3, 2),
+                   (lib.GPS_OP_ADD, 6, 5, 4)]
+    assert d.out_slot == 6
+    np.testing.assert_allclose(prog.theta('cpu').detach().numpy(), [1, 1, 1, 1, 1, 0.5], rtol=1e-12)
+
+
+def test_nkn_compiles_and_matches_reference_weights(golden):
+    g = gpf()
+    from gpflowSlim._backend import lib
+    kern = cases.nkn_c3_kernel(g, 3)
+    gold = golden('nkn')
+    # identical numpy-RNG draw as the reference (wrapper.py:100-104)
+    np.testing.assert_allclose(kern.parameters[0].unconstrained_tensor.detach().cpu().numpy(),
+                               gold['param/objective/0'], rtol=1e-15)
+    d = kern.program().desc
+    assert d.n_prims == 6 and d.n_ops == 5
+    assert [d.ops[i].op for i in range(5)] == [lib.GPS_OP_LINEAR, lib.GPS_OP_PRODUCT, lib.GPS_OP_LINEAR,
+                                                lib.GPS_OP_PRODUCT, lib.GPS_OP_LINEAR]
+    assert [d.ops[i].dst for i in range(5)] == [6, 14, 18, 22, 24] and d.out_slot == 24
+    assert d.n_theta == (48 + 8 + 16 + 4 + 2 + 1) + (4 + 4 + 3 + 3 + 3 + 3)
+
+
+def test_adam_matches_oracle_adam():
+    g = gpf()
+    p = torch.tensor([0.3, -1.2], dtype=torch.float64, requires_grad=True)
+    q = p.detach().clone()
+    opt = g.training.AdamOptimizer(1e-2)
+    state = {}
+    for step in range(3):
+        gr = torch.tensor([0.5 * (step + 1), -2.0], dtype=torch.float64)
+        opt.apply_gradients([(gr, p)])
+        q = R.tf_adam_step([q], [gr], state, lr=1e-2)[0]
+    np.testing.assert_allclose(p.detach().numpy(), q.numpy(), rtol=1e-15)
