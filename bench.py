@@ -1,0 +1,264 @@
+#!/usr/bin/env python
+"""Headline benchmark: GPR NLML + gradient evaluations per second, FP64, ARD-RBF, synthetic data
+(BASELINE.json metric; SURVEY.md section 8d inputs).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA path)
+    python bench.py --impl reference --steps K --warmup W    # reference's CPU path (oracle port)
+
+A "step" is one pass of the hot path over one data set: Gram -> Cholesky -> alpha -> NLML and
+the full gradient w.r.t. (variance, D lengthscales, noise).  `value` = steps/s with X, Y
+resident in HBM; `e2e` = the same through the public gpflowSlim API from pinned HOST buffers
+(H2D of X, Y and D2H of objective + gradient inside the timed region).  One JSON line on
+rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, 'gpflow-slim_b200'))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+NOMINAL_FP64_TFLOPS = 37.0   # B200 datasheet (DGX B200: 296 TF / 8); used only if nothing measured
+
+
+def synth_gpr(n, d, seed=0):
+    """X ~ N(0,1)^{N x D}, Y = sin(X.1/sqrt(D)) + 0.1 eps."""
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, d))
+    Y = np.sin(X.sum(1, keepdims=True) / np.sqrt(d)) + 0.1 * rng.standard_normal((n, 1))
+    return X, Y
+
+
+def fp64_peak():
+    """Measured cuBLAS DGEMM throughput on this pool's B200 (tools/measure_fp64.py ->
+    profiles/fp64_peak.json); MEASURED_PEAKS.json has no FP64 figure."""
+    p = os.path.join(ROOT, 'profiles', 'fp64_peak.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {'burst': d['cublas_dgemm_8192_tflops_burst'],
+                'sustained': d['cublas_dgemm_8192_tflops_sustained'],
+                'source': 'measured cuBLAS DGEMM 8192^3 (profiles/fp64_peak.json)'}
+    return {'burst': NOMINAL_FP64_TFLOPS, 'sustained': NOMINAL_FP64_TFLOPS,
+            'source': 'nominal datasheet FP64 (no measurement available)'}
+
+
+class ClockSampler(threading.Thread):
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm = sorted(int(float(r[0])) for r in self.rows if r[0].replace('.', '').isdigit())
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == 'Active' for r in self.rows)]
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(self.rows)}
+
+
+def oracle_eval(n, d, reps, threads=None):
+    """Reference's CPU path (oracle port): NLML + autograd gradient on a bounded sample."""
+    from oracle import ref_torch as R
+    if threads:
+        torch.set_num_threads(threads)
+    X, Y = synth_gpr(n, d)
+    X, Y = torch.tensor(X), torch.tensor(Y)
+    times = []
+    for _ in range(reps):
+        raw = [torch.tensor(R.softplus_inv(v), dtype=torch.float64, requires_grad=True)
+               for v in (1.0, math.sqrt(d) * np.ones(d), 0.1)]
+        t0 = time.perf_counter()
+        spec = dict(type='rbf', variance=R.softplus_fwd(raw[0]), lengthscales=R.softplus_fwd(raw[1]))
+        obj = R.gpr_nlml(spec, X, Y, R.softplus_fwd(raw[2]))
+        torch.autograd.grad(obj, raw)
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port
+    (torch-CPU fp64 restatement; TensorFlow 1.x is not installable), all host threads, each
+    step a bounded sample (N_s = args.cpu_n) of the workload; reported in the workload's unit
+    by the N^3 cost model of the path (Cholesky + its adjoint), which is stated in `sample`."""
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    n, d, ns = args.n, args.d, args.cpu_n
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    times = oracle_eval(ns, d, args.warmup + args.steps)[args.warmup:]
+    t = float(np.mean(times))
+    scale = (float(n) / ns) ** 3
+    val = 1.0 / (t * scale)
+    sample = ('oracle port (torch-CPU fp64 restatement of the reference TF path), NLML+grad at N_s=%d D=%d, '
+              '%.2f s/eval on %d threads; scaled to N=%d by (N/N_s)^3=%.0f' % (ns, d, t, cores, n, scale))
+    line = {'impl': 'reference', 'metric': 'GPR NLML+grad evals/s', 'value': val, 'unit': 'evals/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t * scale * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic', 'config': {'workload': 'GPR ARD-RBF N=%d D=%d fp64 NLML+grad' % (n, d)},
+            'cpu_baseline': {'value': val, 'unit': 'evals/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours')
+    ap.add_argument('--n', type=int, default=32768)
+    ap.add_argument('--d', type=int, default=8)
+    ap.add_argument('--cpu-n', type=int, default=4096, dest='cpu_n')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the product has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+
+    import gpflowSlim as gpf
+    from gpflowSlim._backend.lib import handle_for
+    gpf.settings.device = dev
+    n, d = args.n, args.d
+    # every rank owns one independent problem of the named shape (seed = rank): see DESIGN.md (e)
+    Xh, Yh = synth_gpr(n, d, seed=rank)
+    Xp = torch.from_numpy(Xh).pin_memory()
+    Yp = torch.from_numpy(Yh).pin_memory()
+    kern = gpf.kernels.RBF(d, ARD=True, lengthscales=math.sqrt(d))
+    model = gpf.models.GPR(Xp.to(dev), Yp.to(dev), kern=kern)
+    params = [p.unconstrained_tensor for p in model.parameters]
+    h = handle_for(dev)
+
+    def step():
+        obj = model.objective
+        return obj, torch.autograd.grad(obj, params)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    h.set_option('profile', 1)
+    h.profile_read(reset=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1) / args.steps
+    gemm_ms, gemm_flops, launches = h.profile_read(reset=True)
+    h.set_option('profile', 0)
+
+    # end to end through the public API from pinned host buffers
+    def e2e_step():
+        model.X = Xp.to(dev, non_blocking=True)
+        model.Y = Yp.to(dev, non_blocking=True)
+        obj, grads = step()
+        return obj.cpu(), [g.cpu() for g in grads]
+    e2e_step()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    t1.record()
+    barrier()
+    e2e_ms = t0.elapsed_time(t1) / args.steps
+
+    if world > 1:
+        tt = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(tt[0]), float(tt[1])
+
+    if rank == 0:
+        peak = fp64_peak()
+        ach = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        # the GEMM launches run back to back inside a ~1 s step: sustained figure applies
+        pk = peak['sustained']
+        nparam = d + 2
+        line = {
+            'metric': 'GPR NLML+grad evals/s', 'value': world * 1e3 / ms, 'unit': 'evals/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic',
+            'config': {'workload': 'GPR ARD-RBF N=%d D=%d fp64 NLML+grad (Gram+POTRF+TRSM+backward)' % (n, d),
+                       'parallelism': 'independent problem per GPU' if world > 1 else 'single GPU',
+                       'l2': 'inputs exceed L2 (K is %.1f GiB)' % (8.0 * n * n / 2 ** 30),
+                       'flops_per_eval_model': float(n) ** 3},
+            'e2e': {'value': world * 1e3 / e2e_ms, 'unit': 'evals/s',
+                    'h2d_bytes_per_step': int(Xp.numel() * 8 + Yp.numel() * 8),
+                    'd2h_bytes_per_step': int(8 * (1 + nparam))},
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+            'roofline': {'bound': 'tensor', 'kernel': 'gemm_nt_dmma_kernel (FP64 DMMA)', 'achieved': ach,
+                         'peak': pk, 'unit': 'TFLOP/s', 'frac': ach / pk if pk else None, 'traffic': None,
+                         'peak_source': peak['source'],
+                         'gemm_share_of_step': gemm_ms / (ms * args.steps) if ms > 0 else None,
+                         'step_tflops_vs_n3': float(n) ** 3 / (ms * 1e-3) / 1e12},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            ns = args.cpu_n
+            cores = os.cpu_count()
+            torch.set_num_threads(cores)
+            reps = 3
+            times = oracle_eval(ns, d, reps + 1)[1:]
+            t = float(np.mean(times))
+            scale = (float(n) / ns) ** 3
+            line['cpu_baseline'] = {
+                'value': 1.0 / (t * scale), 'unit': 'evals/s', 'cores': cores, 'kind': 'port',
+                'sample': 'oracle port, NLML+grad at N_s=%d D=%d: %.2f s/eval on %d threads, scaled by '
+                          '(N/N_s)^3=%.0f to N=%d' % (ns, d, t, cores, scale, n)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

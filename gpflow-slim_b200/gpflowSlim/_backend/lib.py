@@ -92,7 +92,7 @@ SIGNATURES = {
 }
 
 _lib = None
-_lock = threading.Lock()
+_lock = threading.RLock()
 _handles = {}
 
 

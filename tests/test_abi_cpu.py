@@ -51,3 +51,17 @@ def test_no_cpu_fallback():
     k = gpf.kernels.RBF(2)
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         k.K(torch.zeros(3, 2, dtype=torch.float64))
+
+
+def test_first_handle_request_does_not_deadlock():
+    """Regression: the very first handle_for() call loads the library under the module lock."""
+    import subprocess
+    import sys
+    code = ('import sys; sys.path.insert(0, %r); import torch\n'
+            'from gpflowSlim._backend import lib\n'
+            'try:\n'
+            '    lib.handle_for(torch.device("cuda", 0)); print("HANDLE")\n'
+            'except RuntimeError as e:\n'
+            '    print("RAISED")\n') % os.path.join(ROOT, 'gpflow-slim_b200')
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120)
+    assert ('RAISED' in out.stdout) or ('HANDLE' in out.stdout), out.stderr[-2000:]
