@@ -275,9 +275,10 @@ class _Gram(torch.autograd.Function):
         h = handle_for(X)
         n, m = X.shape[0], (X.shape[0] if X2 is None else X2.shape[0])
         K = torch.empty((n, m), dtype=F64, device=X.device)
-        vt, vx, vx2, vk = view(theta), view(X), view(X2), view(K)
-        h.check(h.lib.gps_gram_fwd(h.ptr, ctypes.byref(prog.desc), vt.ref, vx.ref, ref(vx2),
-                                   float(diag_add), 0, vk.ref))
+        if n and m:
+            vt, vx, vx2, vk = view(theta), view(X), view(X2), view(K)
+            h.check(h.lib.gps_gram_fwd(h.ptr, ctypes.byref(prog.desc), vt.ref, vx.ref, ref(vx2),
+                                       float(diag_add), 0, vk.ref))
         ctx.save_for_backward(theta, X, X2 if X2 is not None else torch.empty(0))
         ctx.prog = prog
         ctx.has_x2 = X2 is not None
@@ -292,6 +293,10 @@ class _Gram(torch.autograd.Function):
         h = handle_for(X)
         need_dx = ctx.needs_input_grad[1]
         need_dx2 = ctx.has_x2 and ctx.needs_input_grad[2]
+        if W.numel() == 0:
+            return (torch.zeros(prog.n_theta, dtype=F64, device=X.device),
+                    torch.zeros_like(X) if need_dx else None,
+                    torch.zeros_like(X2) if need_dx2 else None, None, None)
         dtheta = torch.empty(prog.n_theta, dtype=F64, device=X.device)
         dX = torch.empty_like(X) if need_dx else None
         if not ctx.has_x2:
@@ -324,8 +329,9 @@ class _Kdiag(torch.autograd.Function):
         X, theta = _prep(X), _prep(theta)
         h = handle_for(X)
         out = torch.empty(X.shape[0], dtype=F64, device=X.device)
-        vt, vx, vo = view(theta), view(X), view(out)
-        h.check(h.lib.gps_kdiag_fwd(h.ptr, ctypes.byref(prog.desc), vt.ref, vx.ref, vo.ref))
+        if X.shape[0]:
+            vt, vx, vo = view(theta), view(X), view(out)
+            h.check(h.lib.gps_kdiag_fwd(h.ptr, ctypes.byref(prog.desc), vt.ref, vx.ref, vo.ref))
         ctx.save_for_backward(theta, X)
         ctx.prog = prog
         return out
