@@ -36,6 +36,8 @@ enum WsSlot {
   WS_MISC,
   WS_INFO,
   WS_THETA,
+  WS_INVW,        // triangular inverse: W = -U11 L21^T of the current recursion node
+  WS_INVT,        // triangular inverse: T22 = U22^T of the current recursion node
   WS_COUNT
 };
 
@@ -46,6 +48,7 @@ struct gps_handle {
   cudaStream_t stream = 0;
   std::string err;
   int gemm_impl = 0;
+  int leaf_impl = 0;   // 0 = blocked DMMA leaf, 1 = simple check kernel
   int profile = 0;
   void* ws_ptr[WS_COUNT] = {};
   size_t ws_bytes[WS_COUNT] = {};

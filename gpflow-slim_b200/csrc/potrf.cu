@@ -162,6 +162,227 @@ potrf_base_kernel(double* __restrict__ Abase, int64_t lda, int n_total, double* 
   }
 }
 
+// ------------------------------------------------------------------ 128x128 leaf, blocked (DMMA)
+// The production leaf.  Right-looking Cholesky over 8-column panels entirely in shared memory:
+//   * the 8x8 diagonal block is factored AND inverted by warp 0 in registers (row per lane,
+//     warp shuffles), one panel ahead of everybody else (look-ahead inside the CTA);
+//   * panel solve  X = B Td^T  and trailing update  C -= X X^T  are m8n8k4 DMMAs on 8x8 tiles,
+//     spread over the 8 warps;
+// then T = L^-1 by block forward substitution (one block column per warp, DMMA products,
+// T_ij kept transposed in the unused strict upper triangle of the same array).
+constexpr int LLD = 132;   // 132 = 4 mod 16: conflict-free m8n8k4 fragment loads
+constexpr int LEAF_SMEM = (NB * LLD + 16 * 64 + 8 * 64 + 32) * (int)sizeof(double);
+
+// inverse of the 8x8 lower block at S[c0.., c0..] -> Tdp[i*8 + c]; lane c = lane & 7 owns column c
+__device__ __forceinline__ void inv8(const double* S, double* Tdp, int c0, int lane, double myrinv) {
+  const int c = lane & 7;
+  double t[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    double sacc = 0.0;
+#pragma unroll
+    for (int k = 0; k < i; ++k) sacc = fma(S[(c0 + i) * LLD + c0 + k], t[k], sacc);
+    double ri = __shfl_sync(0xffffffffu, myrinv, i);
+    t[i] = (i == c) ? ri : ((i > c) ? -sacc * ri : 0.0);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) Tdp[i * 8 + c] = t[i];
+  }
+}
+
+// Cholesky + inverse of the 8x8 diagonal block (executed by one full warp)
+__device__ __forceinline__ void factor8(double* S, double* Tdp, int c0, int lane, int* s_bad) {
+  const int l = lane & 7;
+  double a[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) a[c] = (c <= l) ? S[(c0 + l) * LLD + c0 + c] : 0.0;
+  double myrinv = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    double akk = __shfl_sync(0xffffffffu, a[k], k);
+    if (!(akk > 0.0) && lane == 0 && *s_bad == 0) *s_bad = c0 + k + 1;
+    double rinv = rsqrt(akk);
+    double rk = akk * rinv;
+    if (l == k) {
+      a[k] = rk;
+      myrinv = rinv;
+    } else {
+      a[k] *= rinv;
+    }
+#pragma unroll
+    for (int c = k + 1; c < 8; ++c) {
+      double lck = __shfl_sync(0xffffffffu, a[k], c);
+      a[c] = fma(-a[k], lck, a[c]);
+    }
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c <= l) S[(c0 + l) * LLD + c0 + c] = a[c];
+  }
+  __syncwarp();
+  inv8(S, Tdp, c0, lane, myrinv);
+}
+
+template <bool DO_CHOL>
+__global__ void __launch_bounds__(256, 1)
+potrf_leaf_kernel(double* __restrict__ Abase, int64_t lda, int n_total, double* __restrict__ tinv,
+                  double* __restrict__ logdet, int* __restrict__ info, int row0,
+                  double* __restrict__ Ubase, int64_t ldu) {
+  extern __shared__ __align__(16) double sm[];
+  double* S = sm;                    // [NB][LLD]
+  double* Td = S + NB * LLD;         // [16][8][8] inverses of the diagonal 8x8 blocks
+  double* scr = Td + 16 * 64;        // [8 warps][8][8]
+  double* red = scr + 8 * 64;        // [32]
+  __shared__ int s_bad;
+  const int blk = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
+  const int n = min(NB, n_total - blk * NB);
+  double* A = Abase + (int64_t)blk * NB * (lda + 1);
+
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    int i = idx >> 7, j = idx & (NB - 1);
+    double v = (i == j) ? 1.0 : 0.0;
+    if (i < n && j <= i) v = A[(int64_t)i * lda + j];
+    S[i * LLD + j] = v;
+  }
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+
+  if (DO_CHOL) {
+    if (warp == 0) factor8(S, Td, 0, lane, &s_bad);
+    __syncthreads();
+    for (int p = 0; p < 16; ++p) {
+      const int c0 = 8 * p;
+      // (a) panel solve: tile rows bi > p
+      for (int bi = p + 1 + warp; bi < 16; bi += 8) {
+        const double* ap = S + (8 * bi + lr) * LLD + c0 + lc;
+        const double* tp = Td + p * 64 + lr * 8 + lc;
+        double x0 = 0.0, x1 = 0.0;
+        double a0 = ap[0], a1 = ap[4], b0 = tp[0], b1 = tp[4];
+        dmma884(x0, x1, a0, b0);
+        dmma884(x0, x1, a1, b1);
+        *reinterpret_cast<double2*>(S + (8 * bi + lr) * LLD + c0 + 2 * lc) = make_double2(x0, x1);
+      }
+      __syncthreads();
+      if (p == 15) break;
+      // (b) trailing update with panel p; warp 0 runs one panel ahead on the diagonal
+      const int m = 15 - p;
+      const int ntiles = m * (m + 1) / 2;
+      const int tstart = (warp == 0) ? 0 : warp;
+      const int tstep = (warp == 0) ? ntiles : 7;     // warp 0 takes tile 0 only
+      for (int t = tstart; t < ntiles; t += tstep) {
+        int r = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        while (r * (r + 1) / 2 > t) --r;
+        while ((r + 1) * (r + 2) / 2 <= t) ++r;
+        const int c = t - r * (r + 1) / 2;
+        const int bi = p + 1 + r, bj = p + 1 + c;
+        const double* ap = S + (8 * bi + lr) * LLD + c0 + lc;
+        const double* bp = S + (8 * bj + lr) * LLD + c0 + lc;
+        double2* cp = reinterpret_cast<double2*>(S + (8 * bi + lr) * LLD + 8 * bj + 2 * lc);
+        double a0 = -ap[0], a1 = -ap[4], b0 = bp[0], b1 = bp[4];
+        double2 cv = *cp;
+        dmma884(cv.x, cv.y, a0, b0);
+        dmma884(cv.x, cv.y, a1, b1);
+        *cp = cv;
+      }
+      if (warp == 0) {
+        __syncwarp();
+        factor8(S, Td + (p + 1) * 64, 8 * (p + 1), lane, &s_bad);
+      }
+      __syncthreads();
+    }
+    if (tid == 0 && s_bad != 0 && s_bad <= n) {
+      int val = row0 + blk * NB + s_bad;
+      int old = atomicCAS(info, 0, val);
+      if (old != 0 && old > val) atomicMin(info, val);
+    }
+  } else {
+    for (int b = 2 * warp; b < 2 * warp + 2; ++b) {
+      const int l = lane & 7;
+      double myrinv = 1.0 / S[(8 * b + l) * LLD + 8 * b + l];
+      inv8(S, Td + b * 64, 8 * b, lane, myrinv);
+    }
+    __syncthreads();
+  }
+
+  // T = L^-1: block column j by one warp; T_ij (i > j) stored transposed at S[8j.., 8i..]
+  for (int jj = 0; jj < 2; ++jj) {
+    const int j = (jj == 0) ? warp : 15 - warp;
+    double* sc = scr + warp * 64;
+    for (int i = j + 1; i < 16; ++i) {
+      double c0a = 0.0, c1a = 0.0, c0b = 0.0, c1b = 0.0;
+      {
+        const double* ap = S + (8 * i + lr) * LLD + 8 * j + lc;
+        const double* bp = Td + j * 64 + lc * 8 + lr;
+        dmma884(c0a, c1a, ap[0], bp[0]);
+        dmma884(c0b, c1b, ap[4], bp[32]);
+      }
+      for (int k = j + 1; k < i; ++k) {
+        const double* ap = S + (8 * i + lr) * LLD + 8 * k + lc;
+        const double* bp = S + (8 * j + lr) * LLD + 8 * k + lc;
+        dmma884(c0a, c1a, ap[0], bp[0]);
+        dmma884(c0b, c1b, ap[4], bp[4]);
+      }
+      sc[lr * 8 + 2 * lc] = c0a + c0b;
+      sc[lr * 8 + 2 * lc + 1] = c1a + c1b;
+      __syncwarp();
+      double t0 = 0.0, t1 = 0.0;
+      const double* tp = Td + i * 64 + lr * 8 + lc;
+      dmma884(t0, t1, tp[0], sc[lc * 8 + lr]);
+      dmma884(t0, t1, tp[4], sc[(lc + 4) * 8 + lr]);
+      __syncwarp();
+      S[(8 * j + 2 * lc) * LLD + 8 * i + lr] = -t0;
+      S[(8 * j + 2 * lc + 1) * LLD + 8 * i + lr] = -t1;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  if (DO_CHOL) {
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+      int r = idx >> 7, cc = idx & (NB - 1);
+      if (r < n && cc <= r) A[(int64_t)r * lda + cc] = S[r * LLD + cc];
+    }
+  }
+  if (tinv) {
+    double* T = tinv + (int64_t)blk * NB * NB;
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+      int r = idx >> 7, cc = idx & (NB - 1);
+      double v = 0.0;
+      if ((r >> 3) == (cc >> 3)) v = Td[(r >> 3) * 64 + (r & 7) * 8 + (cc & 7)];
+      else if (cc < r) v = S[cc * LLD + r];
+      T[idx] = v;
+    }
+  }
+  if (Ubase) {
+    double* U = Ubase + (int64_t)blk * NB * (ldu + 1);
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+      int r = idx >> 7, cc = idx & (NB - 1);
+      if (r < n && cc < n) {
+        double v = 0.0;   // U[r][cc] = T[cc][r]
+        if ((r >> 3) == (cc >> 3)) v = Td[(r >> 3) * 64 + (cc & 7) * 8 + (r & 7)];
+        else if (cc > r) v = S[r * LLD + cc];
+        U[(int64_t)r * ldu + cc] = v;
+      }
+    }
+  }
+  if (logdet) {
+    double sdet = 0.0;
+    if (tid < n) sdet = log(S[tid * LLD + tid]);
+    sdet = warp_sum(sdet);
+    if (lane == 0) red[warp] = sdet;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += red[w];
+      logdet[blk] = t;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ strip TRSM on DMMA
 // B[r0:r0+64, 0:n] <- B[r0:r0+64, 0:n] * T^T   (T = 128x128 dense inverse of the diagonal
 // block, lower triangular with explicit zeros above the diagonal).  In place: a CTA reads
@@ -177,18 +398,19 @@ trsm_strip_kernel(double* __restrict__ B, int64_t ldb, int m, int n, const doubl
   double* Bs = sm + NB * TS_LD;     // [STRIP][TS_LD]
   const int tid = threadIdx.x;
   const int r0 = blockIdx.x * STRIP;
+  // all copies in flight at once (cp.async): T in 16-byte chunks, the strip in 8-byte ones
+  // (a user-supplied B may have an odd leading dimension)
   for (int idx = tid; idx < NB * NB / 2; idx += 256) {
     int r = idx >> 6, c2 = (idx & 63) * 2;
-    double2 v = *reinterpret_cast<const double2*>(T + r * NB + c2);
-    Ts[r * TS_LD + c2] = v.x;
-    Ts[r * TS_LD + c2 + 1] = v.y;
+    cp_async16(Ts + r * TS_LD + c2, T + r * NB + c2, 16);
   }
   for (int idx = tid; idx < STRIP * NB; idx += 256) {
     int r = idx >> 7, c = idx & (NB - 1);
-    double v = 0.0;
-    if (r0 + r < m && c < n) v = B[(int64_t)(r0 + r) * ldb + c];
-    Bs[r * TS_LD + c] = v;
+    bool ok = (r0 + r < m) && (c < n);
+    cp_async8(Bs + r * TS_LD + c, ok ? B + (int64_t)(r0 + r) * ldb + c : B, ok ? 8 : 0);
   }
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
   const int lr = lane >> 2, lc = lane & 3;
@@ -232,6 +454,8 @@ void set_attrs() {
   cudaFuncSetAttribute(potrf_base_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BASE_SMEM);
   cudaFuncSetAttribute(potrf_base_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BASE_SMEM);
   cudaFuncSetAttribute(trsm_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STRIP_SMEM);
+  cudaFuncSetAttribute(potrf_leaf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM);
+  cudaFuncSetAttribute(potrf_leaf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM);
   g_attr_set = true;
 }
 
@@ -257,9 +481,14 @@ int gps_potrf_rec(gps_handle* h, Mat A, int64_t n, int64_t below, int64_t blk0, 
   if (n <= 0) return 0;
   if (n <= NB) {
     set_attrs();
-    potrf_base_kernel<true><<<1, BASE_THREADS, BASE_SMEM, h->stream>>>(
-        A.p, A.ld, (int)n, tinv + blk0 * NB * NB, logdet ? logdet + blk0 : nullptr, info_dev,
-        (int)row0, nullptr, 0);
+    if (h->leaf_impl == 1)
+      potrf_base_kernel<true><<<1, BASE_THREADS, BASE_SMEM, h->stream>>>(
+          A.p, A.ld, (int)n, tinv + blk0 * NB * NB, logdet ? logdet + blk0 : nullptr, info_dev,
+          (int)row0, nullptr, 0);
+    else
+      potrf_leaf_kernel<true><<<1, 256, LEAF_SMEM, h->stream>>>(
+          A.p, A.ld, (int)n, tinv + blk0 * NB * NB, logdet ? logdet + blk0 : nullptr, info_dev,
+          (int)row0, nullptr, 0);
     GPS_LAUNCH_CHECK(h);
     if (below > 0) {
       if ((rc = strip_launch(h, A.sub(n, 0, below, n), n, tinv + blk0 * NB * NB))) return rc;
@@ -295,8 +524,12 @@ int gps_block_inverses(gps_handle* h, Mat L, double* tinv) {
   if (L.rows <= 0) return 0;
   set_attrs();
   unsigned nblk = (unsigned)((L.rows + NB - 1) / NB);
-  potrf_base_kernel<false><<<nblk, BASE_THREADS, BASE_SMEM, h->stream>>>(
-      L.p, L.ld, (int)L.rows, tinv, nullptr, nullptr, 0, nullptr, 0);
+  if (h->leaf_impl == 1)
+    potrf_base_kernel<false><<<nblk, BASE_THREADS, BASE_SMEM, h->stream>>>(
+        L.p, L.ld, (int)L.rows, tinv, nullptr, nullptr, 0, nullptr, 0);
+  else
+    potrf_leaf_kernel<false><<<nblk, 256, LEAF_SMEM, h->stream>>>(
+        L.p, L.ld, (int)L.rows, tinv, nullptr, nullptr, 0, nullptr, 0);
   GPS_LAUNCH_CHECK(h);
   return 0;
 }
@@ -326,12 +559,21 @@ int gps_inv_upper_rec(gps_handle* h, Mat L, Mat U, int64_t blk0, const double* t
   if ((rc = gps_inv_upper_rec(h, L.sub(0, 0, n1, n1), U.sub(0, 0, n1, n1), blk0, tinv))) return rc;
   if ((rc = gps_inv_upper_rec(h, L.sub(n1, n1, n2, n2), U.sub(n1, n1, n2, n2), blk0 + n1 / NB, tinv)))
     return rc;
-  // U12 = -U11 * L21^T, then U12 <- U12 * L22^-T
+  // U12 = -(U11 L21^T) U22.  Both products are triangular-aware NT GEMMs (n^3/3 flops overall):
+  //   W   = -U11 L21^T                      (U11 upper)       -> scratch
+  //   U12 =  W T22^T with T22 = U22^T       (T22 lower)       -> in place in U
+  // T22 is produced by an O(n^2) transpose; its garbage upper tiles are never read.
   Mat U12 = U.sub(0, n1, n1, n2);
-  if ((rc = gps_gemm_nt_launch(h, -1.0, U.sub(0, 0, n1, n1), L.sub(n1, 0, n2, n1), 0.0, U12,
+  const int64_t ldw = (n2 + 15) / 16 * 16;
+  double* wbuf = (double*)gps_ws(h, WS_INVW, (size_t)n1 * ldw * sizeof(double));
+  double* tbuf = (double*)gps_ws(h, WS_INVT, (size_t)n2 * ldw * sizeof(double));
+  if (!wbuf || !tbuf) return -102;
+  Mat W(wbuf, n1, n2, ldw), T22(tbuf, n2, n2, ldw);
+  if ((rc = gps_gemm_nt_launch(h, -1.0, U.sub(0, 0, n1, n1), L.sub(n1, 0, n2, n1), 0.0, W,
                                TRI_UPPER, TRI_NONE, C_ALL)))
     return rc;
-  return gps_trsm_rec(h, L.sub(n1, n1, n2, n2), U12, blk0 + n1 / NB, tinv);
+  if ((rc = gps_transpose_launch(h, U.sub(n1, n1, n2, n2), T22))) return rc;
+  return gps_gemm_nt_launch(h, 1.0, W, T22, 0.0, U12, TRI_NONE, TRI_LOWER, C_ALL);
 }
 
 static int u_diag_launch(gps_handle* h, const double* tinv, Mat U) {
@@ -344,6 +586,14 @@ static int u_diag_launch(gps_handle* h, const double* tinv, Mat U) {
 
 int gps_inv_upper_full(gps_handle* h, Mat L, Mat U, const double* tinv) {
   int rc;
+  if (L.rows > NB) {
+    // size the per-node scratch for the top node up front (it is the largest)
+    int64_t n1 = split_point(L.rows), n2 = L.rows - n1;
+    int64_t ldw = (n2 + 15) / 16 * 16;
+    if (!gps_ws(h, WS_INVW, (size_t)n1 * ldw * sizeof(double)) ||
+        !gps_ws(h, WS_INVT, (size_t)n2 * ldw * sizeof(double)))
+      return -102;
+  }
   if ((rc = u_diag_launch(h, tinv, U))) return rc;
   return gps_inv_upper_rec(h, L, U, 0, tinv);
 }

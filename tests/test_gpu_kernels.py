@@ -65,10 +65,22 @@ def test_gemm_nt_triangular_modes(n):
     assert_close(low, np.tril(Up @ Up.T), 1e-13, 'UU^T lower only')
 
 
+@pytest.mark.parametrize('leaf', [0, 1])
 @pytest.mark.parametrize('n', [1, 2, 31, 127, 128, 129, 255, 256, 300, 641, 1500])
-def test_potrf_trsm_inverse(n):
+def test_potrf_trsm_inverse(n, leaf):
+    """leaf=0: blocked DMMA leaf kernel (production); leaf=1: simple check kernel."""
     ops = _ops()
+    from gpflowSlim._backend.lib import handle_for
     S = _spd(n, seed=n)
+    h = handle_for(conv(S))
+    h.set_option('leaf_impl', leaf)
+    try:
+        _check_potrf_trsm_inverse(ops, S, n)
+    finally:
+        h.set_option('leaf_impl', 0)
+
+
+def _check_potrf_trsm_inverse(ops, S, n):
     L = ops.potrf(conv(S))
     Lref = np.linalg.cholesky(S)
     assert_close(L, Lref, 1e-12, 'potrf n=%d' % n)
