@@ -32,6 +32,10 @@ struct GemmArgs {
   double alpha, beta;
   int a_tri, b_tri, c_uplo;
   int tiles_m, tiles_n;
+  // C_ROWMAP: element (r, c) is updated iff c + coff <= rowlim[r]; rowlim is non-decreasing
+  // (block-row distributions: rowlim[r] = global row index of local row r)
+  const int64_t* rowlim;
+  int64_t coff;
 };
 
 __device__ __forceinline__ void tile_coords(const GemmArgs& g, int bid, int& ti, int& tj) {
@@ -113,6 +117,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_dmma_kernel(const Gem
   tile_coords(g, blockIdx.x, ti, tj);
   const int m0 = ti * BM, n0 = tj * BN;
   if (g.c_uplo == C_LOWER && m0 + BM - 1 < n0) return;  // tile entirely above the diagonal
+  if (g.c_uplo == C_ROWMAP && (int64_t)n0 + g.coff > g.rowlim[min(m0 + BM, g.M) - 1]) return;
 
   int klo, khi;
   k_range(g, ti, tj, klo, khi);
@@ -165,6 +170,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_dmma_kernel(const Gem
   // epilogue
   const bool vec_ok = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
   const bool diag_tile = (g.c_uplo == C_LOWER) && (n0 + BN - 1 > m0);
+  if (g.c_uplo == C_ROWMAP) {
+    // block-row distributed lower update: per-row column limit
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int row = m0 + wm * 64 + i * 8 + lr;
+      if (row >= g.M) continue;
+      const int64_t lim = g.rowlim[row] - g.coff;   // last column this row may touch
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int col = n0 + wn * 32 + j * 8 + lc * 2;
+        if (col >= g.N) continue;
+        double* cp = g.C + (int64_t)row * g.ldc + col;
+        const double v0 = g.alpha * acc[i][j][0], v1 = g.alpha * acc[i][j][1];
+        if (col <= lim) cp[0] = (g.beta != 0.0) ? fma(g.beta, cp[0], v0) : v0;
+        if (col + 1 < g.N && col + 1 <= lim) cp[1] = (g.beta != 0.0) ? fma(g.beta, cp[1], v1) : v1;
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     int row = m0 + wm * 64 + i * 8 + lr;
@@ -199,6 +223,7 @@ __global__ void gemm_nt_naive_kernel(const GemmArgs g) {
   int row = blockIdx.y * 16 + threadIdx.y;
   if (row >= g.M || col >= g.N) return;
   if (g.c_uplo == C_LOWER && col > row) return;
+  if (g.c_uplo == C_ROWMAP && (int64_t)col + g.coff > g.rowlim[row]) return;
   int klo = 0, khi = g.K;
   if (g.a_tri == TRI_LOWER) khi = min(khi, row + 1);
   if (g.a_tri == TRI_UPPER) klo = max(klo, row);
@@ -227,7 +252,7 @@ double gemm_flops(const GemmArgs& g) {
 }  // namespace
 
 int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, Mat C, int a_tri,
-                       int b_tri, int c_uplo) {
+                       int b_tri, int c_uplo, const int64_t* rowlim, int64_t coff, double flops) {
   if (A.cols != B.cols) return gps_fail(h, -3, "gemm_nt: K mismatch (%lld vs %lld)",
                                         (long long)A.cols, (long long)B.cols);
   if (C.rows != A.rows || C.cols != B.rows) return gps_fail(h, -6, "gemm_nt: C shape mismatch");
@@ -242,6 +267,8 @@ int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, M
   g.a_tri = a_tri; g.b_tri = b_tri; g.c_uplo = c_uplo;
   g.tiles_m = (g.M + BM - 1) / BM;
   g.tiles_n = (g.N + BN - 1) / BN;
+  g.rowlim = rowlim; g.coff = coff;
+  if (c_uplo == C_ROWMAP && !rowlim) return gps_fail(h, -7, "gemm_nt: C_ROWMAP needs a row-limit array");
 
   GemmEvent* ev = nullptr;
   if (h->profile) {
@@ -253,7 +280,7 @@ int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, M
       h->events.push_back(e);
     }
     ev = &h->events[h->events_used++];
-    ev->flops = gemm_flops(g);
+    ev->flops = flops >= 0.0 ? flops : gemm_flops(g);
     cudaEventRecord(ev->a, h->stream);
   }
 
@@ -295,4 +322,20 @@ extern "C" int gps_gemm_nt(gps_handle* h, double alpha, const DLTensor* A, const
     return gps_fail(h, -7, "gemm_nt: bad tri/uplo flag");
   GPS_CUDA(h, cudaSetDevice(h->device));
   return gps_gemm_nt_launch(h, alpha, a, b, beta, c, a_tri, b_tri, c_uplo);
+}
+
+extern "C" int gps_gemm_nt_rowmap(gps_handle* h, double alpha, const DLTensor* A, const DLTensor* B,
+                                  double beta, DLTensor* C, const DLTensor* row_limit,
+                                  int64_t col_offset, double flops) {
+  if (!h) return -1;
+  Mat a, b, c;
+  int rc;
+  const int64_t* lim;
+  if ((rc = gps_as_mat(h, A, 3, "A", &a, false))) return rc;
+  if ((rc = gps_as_mat(h, B, 4, "B", &b, false))) return rc;
+  if ((rc = gps_as_mat(h, C, 6, "C", &c, false))) return rc;
+  if ((rc = gps_as_i64(h, row_limit, 7, "row_limit", c.rows, &lim))) return rc;
+  GPS_CUDA(h, cudaSetDevice(h->device));
+  return gps_gemm_nt_launch(h, alpha, a, b, beta, c, TRI_NONE, TRI_NONE, C_ROWMAP, lim, col_offset,
+                            flops);
 }

@@ -70,6 +70,32 @@ __global__ void var_kernel(const double* __restrict__ kdiag, const double* __res
   if (i < n) var[i] = kdiag[i] - ss[i];
 }
 
+// Row-panel form of W = 1/2 (R K^-1 - beta beta^T) for a block-row distributed K^-1: row r of
+// the panel is global row g = grow[r] and holds K^-1[g, j] for j >= c0 (c0 = first column of
+// g's distribution block).  By symmetry, entries right of the diagonal block stand for (g, j)
+// and (j, g): they weigh double; entries left of c0 are not this rank's and become zero.
+__global__ void gpr_weight_rows_kernel(double* __restrict__ W, int64_t ldw, int64_t m, int64_t N,
+                                       const int64_t* __restrict__ grow, const double* __restrict__ beta,
+                                       int64_t ldb, int R, int64_t bs) {
+  const int64_t r = blockIdx.y;
+  if (r >= m) return;
+  const int64_t g = grow[r];
+  const int64_t c0 = g / bs * bs, c1 = c0 + bs;
+  double bg[16];
+  for (int q = 0; q < R; ++q) bg[q] = beta[(int64_t)q * ldb + g];
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < N;
+       j += (int64_t)gridDim.x * blockDim.x) {
+    double v = 0.0;
+    if (j >= c0) {
+      double bb = 0.0;
+      for (int q = 0; q < R; ++q) bb = fma(bg[q], beta[(int64_t)q * ldb + j], bb);
+      v = 0.5 * ((double)R * W[r * ldw + j] - bb);
+      if (j >= c1) v *= 2.0;
+    }
+    W[r * ldw + j] = v;
+  }
+}
+
 int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 // Build K + noise I (lower) and Yc^T into the work matrix and factor it.
@@ -172,6 +198,31 @@ int gps_gpr_nlml_fwd_bwd(gps_handle* h, const gps_kernel_desc* desc, const DLTen
     GPS_LAUNCH_CHECK(h);
   }
   return read_info(h, info, info_host);
+}
+
+int gps_gpr_weight_rows(gps_handle* h, DLTensor* W_inout, const DLTensor* row_index,
+                        const DLTensor* beta_t, int64_t block) {
+  if (!h) return -1;
+  Mat W, B;
+  const int64_t* grow;
+  int rc;
+  if ((rc = gps_as_mat(h, W_inout, 2, "W_inout", &W, false))) return rc;
+  if ((rc = gps_as_i64(h, row_index, 3, "row_index", W.rows, &grow))) return rc;
+  if ((rc = gps_as_mat(h, beta_t, 4, "beta", &B, false))) return rc;
+  if (B.cols != W.cols) return gps_fail(h, -4, "beta must be R x %lld", (long long)W.cols);
+  if (B.rows < 1 || B.rows > 16) return gps_fail(h, -4, "beta must have 1..16 rows");
+  if (block < 1) return gps_fail(h, -5, "block must be positive");
+  GPS_CUDA(h, cudaSetDevice(h->device));
+  if (W.rows == 0 || W.cols == 0) return 0;
+  if (W.rows > 65535 * 64) return gps_fail(h, -2, "too many rows");
+  for (int64_t r0 = 0; r0 < W.rows; r0 += 65535) {
+    int64_t mr = W.rows - r0 < 65535 ? W.rows - r0 : 65535;
+    dim3 grid((unsigned)((W.cols + 1023) / 1024 < 64 ? (W.cols + 1023) / 1024 : 64), (unsigned)mr);
+    gpr_weight_rows_kernel<<<grid, 256, 0, h->stream>>>(W.p + r0 * W.ld, W.ld, mr, W.cols, grow + r0,
+                                                        B.p, B.ld, (int)B.rows, block);
+    GPS_LAUNCH_CHECK(h);
+  }
+  return 0;
 }
 
 int gps_gpr_predict(gps_handle* h, const gps_kernel_desc* desc, const DLTensor* theta,

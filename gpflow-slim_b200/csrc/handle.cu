@@ -78,6 +78,21 @@ int gps_as_mat(gps_handle* h, const DLTensor* t, int argidx, const char* name, M
                   t->ndim);
 }
 
+int gps_as_i64(gps_handle* h, const DLTensor* t, int argidx, const char* name, int64_t n,
+               const int64_t** out) {
+  if (!t || !t->data) return gps_fail(h, -argidx, "argument %d (%s): null tensor", argidx, name);
+  if (t->device.device_type != 2 || t->device.device_id != h->device)
+    return gps_fail(h, -argidx, "argument %d (%s): must be a CUDA tensor on device %d", argidx, name,
+                    h->device);
+  if (t->dtype.code != 0 /*kDLInt*/ || t->dtype.bits != 64 || t->dtype.lanes != 1)
+    return gps_fail(h, -argidx, "argument %d (%s): dtype must be int64", argidx, name);
+  if (t->ndim != 1 || t->shape[0] != n || (t->strides && n > 1 && t->strides[0] != 1))
+    return gps_fail(h, -argidx, "argument %d (%s): need a contiguous vector of %lld entries", argidx,
+                    name, (long long)n);
+  *out = reinterpret_cast<const int64_t*>(reinterpret_cast<char*>(t->data) + t->byte_offset);
+  return 0;
+}
+
 extern "C" {
 
 int gps_version(void) { return 100; }

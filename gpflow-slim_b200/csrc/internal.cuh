@@ -82,14 +82,20 @@ void* gps_ws(gps_handle* h, int slot, size_t bytes);  // nullptr on failure (err
 // argument checking: returns 0 or sets the error and returns -(argidx)
 int gps_as_mat(gps_handle* h, const DLTensor* t, int argidx, const char* name, Mat* out,
                bool allow_vec = true);
+// contiguous int64 device vector with exactly n entries
+int gps_as_i64(gps_handle* h, const DLTensor* t, int argidx, const char* name, int64_t n,
+               const int64_t** out);
 
 // ----------------------------------------------------------------------------- GEMM family
 enum { TRI_NONE = 0, TRI_LOWER = 1, TRI_UPPER = 2 };
-enum { C_ALL = 0, C_LOWER = 1 };
+enum { C_ALL = 0, C_LOWER = 1, C_ROWMAP = 2 };
 
 // C = alpha * A * B^T + beta * C   (A: MxK, B: NxK, C: MxN, all row-major)
+// c_uplo == C_ROWMAP: element (r, c) is updated iff c + coff <= rowlim[r] (device array,
+// non-decreasing).  flops >= 0 overrides the profile's flop count for this launch.
 int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, Mat C, int a_tri,
-                       int b_tri, int c_uplo);
+                       int b_tri, int c_uplo, const int64_t* rowlim = nullptr, int64_t coff = 0,
+                       double flops = -1.0);
 
 // ----------------------------------------------------------------------------- factorisation
 // Factor the n x n block at A (lower, in place) and solve the `below` rows under it:

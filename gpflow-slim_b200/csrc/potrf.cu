@@ -391,6 +391,10 @@ constexpr int TS_LD = 132;   // 132 = 4 mod 16 -> conflict-free DMMA fragment lo
 constexpr int STRIP = 64;
 constexpr int STRIP_SMEM = (NB + STRIP) * TS_LD * (int)sizeof(double);
 
+// NOTRANS = false:  B <- B T^T   (forward solve  B L^-T, T = L_kk^-1 lower)
+// NOTRANS = true :  B <- B T     (solve against the untransposed factor, B L^-1): the tile is
+//                   staged transposed, i.e. the kernel multiplies by (T^T)^T with T^T upper.
+template <bool NOTRANS>
 __global__ void __launch_bounds__(256, 1)
 trsm_strip_kernel(double* __restrict__ B, int64_t ldb, int m, int n, const double* __restrict__ T) {
   extern __shared__ __align__(16) double sm[];
@@ -400,9 +404,16 @@ trsm_strip_kernel(double* __restrict__ B, int64_t ldb, int m, int n, const doubl
   const int r0 = blockIdx.x * STRIP;
   // all copies in flight at once (cp.async): T in 16-byte chunks, the strip in 8-byte ones
   // (a user-supplied B may have an odd leading dimension)
-  for (int idx = tid; idx < NB * NB / 2; idx += 256) {
-    int r = idx >> 6, c2 = (idx & 63) * 2;
-    cp_async16(Ts + r * TS_LD + c2, T + r * NB + c2, 16);
+  if (NOTRANS) {
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+      int r = idx >> 7, c = idx & (NB - 1);
+      Ts[c * TS_LD + r] = T[idx];   // Ts = T^T (upper); T is L2-resident (128 KiB)
+    }
+  } else {
+    for (int idx = tid; idx < NB * NB / 2; idx += 256) {
+      int r = idx >> 6, c2 = (idx & 63) * 2;
+      cp_async16(Ts + r * TS_LD + c2, T + r * NB + c2, 16);
+    }
   }
   for (int idx = tid; idx < STRIP * NB; idx += 256) {
     int r = idx >> 7, c = idx & (NB - 1);
@@ -421,13 +432,15 @@ trsm_strip_kernel(double* __restrict__ B, int64_t ldb, int m, int n, const doubl
   for (int a = 0; a < 2; ++a)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[a][j][0] = acc[a][j][1] = 0.0;
-  const int kend = min(n, nbase + 64);  // T[c][k] == 0 for k > c
-  for (int k0 = 0; k0 < kend; k0 += 4) {
+  // lower tile: Ts[c][k] == 0 for k > c; upper tile (NOTRANS): Ts[c][k] == 0 for k < c
+  const int kbeg = NOTRANS ? nbase : 0;
+  const int kend = NOTRANS ? n : min(n, nbase + 64);
+  for (int k0 = kbeg; k0 < kend; k0 += 4) {
     double a0 = Bs[(mrow + lr) * TS_LD + k0 + lc];
     double a1 = Bs[(mrow + 8 + lr) * TS_LD + k0 + lc];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      if (k0 <= nbase + j * 8 + 7) {     // warp-uniform
+      if (NOTRANS ? (k0 + 3 >= nbase + j * 8) : (k0 <= nbase + j * 8 + 7)) {     // warp-uniform
         double b = Ts[(nbase + j * 8 + lr) * TS_LD + k0 + lc];
         dmma884(acc[0][j][0], acc[0][j][1], a0, b);
         dmma884(acc[1][j][0], acc[1][j][1], a1, b);
@@ -453,7 +466,8 @@ void set_attrs() {
   if (g_attr_set) return;
   cudaFuncSetAttribute(potrf_base_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BASE_SMEM);
   cudaFuncSetAttribute(potrf_base_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BASE_SMEM);
-  cudaFuncSetAttribute(trsm_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STRIP_SMEM);
+  cudaFuncSetAttribute(trsm_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRIP_SMEM);
+  cudaFuncSetAttribute(trsm_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRIP_SMEM);
   cudaFuncSetAttribute(potrf_leaf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM);
   cudaFuncSetAttribute(potrf_leaf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM);
   g_attr_set = true;
@@ -464,13 +478,23 @@ int64_t split_point(int64_t n) {
   return (nb / 2) * NB;
 }
 
-int strip_launch(gps_handle* h, Mat B, int64_t n, const double* T) {
+int strip_launch(gps_handle* h, Mat B, int64_t n, const double* T, bool notrans = false) {
   if (B.rows <= 0) return 0;
   set_attrs();
   unsigned grid = (unsigned)((B.rows + STRIP - 1) / STRIP);
-  trsm_strip_kernel<<<grid, 256, STRIP_SMEM, h->stream>>>(B.p, B.ld, (int)B.rows, (int)n, T);
+  if (notrans)
+    trsm_strip_kernel<true><<<grid, 256, STRIP_SMEM, h->stream>>>(B.p, B.ld, (int)B.rows, (int)n, T);
+  else
+    trsm_strip_kernel<false><<<grid, 256, STRIP_SMEM, h->stream>>>(B.p, B.ld, (int)B.rows, (int)n, T);
   GPS_LAUNCH_CHECK(h);
   return 0;
+}
+
+// rows of B that take part in the node covering 128-blocks [blk0, blk0 + nblk): a prefix
+int64_t active_rows(const int64_t* act, int64_t blk_last, int64_t rows) {
+  if (!act) return rows;
+  int64_t a = act[blk_last];
+  return a < rows ? (a < 0 ? 0 : a) : rows;
 }
 
 }  // namespace
@@ -518,6 +542,53 @@ int gps_trsm_rec(gps_handle* h, Mat L, Mat B, int64_t blk0, const double* tinv) 
                                C_ALL)))
     return rc;
   return gps_trsm_rec(h, L.sub(n1, n1, n2, n2), B2, blk0 + n1 / NB, tinv);
+}
+
+// Forward solve with a row prefix per column block:  rows [0, act[b]) of B are solved for
+// the columns of 128-block b (act non-decreasing: row r is identically zero left of its first
+// active block, e.g. B = selected rows of the identity -> rows of U = L^-T).
+int gps_trsm_rec_prefix(gps_handle* h, Mat L, Mat B, int64_t blk0, const double* tinv,
+                        const int64_t* act) {
+  int rc;
+  int64_t n = L.rows;
+  if (n <= 0 || B.rows <= 0) return 0;
+  const int64_t blk_last = blk0 + (n + NB - 1) / NB - 1;
+  const int64_t rows = active_rows(act, blk_last, B.rows);
+  if (rows <= 0) return 0;
+  if (n <= NB) return strip_launch(h, B.sub(0, 0, rows, n), n, tinv + blk0 * NB * NB);
+  int64_t n1 = split_point(n), n2 = n - n1;
+  const int64_t rows1 = active_rows(act, blk0 + n1 / NB - 1, B.rows);
+  Mat B1 = B.sub(0, 0, rows, n1), B2 = B.sub(0, n1, rows, n2);
+  if ((rc = gps_trsm_rec_prefix(h, L.sub(0, 0, n1, n1), B1, blk0, tinv, act))) return rc;
+  if (rows1 > 0 &&
+      (rc = gps_gemm_nt_launch(h, -1.0, B.sub(0, 0, rows1, n1), L.sub(n1, 0, n2, n1), 1.0,
+                               B.sub(0, n1, rows1, n2), TRI_NONE, TRI_NONE, C_ALL)))
+    return rc;
+  return gps_trsm_rec_prefix(h, L.sub(n1, n1, n2, n2), B2, blk0 + n1 / NB, tinv, act);
+}
+
+// B <- B L^-1 (solve X L = B) given Lt = L^T (upper, row-major) so that every product is NT;
+// columns are resolved right to left; rows [0, act[b]) want the columns of 128-block b.
+int gps_trsm_rln_rec(gps_handle* h, Mat Lt, Mat B, int64_t blk0, const double* tinv,
+                     const int64_t* act) {
+  int rc;
+  int64_t n = Lt.rows;
+  if (n <= 0 || B.rows <= 0) return 0;
+  const int64_t blk_last = blk0 + (n + NB - 1) / NB - 1;
+  const int64_t rows = active_rows(act, blk_last, B.rows);
+  if (rows <= 0) return 0;
+  if (n <= NB) return strip_launch(h, B.sub(0, 0, rows, n), n, tinv + blk0 * NB * NB, true);
+  int64_t n1 = split_point(n), n2 = n - n1;
+  if ((rc = gps_trsm_rln_rec(h, Lt.sub(n1, n1, n2, n2), B.sub(0, n1, rows, n2), blk0 + n1 / NB, tinv,
+                             act)))
+    return rc;
+  const int64_t rows1 = active_rows(act, blk0 + n1 / NB - 1, B.rows);
+  if (rows1 <= 0) return 0;
+  // B1 -= X2 L21:  C[r][j] -= sum_k X2[r][k] Lt[j][n1 + k]
+  if ((rc = gps_gemm_nt_launch(h, -1.0, B.sub(0, n1, rows1, n2), Lt.sub(0, n1, n1, n2), 1.0,
+                               B.sub(0, 0, rows1, n1), TRI_NONE, TRI_NONE, C_ALL)))
+    return rc;
+  return gps_trsm_rln_rec(h, Lt.sub(0, 0, n1, n1), B.sub(0, 0, rows1, n1), blk0, tinv, act);
 }
 
 int gps_block_inverses(gps_handle* h, Mat L, double* tinv) {
@@ -647,6 +718,61 @@ int gps_trsm_rlt(gps_handle* h, const DLTensor* Lt, DLTensor* B_inout) {
   if (!tinv) return -102;
   if ((rc = gps_block_inverses(h, L, tinv))) return rc;
   return gps_trsm_rec(h, L, B, 0, tinv);
+}
+
+namespace {
+int check_prefix(gps_handle* h, const int64_t* act, int64_t nblk_given, int64_t nblk, int64_t rows) {
+  if (!act) return 0;
+  if (nblk_given != nblk)
+    return gps_fail(h, -5, "active_rows has %lld entries, L has %lld 128-blocks", (long long)nblk_given,
+                    (long long)nblk);
+  for (int64_t b = 0; b < nblk; ++b)
+    if (act[b] < 0 || act[b] > rows || (b > 0 && act[b] < act[b - 1]))
+      return gps_fail(h, -4, "active_rows must be non-decreasing within [0, rows]");
+  return 0;
+}
+}  // namespace
+
+int gps_trsm_rlt_prefix(gps_handle* h, const DLTensor* Lt, DLTensor* B_inout,
+                        const int64_t* active_rows_host, int64_t nblk_given) {
+  if (!h) return -1;
+  Mat L, B;
+  int rc;
+  if ((rc = gps_as_mat(h, Lt, 2, "L", &L, false))) return rc;
+  if ((rc = gps_as_mat(h, B_inout, 3, "B_inout", &B, false))) return rc;
+  if (L.rows != L.cols) return gps_fail(h, -2, "trsm: L must be square");
+  if (B.cols != L.rows) return gps_fail(h, -3, "trsm: B has %lld columns, L is %lld x %lld",
+                                        (long long)B.cols, (long long)L.rows, (long long)L.rows);
+  GPS_CUDA(h, cudaSetDevice(h->device));
+  if (L.rows == 0 || B.rows == 0) return 0;
+  int64_t nblk = (L.rows + NB - 1) / NB;
+  if ((rc = check_prefix(h, active_rows_host, nblk_given, nblk, B.rows))) return rc;
+  double* tinv = (double*)gps_ws(h, WS_TINV, (size_t)nblk * NB * NB * sizeof(double));
+  if (!tinv) return -102;
+  if ((rc = gps_block_inverses(h, L, tinv))) return rc;
+  return gps_trsm_rec_prefix(h, L, B, 0, tinv, active_rows_host);
+}
+
+int gps_trsm_rln_prefix(gps_handle* h, const DLTensor* Lt, const DLTensor* Ltt, DLTensor* B_inout,
+                        const int64_t* active_rows_host, int64_t nblk_given) {
+  if (!h) return -1;
+  Mat L, LT, B;
+  int rc;
+  if ((rc = gps_as_mat(h, Lt, 2, "L", &L, false))) return rc;
+  if ((rc = gps_as_mat(h, Ltt, 3, "Lt", &LT, false))) return rc;
+  if ((rc = gps_as_mat(h, B_inout, 4, "B_inout", &B, false))) return rc;
+  if (L.rows != L.cols || LT.rows != L.rows || LT.cols != L.cols)
+    return gps_fail(h, -3, "trsm_rln: L and Lt must be square and of equal size");
+  if (B.cols != L.rows) return gps_fail(h, -4, "trsm_rln: B has %lld columns, L is %lld x %lld",
+                                        (long long)B.cols, (long long)L.rows, (long long)L.rows);
+  GPS_CUDA(h, cudaSetDevice(h->device));
+  if (L.rows == 0 || B.rows == 0) return 0;
+  int64_t nblk = (L.rows + NB - 1) / NB;
+  if ((rc = check_prefix(h, active_rows_host, nblk_given, nblk, B.rows))) return rc;
+  double* tinv = (double*)gps_ws(h, WS_TINV, (size_t)nblk * NB * NB * sizeof(double));
+  if (!tinv) return -102;
+  if ((rc = gps_block_inverses(h, L, tinv))) return rc;
+  return gps_trsm_rln_rec(h, LT, B, 0, tinv, active_rows_host);
 }
 
 int gps_tri_inv_t(gps_handle* h, const DLTensor* Lt, DLTensor* U_out) {

@@ -20,6 +20,7 @@ from . import mean_functions
 from . import models
 from . import neural_kernel_network
 from . import training
+from . import parallel
 
 from .params import Parameter as Param
 from .params import Parameter

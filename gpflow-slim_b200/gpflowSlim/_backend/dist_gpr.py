@@ -1,0 +1,363 @@
+"""Block-row distributed GPR objective + gradient: one process per GPU, NCCL over NVLink.
+
+What is distributed (reference call sites: models/gpr.py:55-72, densities.py:73-95 and the
+TensorFlow gradient of tf.cholesky taken by optimizer.minimize, examples/gpr.py:53-54):
+
+  K + noise I  ->  L  ->  alpha = L^-1 (Y - m)  ->  NLML,
+  dNLML/dtheta = sum_ij W_ij dK_ij/dtheta,  W = 1/2 (R K^-1 - beta beta^T),  beta = L^-T alpha.
+
+Layout.  The N x N matrix is cut into block rows of `block` rows (a multiple of 128).  Block
+row b belongs to rank `owner(b)` in SNAKE order (0..P-1, P-1..0, ...), which balances the
+triangular work of a lower factorisation to within one block.  A rank stores its block rows
+contiguously (ascending global order) in one local row-major matrix, followed by the R rows of
+(Y - m)^T that ride along every panel solve and leave alpha^T behind (replicated, no TRSV).
+
+Factorisation (right-looking, one exchange per block column k):
+  owner(k) factors the diagonal block   -> broadcast  (block^2 doubles)
+  every rank solves its rows of the panel against it (DMMA TRSM)
+  all-gather of the solved panel        -> every rank now holds column k of L
+  every rank updates its own rows of the trailing matrix with ONE masked DMMA GEMM
+  (gps_gemm_nt_rowmap: the lower-triangle mask follows the global index of each local row).
+Communication per rank: N^2/2 doubles in total, independent of P -- NVSwitch gives every GPU
+the same bandwidth to every peer, so the 1-D layout costs no more than a 2-D one at P <= 8
+and keeps every GEMM large.  The gathered panels are kept: at the end EVERY rank owns all of L
+(N^2 doubles -- 8 GiB at N = 32768, 32 GiB at N = 65536 of the 180 GB).
+
+Gradient.  With L replicated the inverse needs NO further communication: the block rows of
+K^-1 are dealt out (largest-first by their (N-c)^2 cost), and each rank computes
+  rows of U = L^-T   (gps_trsm_rlt_prefix on rows of the identity),
+  rows of K^-1 = U L^-1, columns >= the row block only (gps_trsm_rln_prefix),
+at the true flop count (N^3/3 + N^3/3 over all ranks), then contracts its rows of W with
+dK/dtheta (Gram tiles recomputed on the fly).  One all-reduce of n_theta + 1 doubles ends
+the step.
+
+The arithmetic is behind a small `backend` object: `CudaBackend` (the product: C-ABI calls
+into libgpslim_b200.so) -- tests inject a torch-CPU stand-in to exercise this host logic
+under gloo without a GPU.
+"""
+import ctypes
+import math
+
+import torch
+
+F64 = torch.float64
+NEVER = 1 << 60           # row limit of the ride-along rows: never masked
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class BlockRowLayout(object):
+    """Snake block-cyclic ownership of the block rows of an n x n matrix."""
+
+    def __init__(self, n, block, world):
+        if block % 128:
+            raise ValueError('block must be a multiple of 128 (the tile of the DMMA kernels)')
+        self.n, self.block, self.world = int(n), int(block), int(world)
+        self.nblk = (self.n + self.block - 1) // self.block
+
+    def owner(self, b):
+        rnd, pos = divmod(b, self.world)
+        return pos if rnd % 2 == 0 else self.world - 1 - pos
+
+    def rows(self, b):
+        return b * self.block, min(self.n, (b + 1) * self.block)
+
+    def blocks_of(self, rank):
+        return [b for b in range(self.nblk) if self.owner(b) == rank]
+
+    def local_offsets(self, rank):
+        """block -> first local row, and the number of local rows."""
+        off, out = 0, {}
+        for b in self.blocks_of(rank):
+            r0, r1 = self.rows(b)
+            out[b] = off
+            off += r1 - r0
+        return out, off
+
+    def rows_below(self, rank, k):
+        """(first local row, number of local rows) of `rank` in block rows > k."""
+        offs, nloc = self.local_offsets(rank)
+        lo = nloc
+        for b in self.blocks_of(rank):
+            if b > k:
+                lo = offs[b]
+                break
+        return lo, nloc - lo
+
+    def inverse_assignment(self):
+        """Deal the block rows of K^-1 to ranks, largest (N - c)^2 first, each to the least
+        loaded rank (L is replicated, so any assignment is legal).  Returns per-rank sorted
+        block lists."""
+        load = [0.0] * self.world
+        mine = [[] for _ in range(self.world)]
+        for b in range(self.nblk):          # cost decreases with b: already largest-first
+            r0, r1 = self.rows(b)
+            cost = float(self.n - r0) ** 2 * (r1 - r0)
+            q = min(range(self.world), key=lambda i: (load[i], i))
+            load[q] += cost
+            mine[q].append(b)
+        return [sorted(m) for m in mine]
+
+
+# --------------------------------------------------------------------------------- backends
+class CudaBackend(object):
+    """The product backend: every method is one or two C-ABI calls (no CPU fallback)."""
+
+    def __init__(self, device):
+        from . import lib as _L
+        self._L = _L
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise RuntimeError('the distributed GPR path computes on CUDA devices only')
+
+    def _h(self):
+        return self._L.handle_for(self.device)
+
+    def empty(self, *shape):
+        return torch.empty(*shape, dtype=F64, device=self.device)
+
+    def zeros(self, *shape):
+        return torch.zeros(*shape, dtype=F64, device=self.device)
+
+    def gram_rows(self, prog, theta, Xr, Xc, out):
+        h, L = self._h(), self._L
+        vt, vx, vx2, vk = L.view(theta), L.view(Xr), L.view(Xc), L.view(out)
+        h.check(h.lib.gps_gram_fwd(h.ptr, ctypes.byref(prog.desc), vt.ref, vx.ref, vx2.ref, 0.0, 0,
+                                   vk.ref))
+
+    def potrf_(self, A):
+        h, L = self._h(), self._L
+        va = L.view(A)
+        h.check(h.lib.gps_potrf(h.ptr, va.ref, 0, None))
+
+    def trsm_rlt_(self, Lm, B):
+        h, L = self._h(), self._L
+        vl, vb = L.view(Lm), L.view(B)
+        h.check(h.lib.gps_trsm_rlt(h.ptr, vl.ref, vb.ref))
+
+    def gemm_rowmap_(self, A, B, C, rowlim, coff, flops=-1.0):
+        h, L = self._h(), self._L
+        va, vb, vc, vr = L.view(A), L.view(B), L.view(C), L.view(rowlim)
+        h.check(h.lib.gps_gemm_nt_rowmap(h.ptr, -1.0, va.ref, vb.ref, 1.0, vc.ref, vr.ref, int(coff),
+                                         float(flops)))
+
+    def transpose(self, A):
+        h, L = self._h(), self._L
+        ld = _round_up(A.shape[0], 16)
+        out = torch.empty((A.shape[1], ld), dtype=F64, device=A.device)[:, :A.shape[0]]
+        va, vo = L.view(A), L.view(out)
+        h.check(h.lib.gps_transpose(h.ptr, va.ref, vo.ref))
+        return out
+
+    @staticmethod
+    def _act(act):
+        return (ctypes.c_int64 * len(act))(*[int(a) for a in act])
+
+    def trsm_rlt_prefix_(self, Lm, B, act):
+        h, L = self._h(), self._L
+        vl, vb = L.view(Lm), L.view(B)
+        h.check(h.lib.gps_trsm_rlt_prefix(h.ptr, vl.ref, vb.ref, self._act(act), len(act)))
+
+    def trsm_rln_prefix_(self, Lm, Lt, B, act):
+        h, L = self._h(), self._L
+        vl, vt, vb = L.view(Lm), L.view(Lt), L.view(B)
+        h.check(h.lib.gps_trsm_rln_prefix(h.ptr, vl.ref, vt.ref, vb.ref, self._act(act), len(act)))
+
+    def weight_rows_(self, W, grow, beta, block):
+        h, L = self._h(), self._L
+        vw, vg, vb = L.view(W), L.view(grow), L.view(beta)
+        h.check(h.lib.gps_gpr_weight_rows(h.ptr, vw.ref, vg.ref, vb.ref, int(block)))
+
+    def gram_bwd(self, prog, theta, Xr, Xc, W):
+        h, L = self._h(), self._L
+        dtheta = torch.empty(prog.n_theta, dtype=F64, device=W.device)
+        vt, vx, vx2, vw, vd = L.view(theta), L.view(Xr), L.view(Xc), L.view(W), L.view(dtheta)
+        h.check(h.lib.gps_gram_bwd(h.ptr, ctypes.byref(prog.desc), vt.ref, vx.ref, vx2.ref, vw.ref,
+                                   vd.ref, None))
+        return dtheta
+
+    def sum_log_diag(self, Lm):
+        h, L = self._h(), self._L
+        out = torch.empty(1, dtype=F64, device=Lm.device)
+        vl, vo = L.view(Lm), L.view(out)
+        h.check(h.lib.gps_sum_log_diag(h.ptr, vl.ref, vo.ref))
+        return out[0]
+
+
+# --------------------------------------------------------------------------------- collectives
+class _Comm(object):
+    """torch.distributed plumbing (NCCL on GPUs, gloo in the CPU tests); a world of one needs
+    no process group at all."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        if dist.is_available() and dist.is_initialized():
+            self.world = dist.get_world_size(group)
+            self.rank = dist.get_rank(group)
+        else:
+            self.world, self.rank = 1, 0
+
+    def global_rank(self, r):
+        if self.group is None or self.world == 1:
+            return r
+        return self.dist.get_global_rank(self.group, r)
+
+    def broadcast(self, t, src):
+        if self.world > 1:
+            self.dist.broadcast(t, src=self.global_rank(src), group=self.group)
+
+    def all_gather(self, out, inp):
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(out, inp, group=self.group)
+        else:
+            out.copy_(inp.reshape(out.shape))
+
+    def all_reduce_sum(self, t):
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+
+# --------------------------------------------------------------------------------- the path
+def factor(prog, theta, noise, X, Yc, lay, comm, be):
+    """Distributed Gram + Cholesky.  Returns (Lfull [N, ld] with the lower block triangle of
+    L -- identical on every rank --, alpha_t [R, N] = (L^-1 Yc)^T)."""
+    N, R = Yc.shape
+    P, rank = comm.world, comm.rank
+    bs = lay.block
+    ld = _round_up(N, 16)
+    mine = lay.blocks_of(rank)
+    offs, nloc = lay.local_offsets(rank)
+    dev = X.device
+
+    # ---- local rows of K + noise I, then the ride-along rows (Y - m)^T
+    Aloc = be.empty(nloc + R, ld)
+    grow = torch.full((nloc + R,), NEVER, dtype=torch.int64, device=dev)
+    for b in mine:
+        r0, r1 = lay.rows(b)
+        o = offs[b]
+        be.gram_rows(prog, theta, X[r0:r1], X[:r1], Aloc[o:o + r1 - r0, :r1])
+        Aloc[o:o + r1 - r0, r0:r1].diagonal().add_(noise)
+        grow[o:o + r1 - r0] = torch.arange(r0, r1, dtype=torch.int64, device=dev)
+    Aloc[nloc:, :N] = Yc.t()
+
+    Lfull = be.zeros(N, ld)
+    # static maps for unpacking gathered panels: owner and local row of every global row
+    own_of_row = torch.empty(N, dtype=torch.int64, device=dev)
+    lrow_of_row = torch.empty(N, dtype=torch.int64, device=dev)
+    for q in range(P):
+        oq, _ = lay.local_offsets(q)
+        for b, o in oq.items():
+            r0, r1 = lay.rows(b)
+            own_of_row[r0:r1] = q
+            lrow_of_row[r0:r1] = torch.arange(o, o + r1 - r0, dtype=torch.int64, device=dev)
+
+    # first local row below block row k, for every (k, rank)
+    below_all = [[lay.rows_below(q, k) for q in range(P)] for k in range(lay.nblk)]
+    lo_table = torch.tensor([[l for l, _ in row] for row in below_all], dtype=torch.int64).to(dev)
+
+    Lkk_buf = be.empty(bs * bs)
+    mmax_all = max(lay.local_offsets(q)[1] for q in range(P))
+    send_buf = be.empty(mmax_all * bs)
+    recv_buf = be.empty(P * mmax_all * bs) if P > 1 else None
+
+    for k in range(lay.nblk):
+        r0, r1 = lay.rows(k)
+        nb = r1 - r0
+        own = lay.owner(k)
+        Lkk = Lkk_buf[:nb * nb].view(nb, nb)
+        if rank == own:
+            D = Aloc[offs[k]:offs[k] + nb, r0:r1]
+            be.potrf_(D)
+            Lkk.copy_(D)
+        comm.broadcast(Lkk, own)
+        Lfull[r0:r1, r0:r1] = Lkk
+        lo, mrows = below_all[k][rank]
+        Pn = Aloc[lo:, r0:r1]                       # my panel rows + the ride-along rows
+        be.trsm_rlt_(Lkk, Pn)
+        if k == lay.nblk - 1:
+            break
+        # ---- all-gather the solved panel: every rank ends up with column k of L
+        if P > 1:
+            mmax = max(m for _, m in below_all[k])
+            send = send_buf[:mmax * nb].view(mmax, nb)
+            if mrows:
+                send[:mrows].copy_(Pn[:mrows])
+            recv = recv_buf[:P * mmax * nb]
+            comm.all_gather(recv, send.reshape(-1))
+            oq = own_of_row[r1:]
+            src = oq * mmax + lrow_of_row[r1:] - lo_table[k][oq]
+            Lfull[r1:, r0:r1] = recv.view(P * mmax, nb).index_select(0, src)
+        else:
+            Lfull[r1:, r0:r1] = Pn[:mrows]
+        # ---- trailing update of my rows (lower part only, by global row index)
+        flops = 2.0 * nb * R * (N - r1)            # algorithmic flops of my masked update
+        for b in mine:
+            if b > k:
+                b0, b1 = lay.rows(b)
+                flops += 2.0 * nb * ((b1 - b0) * (b0 - r1 + 1) + (b1 - b0) * (b1 - b0 - 1) / 2.0)
+        be.gemm_rowmap_(Pn, Lfull[r1:N, r0:r1], Aloc[lo:, r1:N], grow[lo:], r1, flops)
+    alpha_t = Aloc[nloc:, :N]
+    return Lfull, alpha_t
+
+
+def nlml_and_grad(prog, theta, noise, X, Yc, block=512, group=None, backend=None, want_grad=True):
+    """NLML of GPR and its gradient w.r.t. (theta, noise, Yc), computed by all ranks of
+    `group` together.  Inputs are replicated (X is N x D: small); every rank returns the same
+    values.  Returns (nlml, dtheta, dnoise, dYc) -- 0-d / [n_theta] / 0-d / [N, R] tensors;
+    the gradients are None when want_grad is False."""
+    comm = _Comm(group)
+    be = backend if backend is not None else CudaBackend(X.device)
+    N, R = Yc.shape
+    if R < 1 or R > 16:
+        raise ValueError('1..16 output columns supported')
+    noise = float(noise)
+    lay = BlockRowLayout(N, block, comm.world)
+    Lfull, alpha_t = factor(prog, theta, noise, X, Yc, lay, comm, be)
+    Lsq = Lfull[:, :N]
+    logdet = be.sum_log_diag(Lsq)
+    nlml = 0.5 * N * R * math.log(2.0 * math.pi) + R * logdet + 0.5 * (alpha_t ** 2).sum()
+    if not torch.isfinite(nlml):
+        from .lib import CholeskyError
+        raise CholeskyError('distributed Cholesky failed: K + noise*I is not positive definite')
+    if not want_grad:
+        return nlml, None, None, None
+
+    # ---- rows of K^-1, no communication: L is replicated
+    dev = X.device
+    bs = lay.block
+    mine = lay.inverse_assignment()[comm.rank]
+    m = R + sum(lay.rows(b)[1] - lay.rows(b)[0] for b in mine)
+    ld = _round_up(N, 16)
+    B = be.zeros(m, ld)[:, :N]
+    B[:R] = alpha_t
+    growB = torch.empty(m - R, dtype=torch.int64, device=dev)
+    starts, o = [], R
+    for b in mine:
+        r0, r1 = lay.rows(b)
+        B[o:o + r1 - r0, r0:r1].diagonal().fill_(1.0)
+        growB[o - R:o - R + r1 - r0] = torch.arange(r0, r1, dtype=torch.int64, device=dev)
+        starts.append((r0, o - R, r1 - r0))
+        o += r1 - r0
+    n128 = (N + 127) // 128
+    act_u = []
+    for j in range(n128):
+        end = (j + 1) * 128
+        act_u.append(sum(nr for (r0, _, nr) in starts if r0 < end))
+    act = [a + R for a in act_u]
+    Lt = be.transpose(Lsq)
+    if m > R:
+        be.trsm_rlt_prefix_(Lsq, B[R:], act_u)            # rows of U = L^-T
+    be.trsm_rln_prefix_(Lsq, Lt, B, act)                  # beta^T ; rows of K^-1 (cols >= block)
+    beta_t = B[:R]
+    out = torch.zeros(prog.n_theta + 1, dtype=F64, device=dev)
+    if m > R:
+        W = B[R:]
+        be.weight_rows_(W, growB, beta_t, bs)
+        out[prog.n_theta] = W[torch.arange(m - R, device=dev), growB].sum()     # tr W
+        out[:prog.n_theta] = be.gram_bwd(prog, theta, X.index_select(0, growB), X, W)
+    comm.all_reduce_sum(out)
+    return nlml, out[:prog.n_theta], out[prog.n_theta], beta_t.t().contiguous()

@@ -83,6 +83,11 @@ SIGNATURES = {
     'gps_gemm_nt': [_H, ctypes.c_double, _T, _T, ctypes.c_double, _T, ctypes.c_int, ctypes.c_int,
                     ctypes.c_int],
     'gps_transpose': [_H, _T, _T],
+    'gps_gemm_nt_rowmap': [_H, ctypes.c_double, _T, _T, ctypes.c_double, _T, _T, ctypes.c_int64,
+                           ctypes.c_double],
+    'gps_trsm_rlt_prefix': [_H, _T, _T, _P(ctypes.c_int64), ctypes.c_int64],
+    'gps_trsm_rln_prefix': [_H, _T, _T, _T, _P(ctypes.c_int64), ctypes.c_int64],
+    'gps_gpr_weight_rows': [_H, _T, _T, _T, ctypes.c_int64],
     'gps_sum_log_diag': [_H, _T, _T],
     'gps_row_sumsq': [_H, ctypes.c_double, _T, ctypes.c_double, _T],
     'gps_gpr_nlml_fwd_bwd': [_H, _D, _T, _T, _T, ctypes.c_double, ctypes.c_int, _T, _T, _T,
@@ -174,8 +179,8 @@ class _View(object):
     __slots__ = ('dl', 'shape', 'strides', 'tensor')
 
     def __init__(self, t):
-        if t.dtype != torch.float64:
-            raise TypeError('float64 tensor required, got %s' % t.dtype)
+        if t.dtype not in (torch.float64, torch.int64):
+            raise TypeError('float64 (or int64 index) tensor required, got %s' % t.dtype)
         nd = t.dim()
         self.tensor = t
         self.shape = (ctypes.c_int64 * max(nd, 1))(*t.shape)
@@ -183,7 +188,8 @@ class _View(object):
         idx = t.device.index if t.device.index is not None else 0
         self.dl = DLTensor(ctypes.c_void_p(t.data_ptr()),
                            DLDevice(2 if t.device.type == 'cuda' else 1, idx), nd,
-                           DLDataType(2, 64, 1), self.shape, self.strides, 0)
+                           DLDataType(2 if t.dtype == torch.float64 else 0, 64, 1), self.shape,
+                           self.strides, 0)
 
     @property
     def ref(self):

@@ -386,9 +386,36 @@ class _GprLogLik(torch.autograd.Function):
         return gt, gn, gy, None, None
 
 
+class _GprLogLikDist(torch.autograd.Function):
+    """log p(Y) of GPR computed by all ranks of a process group together (block-row
+    distributed Cholesky / inverse, _backend/dist_gpr.py)."""
+
+    @staticmethod
+    def forward(ctx, theta, noise, Yc, X, prog, group, block):
+        from . import dist_gpr
+        X, Yc, theta = _prep(X), _prep(Yc), _prep(theta)
+        want_grad = any(ctx.needs_input_grad[:3])
+        nlml, dtheta, dnoise, dY = dist_gpr.nlml_and_grad(prog, theta.detach(), float(noise), X, Yc.detach(),
+                                                          block=block, group=group, want_grad=want_grad)
+        ctx.grads = (dtheta, dnoise, dY)
+        return -nlml
+
+    @staticmethod
+    def backward(ctx, g):
+        dtheta, dnoise, dY = ctx.grads
+        gt = -g * dtheta if ctx.needs_input_grad[0] else None
+        gn = -g * dnoise if ctx.needs_input_grad[1] else None
+        gy = -g * dY if ctx.needs_input_grad[2] else None
+        return gt, gn, gy, None, None, None, None
+
+
 def gpr_loglik(prog, X, Yc, noise):
     noise = noise if isinstance(noise, torch.Tensor) else torch.as_tensor(noise, dtype=F64,
                                                                           device=X.device)
+    from .. import parallel
+    if parallel.active():
+        return _GprLogLikDist.apply(prog.theta(X.device), noise.reshape(()), Yc, X, prog,
+                                    parallel.group(), parallel.block())
     return _GprLogLik.apply(prog.theta(X.device), noise.reshape(()), Yc, X, prog)
 
 

@@ -168,6 +168,37 @@ int gps_gemm_nt(gps_handle* h, double alpha, const DLTensor* A, const DLTensor* 
                 DLTensor* C, int a_tri, int b_tri, int c_uplo);
 int gps_transpose(gps_handle* h, const DLTensor* A, DLTensor* At_out);
 
+/* ---- building blocks of the block-row distributed GPR (one process per GPU) ---------------
+ * The multi-GPU path (gpflowSlim/_backend/dist_gpr.py) distributes the rows of K over the
+ * ranks in blocks; NCCL moves the panels, these entry points do the arithmetic.
+ * gps_gemm_nt_rowmap: C[r,c] = alpha (A B^T)[r,c] + beta C[r,c] only where
+ *   c + col_offset <= row_limit[r]  (row_limit: int64 device vector, one entry per row of C,
+ *   non-decreasing = global row index of each local row).  This is the trailing update
+ *   A22 -= L21 L21^T of tf.cholesky (models/gpr.py:70) restricted to the lower triangle when
+ *   the rows of A22 are a block-cyclic subset.  Tiles wholly above the limit are skipped.
+ *   `flops` (>= 0) is what the profile option books for the launch.
+ * gps_trsm_rlt_prefix: B <- B L^-T where, for the columns of 128-block b, only the first
+ *   active_rows[b] rows of B are solved (HOST array, one entry per 128-block of L,
+ *   non-decreasing; NULL = all rows).  With B = rows of the identity sorted by column this
+ *   yields rows of U = L^-T at their true flop count.
+ * gps_trsm_rln_prefix: B <- B L^-1 (the solve against the untransposed factor), columns right
+ *   to left, same prefix rule; Lt = L^T (row-major upper) must be supplied so that every
+ *   product is K-contiguous.  Rows of U go in, rows of K^-1 = L^-T L^-1 come out
+ *   (the O(N^3) part of TensorFlow's Cholesky gradient, examples/gpr.py:53-54).
+ * gps_gpr_weight_rows: W[r,j] <- m(r,j)/2 (R K^-1[g_r,j] - sum_q beta_q[g_r] beta_q[j]) in
+ *   place on a row panel of K^-1; g_r = row_index[r]; m = 0 left of g_r's block (of size
+ *   `block`), 1 inside it, 2 to the right (symmetric counterpart).
+ */
+int gps_gemm_nt_rowmap(gps_handle* h, double alpha, const DLTensor* A, const DLTensor* B,
+                       double beta, DLTensor* C, const DLTensor* row_limit, int64_t col_offset,
+                       double flops);
+int gps_trsm_rlt_prefix(gps_handle* h, const DLTensor* L, DLTensor* B_inout,
+                        const int64_t* active_rows, int64_t n_blocks);
+int gps_trsm_rln_prefix(gps_handle* h, const DLTensor* L, const DLTensor* Lt, DLTensor* B_inout,
+                        const int64_t* active_rows, int64_t n_blocks);
+int gps_gpr_weight_rows(gps_handle* h, DLTensor* W_inout, const DLTensor* row_index,
+                        const DLTensor* beta, int64_t block);
+
 /* ---- reductions on the hot path ----------------------------------------------------------
  * gps_sum_log_diag: out[0] = sum_i log(L[i,i])           (densities.py:93)
  * gps_row_sumsq:    out[i] = beta*out[i] + alpha * sum_j A[i,j]^2

@@ -1,0 +1,76 @@
+"""TEST DOUBLE (never shipped): torch-CPU stand-in for gpflowSlim._backend.dist_gpr.CudaBackend,
+so the host logic of the distributed GPR path (ownership maps, panel packing / unpacking, masks,
+prefix tables, collectives) runs under gloo on a machine without a GPU.  The Gram arithmetic comes
+from the oracle (`spec_fn(theta)` -> oracle kernel spec)."""
+import torch
+
+from oracle import ref_torch as R
+
+F64 = torch.float64
+
+
+class CpuBackend(object):
+    def __init__(self, spec_fn):
+        self.spec_fn = spec_fn
+
+    def empty(self, *shape):
+        return torch.full(tuple(shape), float('nan'), dtype=F64)   # poison: unwritten reads show up
+
+    def zeros(self, *shape):
+        return torch.zeros(*shape, dtype=F64)
+
+    def gram_rows(self, prog, theta, Xr, Xc, out):
+        out.copy_(R.K(self.spec_fn(theta), Xr, Xc))
+
+    def potrf_(self, A):
+        L = torch.linalg.cholesky(torch.tril(A) + torch.tril(A, -1).T)
+        A.copy_(torch.tril(L) + torch.triu(A, 1))          # strict upper untouched, like the library
+
+    def trsm_rlt_(self, Lm, B):
+        B.copy_(torch.linalg.solve_triangular(torch.tril(Lm), B.T, upper=False).T)
+
+    def gemm_rowmap_(self, A, B, C, rowlim, coff, flops=-1.0):
+        cols = torch.arange(C.shape[1]) + coff
+        mask = cols[None, :] <= rowlim[:, None]
+        upd = A @ B.T
+        C.sub_(torch.where(mask, upd, torch.zeros_like(upd)))
+
+    def transpose(self, A):
+        return A.T.contiguous()
+
+    def trsm_rlt_prefix_(self, Lm, B, act):
+        X = torch.linalg.solve_triangular(torch.tril(Lm), B.T, upper=False).T
+        for j, a in enumerate(act):                       # only the active prefix is written
+            B[:a, j * 128:(j + 1) * 128] = X[:a, j * 128:(j + 1) * 128]
+
+    def trsm_rln_prefix_(self, Lm, Lt, B, act):
+        assert torch.equal(torch.triu(Lt), torch.tril(Lm).T)
+        n = Lm.shape[0]
+        nblk = len(act)
+        # right to left over 128-blocks, honouring the prefix rule exactly
+        Ltri = torch.tril(Lm)
+        for j in reversed(range(nblk)):
+            c0, c1 = j * 128, min(n, (j + 1) * 128)
+            a = act[j]
+            if a == 0:
+                continue
+            rhs = B[:a, c0:c1] - B[:a, c1:] @ Ltri[c1:, c0:c1]
+            B[:a, c0:c1] = torch.linalg.solve_triangular(Ltri[c0:c1, c0:c1], rhs, upper=False, left=False)
+
+    def weight_rows_(self, W, grow, beta, block):
+        n = W.shape[1]
+        cols = torch.arange(n)
+        c0 = (grow // block * block)[:, None]
+        bb = beta[:, grow].T @ beta                        # [m, N]
+        v = 0.5 * (beta.shape[0] * W - bb)
+        v = torch.where(cols[None, :] >= c0 + block, 2.0 * v, v)
+        W.copy_(torch.where(cols[None, :] >= c0, v, torch.zeros_like(v)))
+
+    def gram_bwd(self, prog, theta, Xr, Xc, W):
+        th = theta.detach().clone().requires_grad_(True)
+        K = R.K(self.spec_fn(th), Xr, Xc)
+        (g,) = torch.autograd.grad((K * W).sum(), th)
+        return g
+
+    def sum_log_diag(self, Lm):
+        return torch.log(torch.diagonal(Lm)).sum()

@@ -1,0 +1,79 @@
+"""Launched under torchrun with >= 2 ranks: distributed GPR objective + gradient and the sharded
+SVGP step against the single-GPU values computed on the same rank.  Prints DIST_CHECK_OK."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'gpflow-slim_b200'))
+sys.path.insert(0, ROOT)
+
+
+def rel(a, b):
+    a, b = a.detach().double().reshape(-1), b.detach().double().reshape(-1)
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-300))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--n', type=int, default=3000)
+    ap.add_argument('--block', type=int, default=256)
+    args = ap.parse_args()
+    import gpflowSlim as gpf
+    from bench import synth_gpr
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    gpf.settings.device = dev
+    dist.init_process_group('nccl', device_id=dev)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n, d = args.n, 6
+    X, Y = synth_gpr(n, d)
+    conv = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+    kern = gpf.kernels.Matern52(d, ARD=True, lengthscales=2.0) + gpf.kernels.Linear(d, variance=0.2)
+    m = gpf.models.GPR(conv(X), conv(Y), kern=kern)
+    params = [p.unconstrained_tensor for p in m.parameters]
+    obj = m.objective
+    g = torch.autograd.grad(obj, params)
+    gpf.parallel.init(block=args.block)
+    obj2 = m.objective
+    g2 = torch.autograd.grad(obj2, params)
+    gpf.parallel.shutdown()
+    errs = [rel(obj2, obj)] + [rel(a, b) for a, b in zip(g2, g)]
+    # every rank must hold the same answer
+    t = torch.stack([obj2.detach()] + [x.reshape(-1)[0] for x in g2])
+    lo, hi = t.clone(), t.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    spread = float(((hi - lo).abs() / hi.abs().clamp(min=1e-300)).max())
+    print('rank %d GPR dist vs single: max rel err %.2e, spread over ranks %.2e' % (rank, max(errs), spread), flush=True)
+    assert max(errs) < 1e-8 and spread < 1e-12, (errs, spread)
+
+    # ---- SVGP: minibatch sharded over ranks
+    from oracle import cases
+    nb, M = 512 * world, 64
+    Xs, Ys, Z = cases.synth_svgp(nb, 5, M, seed=0)
+    sv = gpf.models.SVGP(conv(Xs), conv(Ys), gpf.kernels.RBF(5, ARD=True, lengthscales=2.0),
+                         gpf.likelihoods.Gaussian(var=0.1), Z=Z.copy(), num_data=100000)
+    ps = sv.trainable_tensors
+    o1 = sv.objective
+    g1 = torch.autograd.grad(o1, ps)
+    sl = slice(rank * 512, (rank + 1) * 512)
+    gpf.parallel.init()
+    o2, g2 = gpf.parallel.svgp_objective_and_grads(sv, conv(Xs[sl]), conv(Ys[sl]), ps)
+    gpf.parallel.shutdown()
+    errs = [rel(o2, o1)] + [rel(a, b) for a, b in zip(g2, g1)]
+    print('rank %d SVGP sharded vs single: max rel err %.2e' % (rank, max(errs)), flush=True)
+    assert max(errs) < 1e-8, errs
+    dist.barrier()
+    if rank == 0:
+        print('DIST_CHECK_OK', flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
