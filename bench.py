@@ -121,7 +121,7 @@ def run_reference(args):
               '%.2f s/eval on %d threads; scaled to N=%d by (N/N_s)^3=%.0f' % (ns, d, t, cores, n, scale))
     line = {'impl': 'reference', 'metric': 'GPR NLML+grad evals/s', 'value': val, 'unit': 'evals/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t * scale * 1e3,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic', 'config': {'workload': 'GPR ARD-RBF N=%d D=%d fp64 NLML+grad' % (n, d)},
             'cpu_baseline': {'value': val, 'unit': 'evals/s', 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': val, 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -135,8 +135,12 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours')
-    ap.add_argument('--n', type=int, default=32768)
+    ap.add_argument('--size', '--n', type=int, default=32768, dest='n')   # under torchrun use --size
     ap.add_argument('--d', type=int, default=8)
+    ap.add_argument('--mode', default='auto', choices=['auto', 'fused', 'dist', 'independent'],
+                    help='auto: 1 GPU -> fused single-GPU path; N GPUs -> ONE problem distributed over '
+                         'the ranks (strong scaling); independent: one problem per GPU (weak)')
+    ap.add_argument('--block', type=int, default=512)
     ap.add_argument('--cpu-n', type=int, default=4096, dest='cpu_n')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
@@ -158,8 +162,14 @@ def main():
     from gpflowSlim._backend.lib import handle_for
     gpf.settings.device = dev
     n, d = args.n, args.d
-    # every rank owns one independent problem of the named shape (seed = rank): see DESIGN.md (e)
-    Xh, Yh = synth_gpr(n, d, seed=rank)
+    mode = args.mode
+    if mode == 'auto':
+        mode = 'dist' if world > 1 else 'fused'
+    # dist: every rank holds the same (replicated) X, Y of ONE problem and the ranks factor it
+    # together; independent: every rank owns its own problem (seed = rank).  DESIGN.md (e)
+    Xh, Yh = synth_gpr(n, d, seed=rank if mode == 'independent' else 0)
+    if mode == 'dist':
+        gpf.parallel.init(block=args.block)
     Xp = torch.from_numpy(Xh).pin_memory()
     Yp = torch.from_numpy(Yh).pin_memory()
     kern = gpf.kernels.RBF(d, ARD=True, lengthscales=math.sqrt(d))
@@ -223,16 +233,21 @@ def main():
         # the GEMM launches run back to back inside a ~1 s step: sustained figure applies
         pk = peak['sustained']
         nparam = d + 2
+        nprob = world if mode == 'independent' else 1     # problems evaluated per step, whole job
+        par = {'fused': 'single GPU, fused path', 'independent': 'independent problem per GPU',
+               'dist': 'one problem over %d GPU(s): block-row (block %d) distributed Cholesky + inverse, '
+                       'NCCL broadcast / all-gather per panel, look-ahead 1' % (world, args.block)}[mode]
         line = {
-            'metric': 'GPR NLML+grad evals/s', 'value': world * 1e3 / ms, 'unit': 'evals/s',
+            'metric': 'GPR NLML+grad evals/s', 'value': nprob * 1e3 / ms, 'unit': 'evals/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'higher_is_better': True, 'scaling': 'weak' if mode == 'independent' else 'strong',
+            'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic',
             'config': {'workload': 'GPR ARD-RBF N=%d D=%d fp64 NLML+grad (Gram+POTRF+TRSM+backward)' % (n, d),
-                       'parallelism': 'independent problem per GPU' if world > 1 else 'single GPU',
+                       'parallelism': par,
                        'l2': 'inputs exceed L2 (K is %.1f GiB)' % (8.0 * n * n / 2 ** 30),
                        'flops_per_eval_model': float(n) ** 3},
-            'e2e': {'value': world * 1e3 / e2e_ms, 'unit': 'evals/s',
+            'e2e': {'value': nprob * 1e3 / e2e_ms, 'unit': 'evals/s',
                     'h2d_bytes_per_step': int(Xp.numel() * 8 + Yp.numel() * 8),
                     'd2h_bytes_per_step': int(8 * (1 + nparam))},
             'gpu_launches': int(launches),
@@ -241,7 +256,8 @@ def main():
                          'peak': pk, 'unit': 'TFLOP/s', 'frac': ach / pk if pk else None, 'traffic': None,
                          'peak_source': peak['source'],
                          'gemm_share_of_step': gemm_ms / (ms * args.steps) if ms > 0 else None,
-                         'step_tflops_vs_n3': float(n) ** 3 / (ms * 1e-3) / 1e12},
+                         'scope': 'rank 0' if world > 1 else 'the GPU',
+                         'step_tflops_vs_n3': nprob * float(n) ** 3 / (ms * 1e-3) / 1e12},
         }
         if world == 1 and not args.no_cpu_baseline:
             ns = args.cpu_n

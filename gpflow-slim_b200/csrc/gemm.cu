@@ -36,6 +36,12 @@ struct GemmArgs {
   // (block-row distributions: rowlim[r] = global row index of local row r)
   const int64_t* rowlim;
   int64_t coff;
+  // rows sorted by a per-row first column rowlo[r] (global index, multiple of 128):
+  // lo_mode 1: A[r][k] == 0 for lo_off + k < rowlo[r]  -> the K range of a tile starts later
+  // lo_mode 2: C[r][c] is not wanted for lo_off + c < rowlo[r] -> tiles wholly left are skipped
+  const int64_t* rowlo;
+  int64_t lo_off;
+  int lo_mode;
 };
 
 __device__ __forceinline__ void tile_coords(const GemmArgs& g, int bid, int& ti, int& tj) {
@@ -118,9 +124,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_dmma_kernel(const Gem
   const int m0 = ti * BM, n0 = tj * BN;
   if (g.c_uplo == C_LOWER && m0 + BM - 1 < n0) return;  // tile entirely above the diagonal
   if (g.c_uplo == C_ROWMAP && (int64_t)n0 + g.coff > g.rowlim[min(m0 + BM, g.M) - 1]) return;
+  if (g.lo_mode == 2 && (int64_t)n0 + BN - 1 + g.lo_off < g.rowlo[m0]) return;
 
   int klo, khi;
   k_range(g, ti, tj, klo, khi);
+  if (g.lo_mode == 1) {
+    int64_t lo = g.rowlo[m0] - g.lo_off;     // rows are sorted: the tile's first row starts first
+    if (lo > klo) klo = (int)(lo < khi ? lo / BK * BK : khi);
+  }
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps, warp tile 64 x 32
@@ -252,7 +263,8 @@ double gemm_flops(const GemmArgs& g) {
 }  // namespace
 
 int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, Mat C, int a_tri,
-                       int b_tri, int c_uplo, const int64_t* rowlim, int64_t coff, double flops) {
+                       int b_tri, int c_uplo, const int64_t* rowlim, int64_t coff, double flops,
+                       const int64_t* rowlo, int64_t lo_off, int lo_mode) {
   if (A.cols != B.cols) return gps_fail(h, -3, "gemm_nt: K mismatch (%lld vs %lld)",
                                         (long long)A.cols, (long long)B.cols);
   if (C.rows != A.rows || C.cols != B.rows) return gps_fail(h, -6, "gemm_nt: C shape mismatch");
@@ -268,6 +280,7 @@ int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, M
   g.tiles_m = (g.M + BM - 1) / BM;
   g.tiles_n = (g.N + BN - 1) / BN;
   g.rowlim = rowlim; g.coff = coff;
+  g.rowlo = rowlo; g.lo_off = lo_off; g.lo_mode = rowlo ? lo_mode : 0;
   if (c_uplo == C_ROWMAP && !rowlim) return gps_fail(h, -7, "gemm_nt: C_ROWMAP needs a row-limit array");
 
   GemmEvent* ev = nullptr;

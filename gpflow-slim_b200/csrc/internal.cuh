@@ -38,6 +38,7 @@ enum WsSlot {
   WS_THETA,
   WS_INVW,        // triangular inverse: W = -U11 L21^T of the current recursion node
   WS_INVT,        // triangular inverse: T22 = U22^T of the current recursion node
+  WS_ROWLO,       // prefix solves: per-row first column (device copy)
   WS_COUNT
 };
 
@@ -95,7 +96,8 @@ enum { C_ALL = 0, C_LOWER = 1, C_ROWMAP = 2 };
 // non-decreasing).  flops >= 0 overrides the profile's flop count for this launch.
 int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, Mat C, int a_tri,
                        int b_tri, int c_uplo, const int64_t* rowlim = nullptr, int64_t coff = 0,
-                       double flops = -1.0);
+                       double flops = -1.0, const int64_t* rowlo = nullptr, int64_t lo_off = 0,
+                       int lo_mode = 0);
 
 // ----------------------------------------------------------------------------- factorisation
 // Factor the n x n block at A (lower, in place) and solve the `below` rows under it:

@@ -490,13 +490,31 @@ int strip_launch(gps_handle* h, Mat B, int64_t n, const double* T, bool notrans 
   return 0;
 }
 
-// rows of B that take part in the node covering 128-blocks [blk0, blk0 + nblk): a prefix
-int64_t active_rows(const int64_t* act, int64_t blk_last, int64_t rows) {
-  if (!act) return rows;
-  int64_t a = act[blk_last];
-  return a < rows ? (a < 0 ? 0 : a) : rows;
-}
-
+// ---- row structure of the prefix solves -------------------------------------------------
+// The rows of B are sorted by a per-row first column start[r] (a multiple of 128): left of it
+// the row is identically zero (forward solve) / not wanted (solve against L itself).  Held as
+// segments of equal start; a device copy of the per-row array feeds the GEMM masks.
+struct RowSegs {
+  std::vector<int64_t> begin, count, start;
+  int64_t rows = 0;
+  const int64_t* dev = nullptr;   // [rows]
+  // rows with start < colend (a prefix, since start is non-decreasing)
+  int64_t active(int64_t colend) const {
+    int64_t n = 0;
+    for (size_t i = 0; i < start.size() && start[i] < colend; ++i) n += count[i];
+    return n;
+  }
+  // sum over rows r < nrows of (hi - max(lo, start[r]))  clipped at 0
+  double span(int64_t nrows, int64_t lo, int64_t hi) const {
+    double t = 0;
+    for (size_t i = 0; i < start.size() && begin[i] < nrows; ++i) {
+      int64_t c = count[i] < nrows - begin[i] ? count[i] : nrows - begin[i];
+      int64_t l = start[i] > lo ? start[i] : lo;
+      if (hi > l) t += (double)c * (double)(hi - l);
+    }
+    return t;
+  }
+};
 }  // namespace
 
 int gps_potrf_rec(gps_handle* h, Mat A, int64_t n, int64_t below, int64_t blk0, double* tinv,
@@ -544,52 +562,78 @@ int gps_trsm_rec(gps_handle* h, Mat L, Mat B, int64_t blk0, const double* tinv) 
   return gps_trsm_rec(h, L.sub(n1, n1, n2, n2), B2, blk0 + n1 / NB, tinv);
 }
 
-// Forward solve with a row prefix per column block:  rows [0, act[b]) of B are solved for
-// the columns of 128-block b (act non-decreasing: row r is identically zero left of its first
-// active block, e.g. B = selected rows of the identity -> rows of U = L^-T).
-int gps_trsm_rec_prefix(gps_handle* h, Mat L, Mat B, int64_t blk0, const double* tinv,
-                        const int64_t* act) {
+// Forward solve B <- B L^-T where row r of B is zero left of column start[r]: at the node that
+// covers columns [c0, c0 + n) only the rows with start < c0 + n take part, and the update GEMM
+// skips the leading zero K-range of each row tile.  With B = rows of the identity this yields
+// rows of U = L^-T at N^3/3 flops overall.
+namespace {
+int trsm_rlt_segs(gps_handle* h, Mat L, Mat B, int64_t c0, const double* tinv, const RowSegs& rs) {
   int rc;
   int64_t n = L.rows;
-  if (n <= 0 || B.rows <= 0) return 0;
-  const int64_t blk_last = blk0 + (n + NB - 1) / NB - 1;
-  const int64_t rows = active_rows(act, blk_last, B.rows);
+  if (n <= 0) return 0;
+  const int64_t rows = rs.active(c0 + n);
   if (rows <= 0) return 0;
-  if (n <= NB) return strip_launch(h, B.sub(0, 0, rows, n), n, tinv + blk0 * NB * NB);
+  if (n <= NB) return strip_launch(h, B.sub(0, 0, rows, n), n, tinv + (c0 / NB) * NB * NB);
   int64_t n1 = split_point(n), n2 = n - n1;
-  const int64_t rows1 = active_rows(act, blk0 + n1 / NB - 1, B.rows);
-  Mat B1 = B.sub(0, 0, rows, n1), B2 = B.sub(0, n1, rows, n2);
-  if ((rc = gps_trsm_rec_prefix(h, L.sub(0, 0, n1, n1), B1, blk0, tinv, act))) return rc;
-  if (rows1 > 0 &&
-      (rc = gps_gemm_nt_launch(h, -1.0, B.sub(0, 0, rows1, n1), L.sub(n1, 0, n2, n1), 1.0,
-                               B.sub(0, n1, rows1, n2), TRI_NONE, TRI_NONE, C_ALL)))
-    return rc;
-  return gps_trsm_rec_prefix(h, L.sub(n1, n1, n2, n2), B2, blk0 + n1 / NB, tinv, act);
+  if ((rc = trsm_rlt_segs(h, L.sub(0, 0, n1, n1), B.sub(0, 0, rows, n1), c0, tinv, rs))) return rc;
+  const int64_t rows1 = rs.active(c0 + n1);
+  if (rows1 > 0) {
+    double flops = 2.0 * (double)n2 * rs.span(rows1, c0, c0 + n1);
+    if ((rc = gps_gemm_nt_launch(h, -1.0, B.sub(0, 0, rows1, n1), L.sub(n1, 0, n2, n1), 1.0,
+                                 B.sub(0, n1, rows1, n2), TRI_NONE, TRI_NONE, C_ALL, nullptr, 0, flops,
+                                 rs.dev, c0, 1)))
+      return rc;
+  }
+  return trsm_rlt_segs(h, L.sub(n1, n1, n2, n2), B.sub(0, n1, rows, n2), c0 + n1, tinv, rs);
 }
 
 // B <- B L^-1 (solve X L = B) given Lt = L^T (upper, row-major) so that every product is NT;
-// columns are resolved right to left; rows [0, act[b]) want the columns of 128-block b.
-int gps_trsm_rln_rec(gps_handle* h, Mat Lt, Mat B, int64_t blk0, const double* tinv,
-                     const int64_t* act) {
+// columns are resolved right to left; row r wants the columns >= start[r] only.
+int trsm_rln_segs(gps_handle* h, Mat Lt, Mat B, int64_t c0, const double* tinv, const RowSegs& rs) {
   int rc;
   int64_t n = Lt.rows;
-  if (n <= 0 || B.rows <= 0) return 0;
-  const int64_t blk_last = blk0 + (n + NB - 1) / NB - 1;
-  const int64_t rows = active_rows(act, blk_last, B.rows);
+  if (n <= 0) return 0;
+  const int64_t rows = rs.active(c0 + n);
   if (rows <= 0) return 0;
-  if (n <= NB) return strip_launch(h, B.sub(0, 0, rows, n), n, tinv + blk0 * NB * NB, true);
+  if (n <= NB) return strip_launch(h, B.sub(0, 0, rows, n), n, tinv + (c0 / NB) * NB * NB, true);
   int64_t n1 = split_point(n), n2 = n - n1;
-  if ((rc = gps_trsm_rln_rec(h, Lt.sub(n1, n1, n2, n2), B.sub(0, n1, rows, n2), blk0 + n1 / NB, tinv,
-                             act)))
+  if ((rc = trsm_rln_segs(h, Lt.sub(n1, n1, n2, n2), B.sub(0, n1, rows, n2), c0 + n1, tinv, rs)))
     return rc;
-  const int64_t rows1 = active_rows(act, blk0 + n1 / NB - 1, B.rows);
+  const int64_t rows1 = rs.active(c0 + n1);
   if (rows1 <= 0) return 0;
-  // B1 -= X2 L21:  C[r][j] -= sum_k X2[r][k] Lt[j][n1 + k]
+  // B1 -= X2 L21:  C[r][j] -= sum_k X2[r][k] Lt[j][n1 + k]   (tiles left of start[r] skipped)
+  double flops = 2.0 * (double)n2 * rs.span(rows1, c0, c0 + n1);
   if ((rc = gps_gemm_nt_launch(h, -1.0, B.sub(0, n1, rows1, n2), Lt.sub(0, n1, n1, n2), 1.0,
-                               B.sub(0, 0, rows1, n1), TRI_NONE, TRI_NONE, C_ALL)))
+                               B.sub(0, 0, rows1, n1), TRI_NONE, TRI_NONE, C_ALL, nullptr, 0, flops,
+                               rs.dev, c0, 2)))
     return rc;
-  return gps_trsm_rln_rec(h, Lt.sub(0, 0, n1, n1), B.sub(0, 0, rows1, n1), blk0, tinv, act);
+  return trsm_rln_segs(h, Lt.sub(0, 0, n1, n1), B.sub(0, 0, rows1, n1), c0, tinv, rs);
 }
+
+int make_segs(gps_handle* h, const int64_t* row_start, int64_t rows, int64_t ncols, RowSegs* out) {
+  out->rows = rows;
+  if (!row_start) {
+    out->begin.push_back(0); out->count.push_back(rows); out->start.push_back(0);
+    out->dev = nullptr;
+    return 0;
+  }
+  for (int64_t r = 0; r < rows; ++r) {
+    int64_t s = row_start[r];
+    if (s < 0 || s % NB || s >= ncols + NB || (r > 0 && s < row_start[r - 1]))
+      return gps_fail(h, -4, "row_start must be non-decreasing multiples of %d inside the matrix", NB);
+    if (out->start.empty() || out->start.back() != s) {
+      out->begin.push_back(r); out->count.push_back(0); out->start.push_back(s);
+    }
+    out->count.back()++;
+  }
+  int64_t* dev = (int64_t*)gps_ws(h, WS_ROWLO, (size_t)rows * sizeof(int64_t));
+  if (!dev) return -102;
+  GPS_CUDA(h, cudaMemcpyAsync(dev, row_start, (size_t)rows * sizeof(int64_t), cudaMemcpyHostToDevice,
+                              h->stream));
+  out->dev = dev;
+  return 0;
+}
+}  // namespace
 
 int gps_block_inverses(gps_handle* h, Mat L, double* tinv) {
   if (L.rows <= 0) return 0;
@@ -720,21 +764,8 @@ int gps_trsm_rlt(gps_handle* h, const DLTensor* Lt, DLTensor* B_inout) {
   return gps_trsm_rec(h, L, B, 0, tinv);
 }
 
-namespace {
-int check_prefix(gps_handle* h, const int64_t* act, int64_t nblk_given, int64_t nblk, int64_t rows) {
-  if (!act) return 0;
-  if (nblk_given != nblk)
-    return gps_fail(h, -5, "active_rows has %lld entries, L has %lld 128-blocks", (long long)nblk_given,
-                    (long long)nblk);
-  for (int64_t b = 0; b < nblk; ++b)
-    if (act[b] < 0 || act[b] > rows || (b > 0 && act[b] < act[b - 1]))
-      return gps_fail(h, -4, "active_rows must be non-decreasing within [0, rows]");
-  return 0;
-}
-}  // namespace
-
 int gps_trsm_rlt_prefix(gps_handle* h, const DLTensor* Lt, DLTensor* B_inout,
-                        const int64_t* active_rows_host, int64_t nblk_given) {
+                        const int64_t* row_start_host) {
   if (!h) return -1;
   Mat L, B;
   int rc;
@@ -745,16 +776,17 @@ int gps_trsm_rlt_prefix(gps_handle* h, const DLTensor* Lt, DLTensor* B_inout,
                                         (long long)B.cols, (long long)L.rows, (long long)L.rows);
   GPS_CUDA(h, cudaSetDevice(h->device));
   if (L.rows == 0 || B.rows == 0) return 0;
+  RowSegs rs;
+  if ((rc = make_segs(h, row_start_host, B.rows, L.rows, &rs))) return rc;
   int64_t nblk = (L.rows + NB - 1) / NB;
-  if ((rc = check_prefix(h, active_rows_host, nblk_given, nblk, B.rows))) return rc;
   double* tinv = (double*)gps_ws(h, WS_TINV, (size_t)nblk * NB * NB * sizeof(double));
   if (!tinv) return -102;
   if ((rc = gps_block_inverses(h, L, tinv))) return rc;
-  return gps_trsm_rec_prefix(h, L, B, 0, tinv, active_rows_host);
+  return trsm_rlt_segs(h, L, B, 0, tinv, rs);
 }
 
 int gps_trsm_rln_prefix(gps_handle* h, const DLTensor* Lt, const DLTensor* Ltt, DLTensor* B_inout,
-                        const int64_t* active_rows_host, int64_t nblk_given) {
+                        const int64_t* row_start_host) {
   if (!h) return -1;
   Mat L, LT, B;
   int rc;
@@ -767,12 +799,13 @@ int gps_trsm_rln_prefix(gps_handle* h, const DLTensor* Lt, const DLTensor* Ltt, 
                                         (long long)B.cols, (long long)L.rows, (long long)L.rows);
   GPS_CUDA(h, cudaSetDevice(h->device));
   if (L.rows == 0 || B.rows == 0) return 0;
+  RowSegs rs;
+  if ((rc = make_segs(h, row_start_host, B.rows, L.rows, &rs))) return rc;
   int64_t nblk = (L.rows + NB - 1) / NB;
-  if ((rc = check_prefix(h, active_rows_host, nblk_given, nblk, B.rows))) return rc;
   double* tinv = (double*)gps_ws(h, WS_TINV, (size_t)nblk * NB * NB * sizeof(double));
   if (!tinv) return -102;
   if ((rc = gps_block_inverses(h, L, tinv))) return rc;
-  return gps_trsm_rln_rec(h, LT, B, 0, tinv, active_rows_host);
+  return trsm_rln_segs(h, LT, B, 0, tinv, rs);
 }
 
 int gps_tri_inv_t(gps_handle* h, const DLTensor* Lt, DLTensor* U_out) {

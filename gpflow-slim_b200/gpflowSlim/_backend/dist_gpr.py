@@ -48,6 +48,35 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
+class PhaseTimer(object):
+    """Optional CUDA-event phase timing (dist_gpr.TIMER = PhaseTimer() to switch it on)."""
+
+    def __init__(self):
+        self.marks = []
+
+    def mark(self, name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.marks.append((name, e))
+
+    def report(self):
+        torch.cuda.synchronize()
+        acc = {}
+        for (n0, e0), (n1, e1) in zip(self.marks[:-1], self.marks[1:]):
+            acc[n1] = acc.get(n1, 0.0) + e0.elapsed_time(e1)
+        self.marks = []
+        return acc
+
+
+TIMER = None
+_FINE = True     # fine-grained marks only make sense when everything runs on one stream
+
+
+def _mark(name, fine=False):
+    if TIMER is not None and (_FINE or not fine):
+        TIMER.mark(name)
+
+
 class BlockRowLayout(object):
     """Snake block-cyclic ownership of the block rows of an n x n matrix."""
 
@@ -118,6 +147,24 @@ class CudaBackend(object):
     def empty(self, *shape):
         return torch.empty(*shape, dtype=F64, device=self.device)
 
+    # ---- streams / events for the look-ahead (CUDA streams, no tracing compiler)
+    def streams(self):
+        if getattr(self, '_side', None) is None:
+            self._side = torch.cuda.Stream(self.device, priority=-1)
+        return torch.cuda.current_stream(self.device), self._side
+
+    def on(self, stream):
+        return torch.cuda.stream(stream)
+
+    def record(self, stream):
+        e = torch.cuda.Event()
+        e.record(stream)
+        return e
+
+    def wait(self, stream, event):
+        if event is not None:
+            stream.wait_event(event)
+
     def zeros(self, *shape):
         return torch.zeros(*shape, dtype=F64, device=self.device)
 
@@ -152,18 +199,23 @@ class CudaBackend(object):
         return out
 
     @staticmethod
-    def _act(act):
-        return (ctypes.c_int64 * len(act))(*[int(a) for a in act])
+    def _starts(row_start, rows):
+        import numpy as np
+        a = np.ascontiguousarray(row_start, dtype=np.int64)
+        assert a.shape == (rows,)
+        return a, a.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
 
-    def trsm_rlt_prefix_(self, Lm, B, act):
+    def trsm_rlt_prefix_(self, Lm, B, row_start):
         h, L = self._h(), self._L
         vl, vb = L.view(Lm), L.view(B)
-        h.check(h.lib.gps_trsm_rlt_prefix(h.ptr, vl.ref, vb.ref, self._act(act), len(act)))
+        keep, ptr = self._starts(row_start, B.shape[0])
+        h.check(h.lib.gps_trsm_rlt_prefix(h.ptr, vl.ref, vb.ref, ptr))
 
-    def trsm_rln_prefix_(self, Lm, Lt, B, act):
+    def trsm_rln_prefix_(self, Lm, Lt, B, row_start):
         h, L = self._h(), self._L
         vl, vt, vb = L.view(Lm), L.view(Lt), L.view(B)
-        h.check(h.lib.gps_trsm_rln_prefix(h.ptr, vl.ref, vt.ref, vb.ref, self._act(act), len(act)))
+        keep, ptr = self._starts(row_start, B.shape[0])
+        h.check(h.lib.gps_trsm_rln_prefix(h.ptr, vl.ref, vt.ref, vb.ref, ptr))
 
     def weight_rows_(self, W, grow, beta, block):
         h, L = self._h(), self._L
@@ -222,7 +274,7 @@ class _Comm(object):
 
 
 # --------------------------------------------------------------------------------- the path
-def factor(prog, theta, noise, X, Yc, lay, comm, be):
+def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
     """Distributed Gram + Cholesky.  Returns (Lfull [N, ld] with the lower block triangle of
     L -- identical on every rank --, alpha_t [R, N] = (L^-1 Yc)^T)."""
     N, R = Yc.shape
@@ -243,6 +295,7 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be):
         Aloc[o:o + r1 - r0, r0:r1].diagonal().add_(noise)
         grow[o:o + r1 - r0] = torch.arange(r0, r1, dtype=torch.int64, device=dev)
     Aloc[nloc:, :N] = Yc.t()
+    _mark('gram')
 
     Lfull = be.zeros(N, ld)
     # static maps for unpacking gathered panels: owner and local row of every global row
@@ -264,7 +317,25 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be):
     send_buf = be.empty(mmax_all * bs)
     recv_buf = be.empty(P * mmax_all * bs) if P > 1 else None
 
-    for k in range(lay.nblk):
+    import numpy as np
+
+    def update(k, c_lo, c_hi):
+        """my rows below block row k, global columns [c_lo, c_hi):  A -= P_k L[c_lo:c_hi, k]^T,
+        lower part only (by the global index of each local row); ride-along rows unmasked."""
+        if c_hi <= c_lo:
+            return
+        k0, k1 = lay.rows(k)
+        lo, mrows = below_all[k][rank]
+        flops = 2.0 * (k1 - k0) * R * (c_hi - c_lo)            # algorithmic flops of this launch
+        for b in mine:
+            if b > k:
+                g = np.arange(*lay.rows(b))
+                flops += 2.0 * (k1 - k0) * float(np.clip(np.minimum(g, c_hi - 1) - c_lo + 1, 0, None).sum())
+        be.gemm_rowmap_(Aloc[lo:, k0:k1], Lfull[c_lo:c_hi, k0:k1], Aloc[lo:, c_lo:c_hi], grow[lo:], c_lo,
+                        flops)
+
+    def panel(k):
+        """factor the diagonal block, broadcast it, solve my panel rows, all-gather the panel."""
         r0, r1 = lay.rows(k)
         nb = r1 - r0
         own = lay.owner(k)
@@ -273,14 +344,15 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be):
             D = Aloc[offs[k]:offs[k] + nb, r0:r1]
             be.potrf_(D)
             Lkk.copy_(D)
+        _mark('potrf_diag', fine=True)
         comm.broadcast(Lkk, own)
         Lfull[r0:r1, r0:r1] = Lkk
         lo, mrows = below_all[k][rank]
         Pn = Aloc[lo:, r0:r1]                       # my panel rows + the ride-along rows
         be.trsm_rlt_(Lkk, Pn)
+        _mark('bcast+panel_trsm', fine=True)
         if k == lay.nblk - 1:
-            break
-        # ---- all-gather the solved panel: every rank ends up with column k of L
+            return
         if P > 1:
             mmax = max(m for _, m in below_all[k])
             send = send_buf[:mmax * nb].view(mmax, nb)
@@ -293,30 +365,64 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be):
             Lfull[r1:, r0:r1] = recv.view(P * mmax, nb).index_select(0, src)
         else:
             Lfull[r1:, r0:r1] = Pn[:mrows]
-        # ---- trailing update of my rows (lower part only, by global row index)
-        flops = 2.0 * nb * R * (N - r1)            # algorithmic flops of my masked update
-        for b in mine:
-            if b > k:
-                b0, b1 = lay.rows(b)
-                flops += 2.0 * nb * ((b1 - b0) * (b0 - r1 + 1) + (b1 - b0) * (b1 - b0 - 1) / 2.0)
-        be.gemm_rowmap_(Pn, Lfull[r1:N, r0:r1], Aloc[lo:, r1:N], grow[lo:], r1, flops)
+        _mark('gather+unpack', fine=True)
+
+    _mark('setup')
+    streams = be.streams() if lookahead else None
+    if streams is None:
+        # plain right-looking order
+        for k in range(lay.nblk):
+            panel(k)
+            if k < lay.nblk - 1:
+                update(k, lay.rows(k)[1], N)
+                _mark('trailing_gemm', fine=True)
+    else:
+        # look-ahead of one panel: the SIDE stream (high priority) carries the critical path --
+        # block column k+1 is updated with panel k alone, factored, solved and gathered -- while
+        # the MAIN stream is still applying panel k to the columns right of it.
+        global _FINE
+        _FINE = False
+        main, side = streams
+        ev_panel = [None] * lay.nblk
+        ev_bulk = [None] * lay.nblk
+        start = be.record(main)
+        for k in range(lay.nblk):
+            with be.on(side):
+                be.wait(side, start if k == 0 else None)
+                if k >= 2:
+                    be.wait(side, ev_bulk[k - 2])       # column k has seen panels <= k-2
+                if k >= 1:
+                    update(k - 1, *lay.rows(k))         # ... and now panel k-1
+                panel(k)
+                ev_panel[k] = be.record(side)
+            if k < lay.nblk - 1:
+                with be.on(main):
+                    be.wait(main, ev_panel[k])
+                    if k + 2 <= lay.nblk - 1:
+                        update(k, lay.rows(k + 2)[0], N)
+                    ev_bulk[k] = be.record(main)
+        be.wait(main, ev_panel[lay.nblk - 1])
+        _FINE = True
+        _mark('factor(lookahead)')
     alpha_t = Aloc[nloc:, :N]
     return Lfull, alpha_t
 
 
-def nlml_and_grad(prog, theta, noise, X, Yc, block=512, group=None, backend=None, want_grad=True):
+def nlml_and_grad(prog, theta, noise, X, Yc, block=512, group=None, backend=None, want_grad=True,
+                  lookahead=True):
     """NLML of GPR and its gradient w.r.t. (theta, noise, Yc), computed by all ranks of
     `group` together.  Inputs are replicated (X is N x D: small); every rank returns the same
     values.  Returns (nlml, dtheta, dnoise, dYc) -- 0-d / [n_theta] / 0-d / [N, R] tensors;
     the gradients are None when want_grad is False."""
     comm = _Comm(group)
     be = backend if backend is not None else CudaBackend(X.device)
+    _mark('start')
     N, R = Yc.shape
     if R < 1 or R > 16:
         raise ValueError('1..16 output columns supported')
     noise = float(noise)
     lay = BlockRowLayout(N, block, comm.world)
-    Lfull, alpha_t = factor(prog, theta, noise, X, Yc, lay, comm, be)
+    Lfull, alpha_t = factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=lookahead)
     Lsq = Lfull[:, :N]
     logdet = be.sum_log_diag(Lsq)
     nlml = 0.5 * N * R * math.log(2.0 * math.pi) + R * logdet + 0.5 * (alpha_t ** 2).sum()
@@ -342,16 +448,18 @@ def nlml_and_grad(prog, theta, noise, X, Yc, block=512, group=None, backend=None
         growB[o - R:o - R + r1 - r0] = torch.arange(r0, r1, dtype=torch.int64, device=dev)
         starts.append((r0, o - R, r1 - r0))
         o += r1 - r0
-    n128 = (N + 127) // 128
-    act_u = []
-    for j in range(n128):
-        end = (j + 1) * 128
-        act_u.append(sum(nr for (r0, _, nr) in starts if r0 < end))
-    act = [a + R for a in act_u]
+    import numpy as np
+    # first column of every row: its block start (alpha rows: 0)
+    start_u = np.concatenate([np.full(nr, r0, dtype=np.int64) for (r0, _, nr) in starts]
+                             or [np.zeros(0, dtype=np.int64)])
+    start_all = np.concatenate([np.zeros(R, dtype=np.int64), start_u])
     Lt = be.transpose(Lsq)
+    _mark('nlml+inv_setup')
     if m > R:
-        be.trsm_rlt_prefix_(Lsq, B[R:], act_u)            # rows of U = L^-T
-    be.trsm_rln_prefix_(Lsq, Lt, B, act)                  # beta^T ; rows of K^-1 (cols >= block)
+        be.trsm_rlt_prefix_(Lsq, B[R:], start_u)          # rows of U = L^-T
+    _mark('rows_of_U')
+    be.trsm_rln_prefix_(Lsq, Lt, B, start_all)            # beta^T ; rows of K^-1 (cols >= block)
+    _mark('rows_of_Kinv')
     beta_t = B[:R]
     out = torch.zeros(prog.n_theta + 1, dtype=F64, device=dev)
     if m > R:
@@ -360,4 +468,5 @@ def nlml_and_grad(prog, theta, noise, X, Yc, block=512, group=None, backend=None
         out[prog.n_theta] = W[torch.arange(m - R, device=dev), growB].sum()     # tr W
         out[:prog.n_theta] = be.gram_bwd(prog, theta, X.index_select(0, growB), X, W)
     comm.all_reduce_sum(out)
+    _mark('contract+allreduce')
     return nlml, out[:prog.n_theta], out[prog.n_theta], beta_t.t().contiguous()

@@ -391,12 +391,13 @@ class _GprLogLikDist(torch.autograd.Function):
     distributed Cholesky / inverse, _backend/dist_gpr.py)."""
 
     @staticmethod
-    def forward(ctx, theta, noise, Yc, X, prog, group, block):
+    def forward(ctx, theta, noise, Yc, X, prog, group, block, lookahead):
         from . import dist_gpr
         X, Yc, theta = _prep(X), _prep(Yc), _prep(theta)
         want_grad = any(ctx.needs_input_grad[:3])
         nlml, dtheta, dnoise, dY = dist_gpr.nlml_and_grad(prog, theta.detach(), float(noise), X, Yc.detach(),
-                                                          block=block, group=group, want_grad=want_grad)
+                                                          block=block, group=group, want_grad=want_grad,
+                                                          lookahead=lookahead)
         ctx.grads = (dtheta, dnoise, dY)
         return -nlml
 
@@ -406,7 +407,7 @@ class _GprLogLikDist(torch.autograd.Function):
         gt = -g * dtheta if ctx.needs_input_grad[0] else None
         gn = -g * dnoise if ctx.needs_input_grad[1] else None
         gy = -g * dY if ctx.needs_input_grad[2] else None
-        return gt, gn, gy, None, None, None, None
+        return gt, gn, gy, None, None, None, None, None
 
 
 def gpr_loglik(prog, X, Yc, noise):
@@ -415,7 +416,7 @@ def gpr_loglik(prog, X, Yc, noise):
     from .. import parallel
     if parallel.active():
         return _GprLogLikDist.apply(prog.theta(X.device), noise.reshape(()), Yc, X, prog,
-                                    parallel.group(), parallel.block())
+                                    parallel.group(), parallel.block(), parallel.lookahead())
     return _GprLogLik.apply(prog.theta(X.device), noise.reshape(()), Yc, X, prog)
 
 

@@ -12,10 +12,10 @@ section 2.2); this module is what shards its hot path where it shards naturally:
 """
 import torch
 
-_STATE = {'active': False, 'group': None, 'block': 512}
+_STATE = {'active': False, 'group': None, 'block': 512, 'lookahead': True}
 
 
-def init(group=None, block=512, backend='nccl', device=None):
+def init(group=None, block=512, backend='nccl', device=None, lookahead=True):
     """Activate the distributed paths.  If torch.distributed is not initialised yet and the
     torchrun environment variables are present, initialise it (backend NCCL)."""
     import os
@@ -25,7 +25,7 @@ def init(group=None, block=512, backend='nccl', device=None):
             device = torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0)))
             torch.cuda.set_device(device)
         dist.init_process_group(backend, device_id=device if backend == 'nccl' else None)
-    _STATE.update(active=True, group=group, block=int(block))
+    _STATE.update(active=True, group=group, block=int(block), lookahead=bool(lookahead))
 
 
 def shutdown():
@@ -42,6 +42,10 @@ def group():
 
 def block():
     return _STATE['block']
+
+
+def lookahead():
+    return _STATE['lookahead']
 
 
 def world_size():

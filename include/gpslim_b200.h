@@ -177,14 +177,16 @@ int gps_transpose(gps_handle* h, const DLTensor* A, DLTensor* At_out);
  *   A22 -= L21 L21^T of tf.cholesky (models/gpr.py:70) restricted to the lower triangle when
  *   the rows of A22 are a block-cyclic subset.  Tiles wholly above the limit are skipped.
  *   `flops` (>= 0) is what the profile option books for the launch.
- * gps_trsm_rlt_prefix: B <- B L^-T where, for the columns of 128-block b, only the first
- *   active_rows[b] rows of B are solved (HOST array, one entry per 128-block of L,
- *   non-decreasing; NULL = all rows).  With B = rows of the identity sorted by column this
- *   yields rows of U = L^-T at their true flop count.
+ * gps_trsm_rlt_prefix: B <- B L^-T where row r of B is identically zero left of column
+ *   row_start[r] (HOST int64 array, one entry per row of B, non-decreasing multiples of 128;
+ *   NULL = all zeros, i.e. the plain solve).  Rows that have not started yet are skipped and
+ *   the leading zero K-range of every update tile is never read: with B = rows of the
+ *   identity sorted by column this yields rows of U = L^-T at their true flop count.
  * gps_trsm_rln_prefix: B <- B L^-1 (the solve against the untransposed factor), columns right
- *   to left, same prefix rule; Lt = L^T (row-major upper) must be supplied so that every
- *   product is K-contiguous.  Rows of U go in, rows of K^-1 = L^-T L^-1 come out
- *   (the O(N^3) part of TensorFlow's Cholesky gradient, examples/gpr.py:53-54).
+ *   to left; row r only WANTS the columns >= row_start[r] (what lies left of it is left
+ *   undefined).  Lt = L^T (row-major upper) must be supplied so that every product is
+ *   K-contiguous.  Rows of U go in, rows of K^-1 = L^-T L^-1 come out (the O(N^3) part of
+ *   TensorFlow's Cholesky gradient, examples/gpr.py:53-54).
  * gps_gpr_weight_rows: W[r,j] <- m(r,j)/2 (R K^-1[g_r,j] - sum_q beta_q[g_r] beta_q[j]) in
  *   place on a row panel of K^-1; g_r = row_index[r]; m = 0 left of g_r's block (of size
  *   `block`), 1 inside it, 2 to the right (symmetric counterpart).
@@ -193,9 +195,9 @@ int gps_gemm_nt_rowmap(gps_handle* h, double alpha, const DLTensor* A, const DLT
                        double beta, DLTensor* C, const DLTensor* row_limit, int64_t col_offset,
                        double flops);
 int gps_trsm_rlt_prefix(gps_handle* h, const DLTensor* L, DLTensor* B_inout,
-                        const int64_t* active_rows, int64_t n_blocks);
+                        const int64_t* row_start);
 int gps_trsm_rln_prefix(gps_handle* h, const DLTensor* L, const DLTensor* Lt, DLTensor* B_inout,
-                        const int64_t* active_rows, int64_t n_blocks);
+                        const int64_t* row_start);
 int gps_gpr_weight_rows(gps_handle* h, DLTensor* W_inout, const DLTensor* row_index,
                         const DLTensor* beta, int64_t block);
 

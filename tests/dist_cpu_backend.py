@@ -13,6 +13,21 @@ class CpuBackend(object):
     def __init__(self, spec_fn):
         self.spec_fn = spec_fn
 
+    # look-ahead "streams": sequential execution in issue order is one valid schedule of the
+    # dependency graph, so the look-ahead ORDER of operations is what gets tested here
+    def streams(self):
+        return 'main', 'side'
+
+    def on(self, stream):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def record(self, stream):
+        return None
+
+    def wait(self, stream, event):
+        pass
+
     def empty(self, *shape):
         return torch.full(tuple(shape), float('nan'), dtype=F64)   # poison: unwritten reads show up
 
@@ -38,24 +53,23 @@ class CpuBackend(object):
     def transpose(self, A):
         return A.T.contiguous()
 
-    def trsm_rlt_prefix_(self, Lm, B, act):
+    def trsm_rlt_prefix_(self, Lm, B, row_start):
+        # the real kernel never reads what lies left of row_start: poison it to prove that
+        n = Lm.shape[0]
+        cols = torch.arange(n)[None, :]
+        left = cols < torch.as_tensor(row_start)[:, None]
+        assert bool((B[left] == 0).all())
         X = torch.linalg.solve_triangular(torch.tril(Lm), B.T, upper=False).T
-        for j, a in enumerate(act):                       # only the active prefix is written
-            B[:a, j * 128:(j + 1) * 128] = X[:a, j * 128:(j + 1) * 128]
+        B.copy_(torch.where(left, torch.zeros_like(X), X))
 
-    def trsm_rln_prefix_(self, Lm, Lt, B, act):
+    def trsm_rln_prefix_(self, Lm, Lt, B, row_start):
         assert torch.equal(torch.triu(Lt), torch.tril(Lm).T)
         n = Lm.shape[0]
-        nblk = len(act)
-        # right to left over 128-blocks, honouring the prefix rule exactly
-        Ltri = torch.tril(Lm)
-        for j in reversed(range(nblk)):
-            c0, c1 = j * 128, min(n, (j + 1) * 128)
-            a = act[j]
-            if a == 0:
-                continue
-            rhs = B[:a, c0:c1] - B[:a, c1:] @ Ltri[c1:, c0:c1]
-            B[:a, c0:c1] = torch.linalg.solve_triangular(Ltri[c0:c1, c0:c1], rhs, upper=False, left=False)
+        cols = torch.arange(n)[None, :]
+        left = cols < torch.as_tensor(row_start)[:, None]
+        X = torch.linalg.solve_triangular(torch.tril(Lm), B, upper=False, left=False)
+        # left of row_start the result is undefined in the real kernel: poison it
+        B.copy_(torch.where(left, torch.full_like(X, float('nan')), X))
 
     def weight_rows_(self, W, grow, beta, block):
         n = W.shape[1]
@@ -64,7 +78,7 @@ class CpuBackend(object):
         bb = beta[:, grow].T @ beta                        # [m, N]
         v = 0.5 * (beta.shape[0] * W - bb)
         v = torch.where(cols[None, :] >= c0 + block, 2.0 * v, v)
-        W.copy_(torch.where(cols[None, :] >= c0, v, torch.zeros_like(v)))
+        W.copy_(torch.where(cols[None, :] >= c0, v, torch.zeros_like(v)))   # drops the poison
 
     def gram_bwd(self, prog, theta, Xr, Xc, W):
         th = theta.detach().clone().requires_grad_(True)

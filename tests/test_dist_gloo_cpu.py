@@ -40,7 +40,7 @@ def _oracle(n, d, r, noise, ls):
     return X, Y, th.detach(), obj.detach(), [t.detach() for t in g]
 
 
-def _worker(rank, world, port, n, d, r, block, out_q):
+def _worker(rank, world, port, n, d, r, block, lookahead, out_q):
     sys.path.insert(0, HERE)
     import torch.distributed as dist
     from dist_cpu_backend import CpuBackend
@@ -54,7 +54,7 @@ def _worker(rank, world, port, n, d, r, block, out_q):
         n_theta = 1 + d
     be = CpuBackend(lambda t: _spec(t, d))
     nlml, dth, dnz, dY = dist_gpr.nlml_and_grad(Prog(), th, 0.1, torch.tensor(X), torch.tensor(Y),
-                                                block=block, backend=be)
+                                                block=block, backend=be, lookahead=lookahead)
 
     def rel(a, b):
         return float((a - b).abs().max() / b.abs().max())
@@ -65,12 +65,13 @@ def _worker(rank, world, port, n, d, r, block, out_q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world,n,r,block', [(1, 700, 1, 256), (2, 900, 2, 128), (3, 1100, 1, 256)])
-def test_distributed_gpr_host_logic_matches_oracle(world, n, r, block):
+@pytest.mark.parametrize('world,n,r,block,lookahead', [(1, 700, 1, 256, True), (2, 900, 2, 128, True),
+                                                       (3, 1100, 1, 256, True), (2, 600, 1, 128, False)])
+def test_distributed_gpr_host_logic_matches_oracle(world, n, r, block, lookahead):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(i, world, port, n, 3, r, block, q)) for i in range(world)]
+    procs = [ctx.Process(target=_worker, args=(i, world, port, n, 3, r, block, lookahead, q)) for i in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in range(world)]

@@ -20,7 +20,7 @@ def rel(a, b):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--n', type=int, default=3000)
+    ap.add_argument('--size', type=int, default=3000, dest='n')
     ap.add_argument('--block', type=int, default=256)
     args = ap.parse_args()
     import gpflowSlim as gpf

@@ -16,11 +16,12 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--n', type=int, default=16384)
+    ap.add_argument('--size', type=int, default=16384, dest='n')
     ap.add_argument('--d', type=int, default=8)
     ap.add_argument('--block', type=int, default=512)
     ap.add_argument('--reps', type=int, default=3)
     ap.add_argument('--fused', type=int, default=1)
+    ap.add_argument('--lookahead', type=int, default=1)
     args = ap.parse_args()
     import gpflowSlim as gpf
     from bench import synth_gpr
@@ -66,8 +67,15 @@ def main():
     ref = None
     if args.fused and rank == 0 or (args.fused and world > 1):
         ref = timeit('fused 1-GPU')
-    gpf.parallel.init(block=args.block)
+    gpf.parallel.init(block=args.block, lookahead=bool(args.lookahead))
     o, g = timeit('distributed')
+    from gpflowSlim._backend import dist_gpr
+    dist_gpr.TIMER = dist_gpr.PhaseTimer()
+    step()
+    rep = dist_gpr.TIMER.report()
+    dist_gpr.TIMER = None
+    if rank == 0:
+        print('phases (ms): ' + ', '.join('%s %.1f' % kv for kv in rep.items()), flush=True)
     gpf.parallel.shutdown()
     if ref is not None and rank == 0:
         err = max([abs(float(o) - float(ref[0])) / abs(float(ref[0]))] +
