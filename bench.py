@@ -51,6 +51,18 @@ def fp64_peak():
             'source': 'nominal datasheet FP64 (no measurement available)'}
 
 
+def gemm_traffic():
+    """DRAM bytes of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r01_gemm8192_ncu_full.json: one 8192^3 launch), with its algorithmic bytes."""
+    p = os.path.join(ROOT, 'profiles', 'r01_gemm8192_ncu_full.json')
+    if not os.path.exists(p):
+        return None, None
+    s = json.load(open(p))['_summary']
+    return s['dram_traffic_bytes_per_launch'], {
+        'launch': s['kernel'], 'algorithmic_bytes': s['algorithmic_bytes_per_launch'],
+        'source': 'profiles/r01_gemm8192_ncu_full.json (dram__bytes_read.sum + dram__bytes_write.sum)'}
+
+
 class ClockSampler(threading.Thread):
     FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
               'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
@@ -100,6 +112,32 @@ def oracle_eval(n, d, reps, threads=None):
         torch.autograd.grad(obj, raw)
         times.append(time.perf_counter() - t0)
     return times
+
+
+def potrf_metric(gpf, model, dev, n, peak, reps=3):
+    """BASELINE.json metric (ii): Cholesky TFLOP/s (N^3/3 flop) of K + noise I at the bench size,
+    gps_potrf timed alone with CUDA events, against the measured FP64 peak."""
+    import ctypes
+    from gpflowSlim._backend import lib as L
+    h = L.handle_for(dev)
+    with torch.no_grad():
+        K = model.kern.K(model.X)
+        K.diagonal().add_(float(model.likelihood.variance))
+        A = torch.empty_like(K)
+        times = []
+        for _ in range(reps + 1):
+            A.copy_(K)
+            va = L.view(A)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            h.check(h.lib.gps_potrf(h.ptr, va.ref, 0, None))
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+    ms = float(np.mean(times[1:]))
+    tf = float(n) ** 3 / 3.0 / (ms * 1e-3) / 1e12
+    del K, A
+    return {'n': n, 'ms': ms, 'tflops': tf, 'frac_of_fp64_peak': tf / peak['burst'], 'flops': 'N^3/3'}
 
 
 def run_reference(args):
@@ -232,6 +270,7 @@ def main():
         ach = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
         # the GEMM launches run back to back inside a ~1 s step: sustained figure applies
         pk = peak['sustained']
+        traffic, traffic_note = gemm_traffic()
         nparam = d + 2
         nprob = world if mode == 'independent' else 1     # problems evaluated per step, whole job
         par = {'fused': 'single GPU, fused path', 'independent': 'independent problem per GPU',
@@ -253,12 +292,15 @@ def main():
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': {'bound': 'tensor', 'kernel': 'gemm_nt_dmma_kernel (FP64 DMMA)', 'achieved': ach,
-                         'peak': pk, 'unit': 'TFLOP/s', 'frac': ach / pk if pk else None, 'traffic': None,
+                         'peak': pk, 'unit': 'TFLOP/s', 'frac': ach / pk if pk else None, 'traffic': traffic,
+                         'traffic_of': traffic_note,
                          'peak_source': peak['source'],
                          'gemm_share_of_step': gemm_ms / (ms * args.steps) if ms > 0 else None,
                          'scope': 'rank 0' if world > 1 else 'the GPU',
                          'step_tflops_vs_n3': nprob * float(n) ** 3 / (ms * 1e-3) / 1e12},
         }
+        if world == 1:
+            line['potrf'] = potrf_metric(gpf, model, dev, n, peak)
         if world == 1 and not args.no_cpu_baseline:
             ns = args.cpu_n
             cores = os.cpu_count()

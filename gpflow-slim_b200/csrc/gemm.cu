@@ -252,7 +252,9 @@ double gemm_flops(const GemmArgs& g) {
   // algorithmic flops honouring the triangular structure (tile granularity is not counted)
   double full = 2.0 * (double)g.M * (double)g.N * (double)g.K;
   double f = full;
-  if (g.c_uplo == C_LOWER && g.M == g.N) f *= 0.5;
+  // lower-masked C with M >= N (rows beneath ride along): N^2/2 + (M - N) N outputs
+  if (g.c_uplo == C_LOWER && g.M >= g.N)
+    f = 2.0 * (double)g.K * (0.5 * (double)g.N * (double)g.N + (double)(g.M - g.N) * (double)g.N);
   if (g.a_tri != TRI_NONE && g.b_tri != TRI_NONE)
     f = (g.c_uplo == C_LOWER) ? full / 6.0 : full / 3.0;
   else if (g.a_tri != TRI_NONE || g.b_tri != TRI_NONE)
