@@ -13,6 +13,8 @@
 // 128-wide operand tiles are never loaded or multiplied (this is what makes TRMM-, TRTRI- and
 // LAUUM-shaped products cost their true flop count).  c_uplo = lower computes only tiles that
 // intersect the lower triangle and masks stores above the diagonal.
+#include <cuda.h>
+
 #include "internal.cuh"
 
 namespace {
@@ -116,6 +118,100 @@ __device__ __forceinline__ void load_stage(const GemmArgs& g, double* stage, int
   }
 }
 
+// Ask L2 for the C tile at the start of a read-modify-write tile (beta != 0), so that the
+// epilogue's loads find it there: 128 rows x 8 lines of 128 B, 4 lines per thread.
+__device__ __forceinline__ void prefetch_c_tile(const GemmArgs& g, int m0, int n0, int tid) {
+  if (g.beta == 0.0) return;
+  const int row = m0 + (tid >> 1);
+  if (row >= g.M) return;
+  const double* p = g.C + (int64_t)row * g.ldc + n0 + (tid & 1) * 64;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (n0 + (tid & 1) * 64 + q * 16 < g.N) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p + q * 16));
+}
+
+__device__ __forceinline__ void gemm_epilogue(const GemmArgs& g, double (&acc)[8][4][2], int m0, int n0,
+                                              int wm, int wn, int lr, int lc) {
+  const bool vec_ok = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+  const bool diag_tile = (g.c_uplo == C_LOWER) && (n0 + BN - 1 > m0);
+  if (g.c_uplo == C_ROWMAP) {
+    // block-row distributed lower update: per-row column limit
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int row = m0 + wm * 64 + i * 8 + lr;
+      if (row >= g.M) continue;
+      const int64_t lim = g.rowlim[row] - g.coff;   // last column this row may touch
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int col = n0 + wn * 32 + j * 8 + lc * 2;
+        if (col >= g.N) continue;
+        double* cp = g.C + (int64_t)row * g.ldc + col;
+        const double v0 = g.alpha * acc[i][j][0], v1 = g.alpha * acc[i][j][1];
+        if (col <= lim) cp[0] = (g.beta != 0.0) ? fma(g.beta, cp[0], v0) : v0;
+        if (col + 1 < g.N && col + 1 <= lim) cp[1] = (g.beta != 0.0) ? fma(g.beta, cp[1], v1) : v1;
+      }
+    }
+    return;
+  }
+  if (vec_ok && !diag_tile && m0 + BM <= g.M && n0 + BN <= g.N) {
+    // interior tile: all the old values of half a warp tile are requested before the first
+    // store, so the read-modify-write costs two memory round trips instead of eight
+    double* cbase = g.C + (int64_t)(m0 + wm * 64 + lr) * g.ldc + n0 + wn * 32 + lc * 2;
+    if (g.beta != 0.0) {
+#pragma unroll
+      for (int ih = 0; ih < 2; ++ih) {
+        double2 old[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            old[i][j] = __ldcg(reinterpret_cast<const double2*>(cbase + (int64_t)(ih * 4 + i) * 8 * g.ldc + j * 8));
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            double v0 = fma(g.beta, old[i][j].x, g.alpha * acc[ih * 4 + i][j][0]);
+            double v1 = fma(g.beta, old[i][j].y, g.alpha * acc[ih * 4 + i][j][1]);
+            *reinterpret_cast<double2*>(cbase + (int64_t)(ih * 4 + i) * 8 * g.ldc + j * 8) = make_double2(v0, v1);
+          }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<double2*>(cbase + (int64_t)i * 8 * g.ldc + j * 8) =
+              make_double2(g.alpha * acc[i][j][0], g.alpha * acc[i][j][1]);
+    }
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int row = m0 + wm * 64 + i * 8 + lr;
+    if (row >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int col = n0 + wn * 32 + j * 8 + lc * 2;
+      if (col >= g.N) continue;
+      bool ok0 = !diag_tile || col <= row;
+      bool ok1 = (col + 1 < g.N) && (!diag_tile || col + 1 <= row);
+      double* cp = g.C + (int64_t)row * g.ldc + col;
+      double v0 = g.alpha * acc[i][j][0], v1 = g.alpha * acc[i][j][1];
+      if (vec_ok && ok0 && ok1) {
+        if (g.beta != 0.0) {
+          double2 old = *reinterpret_cast<const double2*>(cp);
+          v0 = fma(g.beta, old.x, v0);
+          v1 = fma(g.beta, old.y, v1);
+        }
+        *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
+      } else {
+        if (ok0) cp[0] = (g.beta != 0.0) ? fma(g.beta, cp[0], v0) : v0;
+        if (ok1) cp[1] = (g.beta != 0.0) ? fma(g.beta, cp[1], v1) : v1;
+      }
+    }
+  }
+}
+
 template <bool VEC16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_dmma_kernel(const GemmArgs g) {
   extern __shared__ __align__(16) double smem[];
@@ -178,53 +274,178 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_dmma_kernel(const Gem
   }
   cp_async_wait<0>();
 
-  // epilogue
-  const bool vec_ok = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
-  const bool diag_tile = (g.c_uplo == C_LOWER) && (n0 + BN - 1 > m0);
-  if (g.c_uplo == C_ROWMAP) {
-    // block-row distributed lower update: per-row column limit
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int row = m0 + wm * 64 + i * 8 + lr;
-      if (row >= g.M) continue;
-      const int64_t lim = g.rowlim[row] - g.coff;   // last column this row may touch
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int col = n0 + wn * 32 + j * 8 + lc * 2;
-        if (col >= g.N) continue;
-        double* cp = g.C + (int64_t)row * g.ldc + col;
-        const double v0 = g.alpha * acc[i][j][0], v1 = g.alpha * acc[i][j][1];
-        if (col <= lim) cp[0] = (g.beta != 0.0) ? fma(g.beta, cp[0], v0) : v0;
-        if (col + 1 < g.N && col + 1 <= lim) cp[1] = (g.beta != 0.0) ? fma(g.beta, cp[1], v1) : v1;
-      }
-    }
-    return;
+  gemm_epilogue(g, acc, m0, n0, wm, wn, lr, lc);
+}
+
+// ------------------------------------------------------------------ TMA + mbarrier variant
+// The production kernel when both operands are 16-byte aligned with even leading dimensions
+// (every handle-owned buffer is).  Same tile / warp layout and the same tile-skipping rules as
+// above, but the operand tiles are staged by the TMA unit (cp.async.bulk.tensor.2d, one elected
+// producer thread) into a 6-deep ring of dense 128 x 16 boxes with the 128-byte hardware
+// swizzle, and the eight DMMA warps synchronise with the ring through per-stage full / empty
+// mbarriers only: there is no CTA-wide barrier in the main loop, the warps drift freely, and
+// no DMMA warp spends issue slots on address arithmetic or cp.async.
+//   smem: stage s = [A box 16 KiB][B box 16 KiB] at 1024-byte aligned offsets; element (r, k)
+//   of a box lives at  r*128 + (((k >> 1) ^ (r & 7)) << 4) + (k & 1)*8  (SWIZZLE_128B), which
+//   makes the m8n8k4 fragment loads (8 rows x 4 consecutive k per warp) bank-conflict free.
+constexpr int TBK = 16;                          // doubles per k-tile = one 128-byte swizzle row
+constexpr int TSTAGES = 6;
+constexpr int TBOX_BYTES = BM * TBK * 8;         // 16384
+constexpr int TSTAGE_BYTES = 2 * TBOX_BYTES;     // 32768
+constexpr int TMA_THREADS = GEMM_THREADS;        // 8 DMMA warps; lane 0 of warp 0 also drives the TMA
+constexpr int TMA_SMEM = TSTAGES * TSTAGE_BYTES + 1024 + 2 * 8 * TSTAGES;
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t it = 0; !done; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (it > (1u << 24)) __trap();   // a lost arrival must fail loudly, never hang the GPU
   }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    int row = m0 + wm * 64 + i * 8 + lr;
-    if (row >= g.M) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int col = n0 + wn * 32 + j * 8 + lc * 2;
-      if (col >= g.N) continue;
-      bool ok0 = !diag_tile || col <= row;
-      bool ok1 = (col + 1 < g.N) && (!diag_tile || col + 1 <= row);
-      double* cp = g.C + (int64_t)row * g.ldc + col;
-      double v0 = g.alpha * acc[i][j][0], v1 = g.alpha * acc[i][j][1];
-      if (vec_ok && ok0 && ok1) {
-        if (g.beta != 0.0) {
-          double2 old = *reinterpret_cast<const double2*>(cp);
-          v0 = fma(g.beta, old.x, v0);
-          v1 = fma(g.beta, old.y, v1);
-        }
-        *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
-      } else {
-        if (ok0) cp[0] = (g.beta != 0.0) ? fma(g.beta, cp[0], v0) : v0;
-        if (ok1) cp[1] = (g.beta != 0.0) ? fma(g.beta, cp[1], v1) : v1;
-      }
-    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
+  return v;
+}
+
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+gemm_nt_tma_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmA,
+                   const __grid_constant__ CUtensorMap tmB) {
+  extern __shared__ __align__(16) double smem[];
+  int ti, tj;
+  tile_coords(g, blockIdx.x, ti, tj);
+  const int m0 = ti * BM, n0 = tj * BN;
+  if (g.c_uplo == C_LOWER && m0 + BM - 1 < n0) return;
+  if (g.c_uplo == C_ROWMAP && (int64_t)n0 + g.coff > g.rowlim[min(m0 + BM, g.M) - 1]) return;
+  if (g.lo_mode == 2 && (int64_t)n0 + BN - 1 + g.lo_off < g.rowlo[m0]) return;
+
+  int klo, khi;
+  k_range(g, ti, tj, klo, khi);
+  if (g.lo_mode == 1) {
+    int64_t lo = g.rowlo[m0] - g.lo_off;
+    if (lo > klo) klo = (int)(lo < khi ? lo / TBK * TBK : khi);
   }
+  const int nk = (khi > klo) ? (khi - klo + TBK - 1) / TBK : 0;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(smem) + 1023u) & ~1023u;
+  const uint32_t bar_full = base + TSTAGES * TSTAGE_BYTES;
+  const uint32_t bar_empty = bar_full + 8 * TSTAGES;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TSTAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);                    // the producer's arrive.expect_tx
+      mbar_init(bar_empty + 8 * s, GEMM_THREADS / 32);   // one arrival per DMMA warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  prefetch_c_tile(g, m0, n0, tid);
+
+  // ---------------- producer duty: lane 0 of warp 0 feeds the ring.  Load L goes to slot
+  // L % TSTAGES; it is issued in the middle of iteration L - (TSTAGES - 1), i.e. one full
+  // iteration after the slot's previous contents were consumed, so the wait on the empty
+  // barrier is normally already satisfied and never holds up DMMA issue.
+  auto issue_load = [&](int L) {
+    const int sl = L % TSTAGES;
+    const uint32_t use = (uint32_t)(L / TSTAGES);
+    mbar_wait(bar_empty + 8 * sl, (use & 1u) ^ 1u);      // first use of a slot: returns at once
+    mbar_arrive_expect_tx(bar_full + 8 * sl, TSTAGE_BYTES);
+    const int k = klo + L * TBK;
+    tma_load_2d(base + sl * TSTAGE_BYTES, &tmA, k, m0, bar_full + 8 * sl);
+    tma_load_2d(base + sl * TSTAGE_BYTES + TBOX_BYTES, &tmB, k, n0, bar_full + 8 * sl);
+  };
+  if (tid == 0) {
+    for (int L = 0; L < TSTAGES - 1 && L < nk; ++L) issue_load(L);
+  }
+
+  // ---------------- consumers: 2 x 4 DMMA warps, warp tile 64 x 32
+  const int wm = warp >> 2, wn = warp & 3;
+  const int lr = lane >> 2, lc = lane & 3;
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  // byte offset of this lane's element inside a box row, for the four k-steps of a k-tile
+  uint32_t koff[TBK / 4];
+#pragma unroll
+  for (int kk = 0; kk < TBK / 4; ++kk)
+    koff[kk] = (uint32_t)((((2 * kk + (lc >> 1)) ^ lr) << 4) | ((lc & 1) << 3));
+  const uint32_t a_row = (uint32_t)(wm * 64 + lr) * 128u;
+  const uint32_t b_row = (uint32_t)TBOX_BYTES + (uint32_t)(wn * 32 + lr) * 128u;
+
+  double fa[2][8], fb[2][4];
+  int s = 0;
+  uint32_t ph = 0;
+  if (nk > 0) {
+    mbar_wait(bar_full, 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) fa[0][i] = lds_f64(base + a_row + i * 1024 + koff[0]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) fb[0][j] = lds_f64(base + b_row + j * 1024 + koff[0]);
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    const uint32_t sb = base + s * TSTAGE_BYTES;
+    int s2 = s + 1;
+    uint32_t ph2 = ph;
+    if (s2 == TSTAGES) { s2 = 0; ph2 ^= 1u; }
+#pragma unroll
+    for (int kk = 0; kk < TBK / 4; ++kk) {
+      const int cur = kk & 1, nxt = cur ^ 1;
+      // fragments of the next k-step are fetched while this one's DMMAs issue
+      if (kk + 1 < TBK / 4) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) fa[nxt][i] = lds_f64(sb + a_row + i * 1024 + koff[kk + 1]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) fb[nxt][j] = lds_f64(sb + b_row + j * 1024 + koff[kk + 1]);
+      } else if (kt + 1 < nk) {
+        const uint32_t nb = base + s2 * TSTAGE_BYTES;
+        mbar_wait(bar_full + 8 * s2, ph2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) fa[nxt][i] = lds_f64(nb + a_row + i * 1024 + koff[0]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) fb[nxt][j] = lds_f64(nb + b_row + j * 1024 + koff[0]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[cur][i], fb[cur][j]);
+      if (kk == 1 && tid == 0 && kt + TSTAGES - 1 < nk) issue_load(kt + TSTAGES - 1);
+    }
+    // every fragment of stage s has been consumed by a DMMA: hand the slot back
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+    s = s2;
+    ph = ph2;
+  }
+
+  gemm_epilogue(g, acc, m0, n0, wm, wn, lr, lc);
 }
 
 // plain-FMA check kernel with identical semantics (gps_set_option("gemm_impl", 1)); used by
@@ -246,6 +467,37 @@ __global__ void gemm_nt_naive_kernel(const GemmArgs g) {
   for (int k = klo; k < khi; ++k) s = fma(a[k], b[k], s);
   double* cp = g.C + (int64_t)row * g.ldc + col;
   *cp = (g.beta != 0.0) ? fma(g.beta, *cp, g.alpha * s) : g.alpha * s;
+}
+
+// 2-D tensor map of a row-major operand view: dims (K, rows), row stride ld, box 16 x 128,
+// 128-byte swizzle, out-of-bounds elements read as zero (edge tiles need no predicates).
+// cuTensorMapEncodeTiled is taken from the driver through the runtime (no -lcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+bool make_tensor_map(CUtensorMap* tm, const Mat& X) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)X.cols, (cuuint64_t)X.rows};
+  cuuint64_t strides[1] = {(cuuint64_t)X.ld * sizeof(double)};
+  cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)X.p, dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 double gemm_flops(const GemmArgs& g) {
@@ -315,10 +567,21 @@ int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, M
                  ((reinterpret_cast<uintptr_t>(A.p) & 15) == 0) &&
                  ((reinterpret_cast<uintptr_t>(B.p) & 15) == 0);
     unsigned grid = (unsigned)(g.tiles_m * g.tiles_n);
-    if (vec16)
+    // gemm_impl 0: TMA kernel whenever the operands qualify; 2: force the cp.async kernel
+    CUtensorMap tmA, tmB;
+    bool tma = vec16 && h->gemm_impl == 0 && g.K > 0 && make_tensor_map(&tmA, A) && make_tensor_map(&tmB, B);
+    if (tma) {
+      static bool tma_attr_set = false;
+      if (!tma_attr_set) {
+        cudaFuncSetAttribute(gemm_nt_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM);
+        tma_attr_set = true;
+      }
+      gemm_nt_tma_kernel<<<grid, TMA_THREADS, TMA_SMEM, h->stream>>>(g, tmA, tmB);
+    } else if (vec16) {
       gemm_nt_dmma_kernel<true><<<grid, GEMM_THREADS, GEMM_SMEM, h->stream>>>(g);
-    else
+    } else {
       gemm_nt_dmma_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM, h->stream>>>(g);
+    }
   }
   if (ev) cudaEventRecord(ev->b, h->stream);
   GPS_LAUNCH_CHECK(h);

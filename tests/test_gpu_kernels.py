@@ -24,8 +24,10 @@ def _spd(n, seed=0, cond_shift=None):
 
 
 @pytest.mark.parametrize('m,n,k', [(1, 1, 1), (5, 3, 2), (128, 128, 128), (129, 127, 65),
-                                   (300, 200, 17), (257, 513, 384), (1000, 1, 1000)])
-@pytest.mark.parametrize('impl', [0, 1])
+                                   (300, 200, 17), (257, 513, 384), (1000, 1, 1000),
+                                   (130, 260, 16), (64, 64, 8), (200, 300, 50), (385, 129, 4098),
+                                   (1000, 2, 1000), (127, 1, 2)])
+@pytest.mark.parametrize('impl', [0, 1, 2])
 def test_gemm_nt_matches_torch(m, n, k, impl):
     ops = _ops()
     from gpflowSlim._backend.lib import handle_for
@@ -41,7 +43,8 @@ def test_gemm_nt_matches_torch(m, n, k, impl):
 
 
 def test_gemm_nt_unaligned_views():
-    """Odd leading dimensions / 8-byte aligned bases take the 8-byte cp.async path."""
+    """Odd leading dimensions / 8-byte aligned bases take the 8-byte cp.async path (the TMA
+    kernel needs 16-byte aligned operands with even leading dimensions)."""
     ops = _ops()
     rng = np.random.default_rng(3)
     Abig, Bbig = rng.standard_normal((150, 141)), rng.standard_normal((140, 141))
@@ -50,10 +53,36 @@ def test_gemm_nt_unaligned_views():
     assert_close(out, Abig[3:140, 1:132] @ Bbig[5:133, 1:132].T, 1e-13, 'unaligned gemm')
 
 
+@pytest.mark.parametrize('impl', [0, 2])
 @pytest.mark.parametrize('n', [260, 700])
-def test_gemm_nt_triangular_modes(n):
+def test_gemm_nt_triangular_modes(n, impl):
+    """impl 0: TMA + mbarrier kernel (even n: operands qualify); impl 2: cp.async kernel."""
     ops = _ops()
-    from gpflowSlim._backend.lib import TRI_LOWER, TRI_UPPER
+    from gpflowSlim._backend.lib import TRI_LOWER, TRI_UPPER, handle_for
+    h = handle_for(dev())
+    h.set_option('gemm_impl', impl)
+    try:
+        _triangular_modes(ops, n, TRI_LOWER, TRI_UPPER)
+    finally:
+        h.set_option('gemm_impl', 0)
+
+
+def test_gemm_tma_submatrix_views_and_long_k():
+    """TMA path on aligned sub-matrix views (tensor-map dims must clip at the VIEW's edge, not the
+    parent's: out-of-range rows / k read as zero) and a K long enough to wrap the 6-stage ring
+    many times with a ragged tail."""
+    ops = _ops()
+    rng = np.random.default_rng(11)
+    Abig, Bbig = rng.standard_normal((400, 2100)), rng.standard_normal((300, 2100))
+    for (r0, r1, c0, c1, s0, s1) in [(2, 259, 16, 2066, 4, 133), (0, 400, 0, 2100, 0, 300),
+                                     (130, 131, 64, 66, 7, 8), (1, 129, 1024, 1040, 0, 128)]:
+        A, B = conv(Abig)[r0:r1, c0:c1], conv(Bbig)[s0:s1, c0:c1]
+        Cn = rng.standard_normal((r1 - r0, s1 - s0))
+        out = ops.gemm_nt(A, B, alpha=-1.0, beta=1.0, out=conv(Cn))
+        assert_close(out, Cn - Abig[r0:r1, c0:c1] @ Bbig[s0:s1, c0:c1].T, 1e-13, 'tma view gemm')
+
+
+def _triangular_modes(ops, n, TRI_LOWER, TRI_UPPER):
     rng = np.random.default_rng(n)
     Lo, Up, G = np.tril(rng.standard_normal((n, n))), np.triu(rng.standard_normal((n, n))), \
         rng.standard_normal((n, n))
