@@ -134,7 +134,12 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs& g, double (&acc)[8
                                               int wm, int wn, int lr, int lc) {
   const bool vec_ok = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
   const bool diag_tile = (g.c_uplo == C_LOWER) && (n0 + BN - 1 > m0);
-  if (g.c_uplo == C_ROWMAP) {
+  const bool full_tile = m0 + BM <= g.M && n0 + BN <= g.N;
+  // C_ROWMAP: rowlim is non-decreasing, so a tile whose last column is allowed in its first
+  // row is unmasked throughout (almost all tiles of a trailing update are)
+  const bool rowmap_masked =
+      (g.c_uplo == C_ROWMAP) && !(full_tile && (int64_t)n0 + BN - 1 + g.coff <= g.rowlim[m0]);
+  if (rowmap_masked) {
     // block-row distributed lower update: per-row column limit
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -153,7 +158,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs& g, double (&acc)[8
     }
     return;
   }
-  if (vec_ok && !diag_tile && m0 + BM <= g.M && n0 + BN <= g.N) {
+  if (vec_ok && !diag_tile && full_tile) {
     // interior tile: all the old values of half a warp tile are requested before the first
     // store, so the read-modify-write costs two memory round trips instead of eight
     double* cbase = g.C + (int64_t)(m0 + wm * 64 + lr) * g.ldc + n0 + wn * 32 + lc * 2;

@@ -149,9 +149,11 @@ class CudaBackend(object):
 
     # ---- streams / events for the look-ahead (CUDA streams, no tracing compiler)
     def streams(self):
+        """(main, chain, gather): the caller's stream and two high-priority side streams."""
         if getattr(self, '_side', None) is None:
-            self._side = torch.cuda.Stream(self.device, priority=-1)
-        return torch.cuda.current_stream(self.device), self._side
+            self._side = (torch.cuda.Stream(self.device, priority=-1),
+                          torch.cuda.Stream(self.device, priority=-1))
+        return (torch.cuda.current_stream(self.device),) + self._side
 
     def on(self, stream):
         return torch.cuda.stream(stream)
@@ -274,9 +276,45 @@ class _Comm(object):
 
 
 # --------------------------------------------------------------------------------- the path
+_MAPS = {}
+
+
+def _layout_maps(lay, P, dev):
+    """Static index maps of a layout (cached per shape and device): owner and local row of every
+    global row, and for every (panel, rank) the first local row below the panel."""
+    key = (lay.n, lay.block, P, str(dev))
+    hit = _MAPS.get(key)
+    if hit is not None:
+        return hit
+    own = torch.empty(lay.n, dtype=torch.int64)
+    lrow = torch.empty(lay.n, dtype=torch.int64)
+    for q in range(P):
+        oq, _ = lay.local_offsets(q)
+        for b, o in oq.items():
+            r0, r1 = lay.rows(b)
+            own[r0:r1] = q
+            lrow[r0:r1] = torch.arange(o, o + r1 - r0, dtype=torch.int64)
+    below_all = [[lay.rows_below(q, k) for q in range(P)] for k in range(lay.nblk)]
+    lo_table = torch.tensor([[l for l, _ in row] for row in below_all], dtype=torch.int64)
+    if len(_MAPS) > 8:
+        _MAPS.clear()
+    hit = _MAPS[key] = (own.to(dev), lrow.to(dev), below_all, lo_table.to(dev))
+    return hit
+
+
 def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
     """Distributed Gram + Cholesky.  Returns (Lfull [N, ld] with the lower block triangle of
-    L -- identical on every rank --, alpha_t [R, N] = (L^-1 Yc)^T)."""
+    L -- identical on every rank --, alpha_t [R, N] = (L^-1 Yc)^T).
+
+    With `lookahead` the work of panel k is spread over three CUDA streams:
+      chain  (high priority): factor diagonal block k -> broadcast -> solve my panel rows ->
+              broadcast the solved block row k+1 ("top block") -> apply panel k to block
+              column k+1.  This is the only serial dependency chain of the factorisation and
+              it never waits for an all-gather or for a bulk update of the same panel.
+      gather (high priority): all-gather of the solved panel k -> column k of L on every rank.
+      main:   panel k applied to block column k+2 first (its completion releases the chain two
+              panels ahead), then to everything right of it (one masked DMMA GEMM each).
+    """
     N, R = Yc.shape
     P, rank = comm.world, comm.rank
     bs = lay.block
@@ -298,30 +336,20 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
     _mark('gram')
 
     Lfull = be.zeros(N, ld)
-    # static maps for unpacking gathered panels: owner and local row of every global row
-    own_of_row = torch.empty(N, dtype=torch.int64, device=dev)
-    lrow_of_row = torch.empty(N, dtype=torch.int64, device=dev)
-    for q in range(P):
-        oq, _ = lay.local_offsets(q)
-        for b, o in oq.items():
-            r0, r1 = lay.rows(b)
-            own_of_row[r0:r1] = q
-            lrow_of_row[r0:r1] = torch.arange(o, o + r1 - r0, dtype=torch.int64, device=dev)
-
-    # first local row below block row k, for every (k, rank)
-    below_all = [[lay.rows_below(q, k) for q in range(P)] for k in range(lay.nblk)]
-    lo_table = torch.tensor([[l for l, _ in row] for row in below_all], dtype=torch.int64).to(dev)
+    own_of_row, lrow_of_row, below_all, lo_table = _layout_maps(lay, P, dev)
 
     Lkk_buf = be.empty(bs * bs)
+    top_buf = be.empty(bs * bs)
     mmax_all = max(lay.local_offsets(q)[1] for q in range(P))
-    send_buf = be.empty(mmax_all * bs)
+    send_buf = be.empty(mmax_all * bs) if P > 1 else None
     recv_buf = be.empty(P * mmax_all * bs) if P > 1 else None
 
     import numpy as np
 
-    def update(k, c_lo, c_hi):
+    def update(k, c_lo, c_hi, Bsrc=None):
         """my rows below block row k, global columns [c_lo, c_hi):  A -= P_k L[c_lo:c_hi, k]^T,
-        lower part only (by the global index of each local row); ride-along rows unmasked."""
+        lower part only (by the global index of each local row); ride-along rows unmasked.
+        Bsrc: the rows c_lo:c_hi of panel k when they are not taken from Lfull."""
         if c_hi <= c_lo:
             return
         k0, k1 = lay.rows(k)
@@ -331,11 +359,11 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
             if b > k:
                 g = np.arange(*lay.rows(b))
                 flops += 2.0 * (k1 - k0) * float(np.clip(np.minimum(g, c_hi - 1) - c_lo + 1, 0, None).sum())
-        be.gemm_rowmap_(Aloc[lo:, k0:k1], Lfull[c_lo:c_hi, k0:k1], Aloc[lo:, c_lo:c_hi], grow[lo:], c_lo,
-                        flops)
+        Bop = Lfull[c_lo:c_hi, k0:k1] if Bsrc is None else Bsrc
+        be.gemm_rowmap_(Aloc[lo:, k0:k1], Bop, Aloc[lo:, c_lo:c_hi], grow[lo:], c_lo, flops)
 
-    def panel(k):
-        """factor the diagonal block, broadcast it, solve my panel rows, all-gather the panel."""
+    def factor_diag_and_solve(k):
+        """factor the diagonal block, broadcast it, solve my panel rows (+ the ride-along rows)."""
         r0, r1 = lay.rows(k)
         nb = r1 - r0
         own = lay.owner(k)
@@ -351,6 +379,12 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
         Pn = Aloc[lo:, r0:r1]                       # my panel rows + the ride-along rows
         be.trsm_rlt_(Lkk, Pn)
         _mark('bcast+panel_trsm', fine=True)
+        return Pn, mrows
+
+    def gather_panel(k, Pn, mrows):
+        """all-gather of the solved panel k -> Lfull[r1:, r0:r1] on every rank."""
+        r0, r1 = lay.rows(k)
+        nb = r1 - r0
         if k == lay.nblk - 1:
             return
         if P > 1:
@@ -358,6 +392,8 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
             send = send_buf[:mmax * nb].view(mmax, nb)
             if mrows:
                 send[:mrows].copy_(Pn[:mrows])
+            if mrows < mmax:
+                send[mrows:].zero_()                # padding rows are never unpacked; keep them finite
             recv = recv_buf[:P * mmax * nb]
             comm.all_gather(recv, send.reshape(-1))
             oq = own_of_row[r1:]
@@ -367,41 +403,63 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
             Lfull[r1:, r0:r1] = Pn[:mrows]
         _mark('gather+unpack', fine=True)
 
+    def top_block(k):
+        """the solved block row k+1 of panel k, broadcast by its owner."""
+        r0, r1 = lay.rows(k)
+        t0, t1 = lay.rows(k + 1)
+        nxt = lay.owner(k + 1)
+        T = top_buf[:(t1 - t0) * (r1 - r0)].view(t1 - t0, r1 - r0)
+        if rank == nxt:
+            T.copy_(Aloc[offs[k + 1]:offs[k + 1] + t1 - t0, r0:r1])
+        comm.broadcast(T, nxt)
+        return T
+
     _mark('setup')
     streams = be.streams() if lookahead else None
     if streams is None:
         # plain right-looking order
         for k in range(lay.nblk):
-            panel(k)
+            Pn, mrows = factor_diag_and_solve(k)
+            gather_panel(k, Pn, mrows)
             if k < lay.nblk - 1:
                 update(k, lay.rows(k)[1], N)
                 _mark('trailing_gemm', fine=True)
     else:
-        # look-ahead of one panel: the SIDE stream (high priority) carries the critical path --
-        # block column k+1 is updated with panel k alone, factored, solved and gathered -- while
-        # the MAIN stream is still applying panel k to the columns right of it.
         global _FINE
         _FINE = False
-        main, side = streams
-        ev_panel = [None] * lay.nblk
-        ev_bulk = [None] * lay.nblk
+        main, chain, gath = streams
+        nblk = lay.nblk
+        ev_narrow = [None] * nblk
         start = be.record(main)
-        for k in range(lay.nblk):
-            with be.on(side):
-                be.wait(side, start if k == 0 else None)
-                if k >= 2:
-                    be.wait(side, ev_bulk[k - 2])       # column k has seen panels <= k-2
-                if k >= 1:
-                    update(k - 1, *lay.rows(k))         # ... and now panel k-1
-                panel(k)
-                ev_panel[k] = be.record(side)
-            if k < lay.nblk - 1:
+        be.wait(chain, start)
+        be.wait(gath, start)
+        ev_c = ev_g = None
+        for k in range(nblk):
+            with be.on(chain):
+                # block column k has seen panels <= k-2 (main, before ev_narrow[k-2]) and panel
+                # k-1 (chain, previous iteration)
+                Pn, mrows = factor_diag_and_solve(k)
+                ev_trsm = be.record(chain)
+                if k + 1 < nblk:
+                    T = top_block(k)
+                    if k >= 1:
+                        be.wait(chain, ev_narrow[k - 1])      # column k+1 has seen panels <= k-1
+                    update(k, *lay.rows(k + 1), Bsrc=T)
+                ev_c = be.record(chain)
+            if k + 1 < nblk:
+                with be.on(gath):
+                    be.wait(gath, ev_trsm)
+                    gather_panel(k, Pn, mrows)
+                    ev_g = be.record(gath)
                 with be.on(main):
-                    be.wait(main, ev_panel[k])
-                    if k + 2 <= lay.nblk - 1:
-                        update(k, lay.rows(k + 2)[0], N)
-                    ev_bulk[k] = be.record(main)
-        be.wait(main, ev_panel[lay.nblk - 1])
+                    be.wait(main, ev_g)
+                    if k + 2 < nblk:
+                        update(k, *lay.rows(k + 2))
+                    ev_narrow[k] = be.record(main)
+                    if k + 3 < nblk:
+                        update(k, lay.rows(k + 3)[0], N)
+        be.wait(main, ev_c)
+        be.wait(main, ev_g)
         _FINE = True
         _mark('factor(lookahead)')
     alpha_t = Aloc[nloc:, :N]

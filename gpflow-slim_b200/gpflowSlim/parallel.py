@@ -12,7 +12,7 @@ section 2.2); this module is what shards its hot path where it shards naturally:
 """
 import torch
 
-_STATE = {'active': False, 'group': None, 'block': 512, 'lookahead': True}
+_STATE = {'active': False, 'group': None, 'block': 512, 'lookahead': True, 'own_group': None}
 
 
 def init(group=None, block=512, backend='nccl', device=None, lookahead=True):
@@ -25,6 +25,17 @@ def init(group=None, block=512, backend='nccl', device=None, lookahead=True):
             device = torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0)))
             torch.cuda.set_device(device)
         dist.init_process_group(backend, device_id=device if backend == 'nccl' else None)
+    if group is None and dist.is_initialized() and dist.get_world_size() > 1 \
+            and dist.get_backend() == 'nccl' and _STATE.get('own_group') is None:
+        # a dedicated communicator whose NCCL stream has HIGH priority: the panel broadcasts and
+        # all-gathers of the distributed Cholesky sit on its critical path and must not queue
+        # behind the CTAs of a bulk trailing-update GEMM already in flight
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+        _STATE['own_group'] = dist.new_group(ranks=list(range(dist.get_world_size())), backend='nccl',
+                                             pg_options=opts)
+    if group is None:
+        group = _STATE.get('own_group')
     _STATE.update(active=True, group=group, block=int(block), lookahead=bool(lookahead))
 
 
