@@ -53,14 +53,14 @@ def fp64_peak():
 
 def gemm_traffic():
     """DRAM bytes of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r01_gemm8192_ncu_full.json: one 8192^3 launch), with its algorithmic bytes."""
-    p = os.path.join(ROOT, 'profiles', 'r01_gemm8192_ncu_full.json')
+    (profiles/r01_gemm8192_tma_ncu_full.json: one 8192^3 launch), with its algorithmic bytes."""
+    p = os.path.join(ROOT, 'profiles', 'r01_gemm8192_tma_ncu_full.json')
     if not os.path.exists(p):
         return None, None
     s = json.load(open(p))['_summary']
     return s['dram_traffic_bytes_per_launch'], {
         'launch': s['kernel'], 'algorithmic_bytes': s['algorithmic_bytes_per_launch'],
-        'source': 'profiles/r01_gemm8192_ncu_full.json (dram__bytes_read.sum + dram__bytes_write.sum)'}
+        'source': 'profiles/r01_gemm8192_tma_ncu_full.json (dram__bytes_read.sum + dram__bytes_write.sum)'}
 
 
 class ClockSampler(threading.Thread):
@@ -291,7 +291,7 @@ def main():
                     'd2h_bytes_per_step': int(8 * (1 + nparam))},
             'gpu_launches': int(launches),
             'clocks': clocks,
-            'roofline': {'bound': 'tensor', 'kernel': 'gemm_nt_dmma_kernel (FP64 DMMA)', 'achieved': ach,
+            'roofline': {'bound': 'tensor', 'kernel': 'gemm_nt_tma_kernel (FP64 DMMA, TMA-staged operands)', 'achieved': ach,
                          'peak': pk, 'unit': 'TFLOP/s', 'frac': ach / pk if pk else None, 'traffic': traffic,
                          'traffic_of': traffic_note,
                          'peak_source': peak['source'],

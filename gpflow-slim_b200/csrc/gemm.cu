@@ -398,11 +398,17 @@ gemm_nt_tma_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmA,
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   // byte offset of this lane's element inside a box row, for the four k-steps of a k-tile
-  uint32_t koff[TBK / 4];
+  // A side: fragment row lr of every 8-row group reads box row pr = {0,2,4,6,1,3,5,7}[lr], so the
+  // four rows a half-warp touches per 64-bit load sit in four different 32-byte bank groups of
+  // the swizzled box (consecutive rows would pair up on the same banks).  The C rows follow.
+  const int pr = ((lr & 3) << 1) | (lr >> 2);
+  uint32_t koff[TBK / 4], koffa[TBK / 4];
 #pragma unroll
-  for (int kk = 0; kk < TBK / 4; ++kk)
+  for (int kk = 0; kk < TBK / 4; ++kk) {
     koff[kk] = (uint32_t)((((2 * kk + (lc >> 1)) ^ lr) << 4) | ((lc & 1) << 3));
-  const uint32_t a_row = (uint32_t)(wm * 64 + lr) * 128u;
+    koffa[kk] = (uint32_t)((((2 * kk + (lc >> 1)) ^ pr) << 4) | ((lc & 1) << 3));
+  }
+  const uint32_t a_row = (uint32_t)(wm * 64 + pr) * 128u;
   const uint32_t b_row = (uint32_t)TBOX_BYTES + (uint32_t)(wn * 32 + lr) * 128u;
 
   double fa[2][8], fb[2][4];
@@ -411,7 +417,7 @@ gemm_nt_tma_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmA,
   if (nk > 0) {
     mbar_wait(bar_full, 0);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) fa[0][i] = lds_f64(base + a_row + i * 1024 + koff[0]);
+    for (int i = 0; i < 8; ++i) fa[0][i] = lds_f64(base + a_row + i * 1024 + koffa[0]);
 #pragma unroll
     for (int j = 0; j < 4; ++j) fb[0][j] = lds_f64(base + b_row + j * 1024 + koff[0]);
   }
@@ -426,14 +432,14 @@ gemm_nt_tma_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmA,
       // fragments of the next k-step are fetched while this one's DMMAs issue
       if (kk + 1 < TBK / 4) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) fa[nxt][i] = lds_f64(sb + a_row + i * 1024 + koff[kk + 1]);
+        for (int i = 0; i < 8; ++i) fa[nxt][i] = lds_f64(sb + a_row + i * 1024 + koffa[kk + 1]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) fb[nxt][j] = lds_f64(sb + b_row + j * 1024 + koff[kk + 1]);
       } else if (kt + 1 < nk) {
         const uint32_t nb = base + s2 * TSTAGE_BYTES;
         mbar_wait(bar_full + 8 * s2, ph2);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) fa[nxt][i] = lds_f64(nb + a_row + i * 1024 + koff[0]);
+        for (int i = 0; i < 8; ++i) fa[nxt][i] = lds_f64(nb + a_row + i * 1024 + koffa[0]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) fb[nxt][j] = lds_f64(nb + b_row + j * 1024 + koff[0]);
       }
@@ -450,7 +456,7 @@ gemm_nt_tma_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmA,
     ph = ph2;
   }
 
-  gemm_epilogue(g, acc, m0, n0, wm, wn, lr, lc);
+  gemm_epilogue(g, acc, m0, n0, wm, wn, pr, lc);
 }
 
 // plain-FMA check kernel with identical semantics (gps_set_option("gemm_impl", 1)); used by
