@@ -155,6 +155,39 @@ struct PrimEval {
   double d2;    // stationary: unclipped-side squared distance (after clip)
 };
 
+// value and d/d(d2) of a stationary kernel at squared distance d2 (already clipped at 0;
+// `live` is false where the clip was active and the reference's gradient is zero)
+__device__ __forceinline__ void stat_body(int type, double var, double d2, bool live, double& k,
+                                          double& dk) {
+  if (type == GPS_RBF) {
+    double ex = exp(-0.5 * d2);
+    k = var * ex;
+    dk = live ? -0.5 * var * ex : 0.0;
+  } else {
+    double r = sqrt(d2 + 1e-12);                               // kernels.py:424-426
+    double drd2 = live ? 0.5 / r : 0.0;
+    if (type == GPS_EXPONENTIAL) {
+      double ex = exp(-0.5 * r);
+      k = var * ex;
+      dk = -0.5 * var * ex * drd2;
+    } else if (type == GPS_MATERN12) {
+      double ex = exp(-r);
+      k = var * ex;
+      dk = -var * ex * drd2;
+    } else if (type == GPS_MATERN32) {
+      const double s3 = 1.7320508075688772;
+      double ex = exp(-s3 * r);
+      k = var * (1.0 + s3 * r) * ex;
+      dk = var * (-3.0 * r) * ex * drd2;                       // d/dr[(1+s3 r)e^{-s3 r}] = -3 r e^{-s3 r}
+    } else {
+      const double s5 = 2.23606797749979;
+      double ex = exp(-s5 * r);
+      k = var * (1.0 + s5 * r + (5.0 / 3.0) * r * r) * ex;
+      dk = var * (-(5.0 / 3.0) * r * (1.0 + s5 * r)) * ex * drd2;
+    }
+  }
+}
+
 __device__ __forceinline__ PrimEval prim_eval(const PrimC& P, const double* __restrict__ th,
                                               const double* __restrict__ fi,
                                               const double* __restrict__ fj) {
@@ -167,35 +200,8 @@ __device__ __forceinline__ PrimEval prim_eval(const PrimC& P, const double* __re
     double raw = -2.0 * dot + (fi[P.ndims] + fj[P.ndims]);      // kernels.py:413-414 / 419-420
     bool live = raw >= 0.0;                                      // clip_by_value(dist, 0, inf)
     double d2 = live ? raw : 0.0;
-    const double var = t[0];
     e.d2 = d2;
-    if (P.type == GPS_RBF) {
-      double ex = exp(-0.5 * d2);
-      e.k = var * ex;
-      e.dk = live ? -0.5 * var * ex : 0.0;
-    } else {
-      double r = sqrt(d2 + 1e-12);                               // kernels.py:424-426
-      double drd2 = live ? 0.5 / r : 0.0;
-      if (P.type == GPS_EXPONENTIAL) {
-        double ex = exp(-0.5 * r);
-        e.k = var * ex;
-        e.dk = -0.5 * var * ex * drd2;
-      } else if (P.type == GPS_MATERN12) {
-        double ex = exp(-r);
-        e.k = var * ex;
-        e.dk = -var * ex * drd2;
-      } else if (P.type == GPS_MATERN32) {
-        const double s3 = 1.7320508075688772;
-        double ex = exp(-s3 * r);
-        e.k = var * (1.0 + s3 * r) * ex;
-        e.dk = var * (-3.0 * r) * ex * drd2;                     // d/dr[(1+s3 r)e^{-s3 r}] = -3 r e^{-s3 r}
-      } else {
-        const double s5 = 2.23606797749979;
-        double ex = exp(-s5 * r);
-        e.k = var * (1.0 + s5 * r + (5.0 / 3.0) * r * r) * ex;
-        e.dk = var * (-(5.0 / 3.0) * r * (1.0 + s5 * r)) * ex * drd2;
-      }
-    }
+    stat_body(P.type, t[0], d2, live, e.k, e.dk);
   } else if (P.type == GPS_LINEAR) {
     double dot = 0.0;
     for (int k = 0; k < P.ndims; ++k) dot = fma(fi[k] * t[P.ard ? k : 0], fj[k], dot);
@@ -499,6 +505,245 @@ gram_bwd_kernel(const Plan pl, const PlanDims pd, const double* __restrict__ the
   }
 }
 
+// --------------------------------------------------------------------------- fast path
+// One stationary primitive and no composition program (RBF / Matern / Exponential, ARD or not,
+// <= 16 active dimensions) -- the covariance of every GPR / SVGP config in BASELINE.json except
+// the NKN one.  Same arithmetic as the interpreter above (same feature vectors, same summation
+// order over the dimensions) but with compile-time bounds, so the 4 x 4 micro-tile, the dot
+// products and the gradient accumulators live in registers instead of local memory.
+//   CTA: 64 x 64 tile, 256 threads; thread (ty, tx) owns rows {2ty, 2ty+1, 32+2ty, 33+2ty} and
+//   columns {2tx, 2tx+1, 32+2tx, 33+2tx}: feature reads are 16-byte shared loads (k-major smem),
+//   K / W accesses are 16-byte global accesses, 256 contiguous bytes per half-warp.
+constexpr int SLD = TILE + 2;   // smem row stride of a k-major feature tile (16-byte aligned rows)
+
+template <int DP>
+__device__ __forceinline__ void stat_load_tile(const double* __restrict__ F, int FT, int nd, int64_t r0,
+                                               int64_t nrows, double (*sf)[SLD], double* ss, int tid) {
+  for (int idx = tid; idx < TILE * (DP + 1); idx += GRAM_THREADS) {
+    const int r = idx / (DP + 1), c = idx - r * (DP + 1);
+    const bool ok = r0 + r < nrows;
+    if (c < DP) sf[c][r] = (ok && c < nd) ? F[(r0 + r) * FT + c] : 0.0;
+    else ss[r] = ok ? F[(r0 + r) * FT + nd] : 0.0;
+  }
+}
+
+template <int DP>
+__device__ __forceinline__ void stat_dots(const double (*sl)[SLD], const double (*sr)[SLD], int ty, int tx,
+                                          double (&dot)[4][4]) {
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) dot[a][b] = 0.0;
+#pragma unroll
+  for (int k = 0; k < DP; ++k) {
+    const double2 a01 = *reinterpret_cast<const double2*>(&sl[k][2 * ty]);
+    const double2 a23 = *reinterpret_cast<const double2*>(&sl[k][32 + 2 * ty]);
+    const double2 b01 = *reinterpret_cast<const double2*>(&sr[k][2 * tx]);
+    const double2 b23 = *reinterpret_cast<const double2*>(&sr[k][32 + 2 * tx]);
+    const double fa[4] = {a01.x, a01.y, a23.x, a23.y};
+    const double fb[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) dot[a][b] = fma(fa[a], fb[b], dot[a][b]);
+  }
+}
+
+template <int DP>
+__global__ void __launch_bounds__(GRAM_THREADS)
+gram_fwd_stat_kernel(int type, int nd, int FT, const double* __restrict__ theta,
+                     const double* __restrict__ FL, const double* __restrict__ FR, int64_t N, int64_t M,
+                     double diag_add, int sym, int uplo, double* __restrict__ K, int64_t ldk) {
+  __shared__ __align__(16) double sl[DP][SLD];
+  __shared__ __align__(16) double sr[DP][SLD];
+  __shared__ double ssl[TILE], ssr[TILE];
+  const int64_t i0 = (int64_t)blockIdx.y * TILE, j0 = (int64_t)blockIdx.x * TILE;
+  if (sym && uplo && j0 > i0 + TILE - 1) return;
+  const int tid = threadIdx.x;
+  stat_load_tile<DP>(FL, FT, nd, i0, N, sl, ssl, tid);
+  stat_load_tile<DP>(FR, FT, nd, j0, M, sr, ssr, tid);
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  const double var = theta[0];
+  double dot[4][4];
+  stat_dots<DP>(sl, sr, ty, tx, dot);
+  const bool vec = ((ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(K) & 15) == 0);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int il = (a >> 1) * 32 + 2 * ty + (a & 1);
+    const int64_t gi = i0 + il;
+    if (gi >= N) continue;
+#pragma unroll
+    for (int bp = 0; bp < 2; ++bp) {
+      const int jl = bp * 32 + 2 * tx;
+      const int64_t gj = j0 + jl;
+      double kv[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const double raw = -2.0 * dot[a][2 * bp + q] + (ssl[il] + ssr[jl + q]);   // kernels.py:413-414
+        const bool live = raw >= 0.0;                                            // clip_by_value
+        double kk, dk;
+        stat_body(type, var, live ? raw : 0.0, live, kk, dk);
+        if (sym && gi == gj + q) kk += diag_add;
+        kv[q] = kk;
+      }
+      const bool ok0 = gj < M && !(sym && uplo && gj > gi);
+      const bool ok1 = gj + 1 < M && !(sym && uplo && gj + 1 > gi);
+      double* kp = K + gi * ldk + gj;
+      if (vec && ok0 && ok1) {
+        *reinterpret_cast<double2*>(kp) = make_double2(kv[0], kv[1]);
+      } else {
+        if (ok0) kp[0] = kv[0];
+        if (ok1) kp[1] = kv[1];
+      }
+    }
+  }
+}
+
+// Backward of the same: acc layout = [d/d variance, d/d lengthscale(s), trace W]; per-CTA partials
+// in the layout of gram_bwd_kernel, so the fixed-order second pass is shared.
+template <int DP>
+__global__ void __launch_bounds__(GRAM_THREADS)
+gram_bwd_stat_kernel(int type, int ard, int nd, int FT, int n_theta, const double* __restrict__ theta,
+                     const double* __restrict__ FL, const double* __restrict__ FR, int64_t N, int64_t M,
+                     const BwdArgs w, double* __restrict__ part_theta) {
+  __shared__ __align__(16) double sl[DP][SLD];
+  __shared__ __align__(16) double sr[DP][SLD];
+  __shared__ double ssl[TILE], ssr[TILE];
+  __shared__ double bi[MAX_R][TILE], bj[MAX_R][TILE];
+  __shared__ double red[GRAM_THREADS / 32][DP + 2];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t i0 = (int64_t)blockIdx.y * TILE;
+  const int64_t jtiles = (M + TILE - 1) / TILE;
+  const double var = theta[0];
+  const bool vecw = ((w.ldw & 1) == 0) && ((reinterpret_cast<uintptr_t>(w.W) & 15) == 0);
+
+  double acc_v = 0.0, acc_tr = 0.0, acc_l[DP];
+#pragma unroll
+  for (int k = 0; k < DP; ++k) acc_l[k] = 0.0;
+
+  stat_load_tile<DP>(FL, FT, nd, i0, N, sl, ssl, tid);
+  if (w.mode == W_GPR)
+    for (int idx = tid; idx < w.R * TILE; idx += GRAM_THREADS) {
+      const int r = idx / TILE, c = idx - r * TILE;
+      bi[r][c] = (i0 + c < N) ? w.beta[(int64_t)r * N + i0 + c] : 0.0;
+    }
+
+  for (int64_t jt = blockIdx.x; jt < jtiles; jt += w.njc) {
+    const int64_t j0 = jt * TILE;
+    if (w.sym_lower && j0 > i0 + TILE - 1) break;
+    __syncthreads();   // previous tile fully consumed
+    stat_load_tile<DP>(FR, FT, nd, j0, M, sr, ssr, tid);
+    if (w.mode == W_GPR)
+      for (int idx = tid; idx < w.R * TILE; idx += GRAM_THREADS) {
+        const int r = idx / TILE, c = idx - r * TILE;
+        bj[r][c] = (j0 + c < M) ? w.beta[(int64_t)r * N + j0 + c] : 0.0;
+      }
+    __syncthreads();
+    double dot[4][4];
+    stat_dots<DP>(sl, sr, ty, tx, dot);
+    double G[4][4];      // dObj / d(d2) per element (0 where masked)
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int il = (a >> 1) * 32 + 2 * ty + (a & 1);
+      const int64_t gi = i0 + il;
+#pragma unroll
+      for (int bp = 0; bp < 2; ++bp) {
+        const int jl = bp * 32 + 2 * tx;
+        const int64_t gj = j0 + jl;
+        const bool ok0 = gi < N && gj < M && !(w.sym_lower && gj > gi);
+        const bool ok1 = gi < N && gj + 1 < M && !(w.sym_lower && gj + 1 > gi);
+        double wv[2] = {0.0, 0.0};
+        const double* wp = w.W + gi * w.ldw + gj;
+        if (vecw && ok0 && ok1) {
+          const double2 t2 = *reinterpret_cast<const double2*>(wp);
+          wv[0] = t2.x; wv[1] = t2.y;
+        } else {
+          if (ok0) wv[0] = wp[0];
+          if (ok1) wv[1] = wp[1];
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const bool ok = q ? ok1 : ok0;
+          double wij = wv[q];
+          if (w.mode == W_GPR) {
+            double bb = 0.0;
+            for (int r = 0; r < w.R; ++r) bb = fma(bi[r][il], bj[r][jl + q], bb);
+            wij = 0.5 * ((double)w.R * wij - bb);
+            if (ok && gi == gj + q) acc_tr += wij;            // tr W = d nlml / d noise
+          }
+          if (w.sym_lower && gj + q != gi) wij *= 2.0;
+          const double raw = -2.0 * dot[a][2 * bp + q] + (ssl[il] + ssr[jl + q]);
+          const bool live = raw >= 0.0;
+          const double d2 = live ? raw : 0.0;
+          double kk, dk;
+          stat_body(type, var, d2, live, kk, dk);
+          const double g = ok ? wij : 0.0;
+          acc_v = fma(g, kk, acc_v);
+          const double Gq = g * dk;
+          G[a][2 * bp + q] = Gq;
+          if (!ard) acc_l[0] = fma(Gq, d2, acc_l[0]);
+        }
+      }
+    }
+    if (ard) {
+#pragma unroll
+      for (int k = 0; k < DP; ++k) {
+        const double2 a01 = *reinterpret_cast<const double2*>(&sl[k][2 * ty]);
+        const double2 a23 = *reinterpret_cast<const double2*>(&sl[k][32 + 2 * ty]);
+        const double2 b01 = *reinterpret_cast<const double2*>(&sr[k][2 * tx]);
+        const double2 b23 = *reinterpret_cast<const double2*>(&sr[k][32 + 2 * tx]);
+        const double fa[4] = {a01.x, a01.y, a23.x, a23.y};
+        const double fb[4] = {b01.x, b01.y, b23.x, b23.y};
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const double df = fa[a] - fb[b];
+            s = fma(G[a][b] * df, df, s);
+          }
+        acc_l[k] += s;
+      }
+    }
+  }
+  // constant factors: d k / d variance = k / variance; d d2 / d l_k = -2 (f_ik - f_jk)^2 / l_k
+  // (features are x / l); non-ARD: d d2 / d l = -2 d2 / l
+  acc_v /= var;
+#pragma unroll
+  for (int k = 0; k < DP; ++k) {
+    const int nl = ard ? nd : 1;
+    acc_l[k] = (k < nl) ? acc_l[k] * (-2.0) / theta[1 + k] : 0.0;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  {
+    double sv = warp_sum(acc_v), st = warp_sum(acc_tr);
+    if (lane == 0) { red[warp][0] = sv; red[warp][DP + 1] = st; }
+#pragma unroll
+    for (int k = 0; k < DP; ++k) {
+      double sk = warp_sum(acc_l[k]);
+      if (lane == 0) red[warp][1 + k] = sk;
+    }
+  }
+  __syncthreads();
+  const int nacc = n_theta + 1;
+  const int64_t cta = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+  for (int t = tid; t < nacc; t += GRAM_THREADS) {
+    const int src = (t == n_theta) ? DP + 1 : t;          // [variance, l_0.., trace]
+    double sacc = 0.0;
+    for (int wq = 0; wq < GRAM_THREADS / 32; ++wq) sacc += red[wq][src];
+    part_theta[cta * nacc + t] = sacc;
+  }
+}
+
+// single stationary primitive with the identity program and <= 16 active dimensions?
+bool stat_fast(const gps_handle* h, const Plan& pl) {
+  return h->gram_impl == 0 && pl.n_prims == 1 && pl.n_ops == 0 && pl.out_slot == 0 &&
+         is_stationary(pl.prims[0].type) && pl.prims[0].ndims <= 16 && pl.prims[0].theta_off == 0;
+}
+
 // out[t] = sum_c part[c][t] (fixed order)
 __global__ void reduce_cols_kernel(const double* __restrict__ part, int64_t nrows, int64_t ncols,
                                    double scale, double* __restrict__ out, int64_t out_stride_skip,
@@ -639,6 +884,18 @@ int gps_gram_fwd_mat(gps_handle* h, const gps_kernel_desc* desc, const double* t
   size_t smem = (size_t)(pl.n_theta + 2 * TILE * pl.S) * sizeof(double);
   dim3 grid((unsigned)((M + TILE - 1) / TILE), (unsigned)((N + TILE - 1) / TILE));
   if (grid.y > 65535) return gps_fail(h, -4, "gram: too many rows");
+  if (stat_fast(h, pl)) {
+    const PrimC P = pl.prims[0];
+    const int sym = X2 ? 0 : 1, up = X2 ? 0 : uplo;
+    if (P.ndims <= 4)
+      gram_fwd_stat_kernel<4><<<grid, GRAM_THREADS, 0, h->stream>>>(P.type, P.ndims, pl.FT, theta, FL, FR, N, M, diag_add, sym, up, K.p, K.ld);
+    else if (P.ndims <= 8)
+      gram_fwd_stat_kernel<8><<<grid, GRAM_THREADS, 0, h->stream>>>(P.type, P.ndims, pl.FT, theta, FL, FR, N, M, diag_add, sym, up, K.p, K.ld);
+    else
+      gram_fwd_stat_kernel<16><<<grid, GRAM_THREADS, 0, h->stream>>>(P.type, P.ndims, pl.FT, theta, FL, FR, N, M, diag_add, sym, up, K.p, K.ld);
+    GPS_LAUNCH_CHECK(h);
+    return 0;
+  }
   gram_fwd_kernel<<<grid, GRAM_THREADS, smem, h->stream>>>(pl, theta, FL, FR, N, M, diag_add,
                                                            X2 ? 0 : 1, X2 ? 0 : uplo, K.p, K.ld);
   GPS_LAUNCH_CHECK(h);
@@ -689,8 +946,19 @@ int gps_gram_bwd_mat(gps_handle* h, const gps_kernel_desc* desc, const double* t
   size_t smem = (size_t)(pl.n_theta + 2 * TILE * pl.S + (w.mode == W_GPR ? 2 * w.R * TILE : 0) +
                          8 * nacc + (dX ? TILE * X.cols : 0)) * sizeof(double);
   if (smem > 220 * 1024) return gps_fail(h, -2, "gram_bwd: kernel too large for shared memory");
-  gram_bwd_kernel<<<dim3((unsigned)njc, (unsigned)itiles), GRAM_THREADS, smem, h->stream>>>(
-      pl, pd, theta, FL, FR, N, M, a, part, pdx);
+  if (!dX && stat_fast(h, pl)) {
+    const PrimC P = pl.prims[0];
+    const dim3 g2((unsigned)njc, (unsigned)itiles);
+    if (P.ndims <= 4)
+      gram_bwd_stat_kernel<4><<<g2, GRAM_THREADS, 0, h->stream>>>(P.type, P.ard, P.ndims, pl.FT, pl.n_theta, theta, FL, FR, N, M, a, part);
+    else if (P.ndims <= 8)
+      gram_bwd_stat_kernel<8><<<g2, GRAM_THREADS, 0, h->stream>>>(P.type, P.ard, P.ndims, pl.FT, pl.n_theta, theta, FL, FR, N, M, a, part);
+    else
+      gram_bwd_stat_kernel<16><<<g2, GRAM_THREADS, 0, h->stream>>>(P.type, P.ard, P.ndims, pl.FT, pl.n_theta, theta, FL, FR, N, M, a, part);
+  } else {
+    gram_bwd_kernel<<<dim3((unsigned)njc, (unsigned)itiles), GRAM_THREADS, smem, h->stream>>>(
+        pl, pd, theta, FL, FR, N, M, a, part, pdx);
+  }
   GPS_LAUNCH_CHECK(h);
   // theta gradient
   reduce_cols_kernel<<<(nacc + 127) / 128, 128, 0, h->stream>>>(part, nctas, nacc, 1.0, part, 0, 0);

@@ -148,6 +148,10 @@ int gps_set_option(gps_handle* h, const char* name, int64_t value) {
     h->gemm_impl = (int)value;
     return 0;
   }
+  if (!strcmp(name, "gram_impl")) {
+    h->gram_impl = (int)value;
+    return 0;
+  }
   if (!strcmp(name, "leaf_impl")) {
     h->leaf_impl = (int)value;
     return 0;

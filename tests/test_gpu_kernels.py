@@ -257,3 +257,38 @@ def test_wrong_inputs_raise():
         gpf.kernels.RBF(4).K(conv(np.zeros((5, 2))))          # active dims beyond X's columns
     with pytest.raises(RuntimeError):
         ops.gemm_nt(torch.zeros(2, 2, dtype=torch.float64), torch.zeros(2, 2, dtype=torch.float64))
+
+
+@pytest.mark.parametrize('cls', ['RBF', 'Matern12', 'Matern32', 'Matern52', 'Exponential'])
+@pytest.mark.parametrize('d,ard', [(1, False), (3, True), (8, True), (11, True), (16, True), (5, False)])
+def test_gram_fast_path_equals_interpreter(cls, d, ard):
+    """The register-tiled kernels for a single stationary covariance (gram_impl 0) against the
+    generic interpreter kernels (gram_impl 1): Gram K(X), K(X, X2), the dense backward and the
+    fused GPR objective + gradient, on ragged sizes that leave partial 64-tiles."""
+    import gpflowSlim as gpf
+    from gpflowSlim._backend.lib import handle_for
+    rng = np.random.default_rng(100 * d + len(cls))
+    n, m = 203, 131
+    Xn, X2n = rng.standard_normal((n, d)), rng.standard_normal((m, d))
+    Wn, Wsn = rng.standard_normal((n, m)), rng.standard_normal((n, n))
+    Yn = rng.standard_normal((n, 2))
+    ls = 0.8 + 0.1 * np.arange(d) if ard else 1.3
+    h = handle_for(dev())
+    out = {}
+    for impl in (0, 1):
+        h.set_option('gram_impl', impl)
+        try:
+            kern = getattr(gpf.kernels, cls)(d, variance=1.4, lengthscales=ls, ARD=ard)
+            params = [p.unconstrained_tensor for p in kern.parameters]
+            K, K2 = kern.K(conv(Xn)), kern.K(conv(Xn), conv(X2n))
+            val = (K2 * conv(Wn)).sum() + (K * conv(Wsn)).sum()
+            g = torch.autograd.grad(val, params)
+            mdl = gpf.models.GPR(conv(Xn), conv(Yn), kern=kern)
+            obj = mdl.objective
+            go = torch.autograd.grad(obj, [p.unconstrained_tensor for p in mdl.parameters])
+            out[impl] = [K.detach(), K2.detach(), val.detach(), obj.detach()] + [t.detach() for t in g + go]
+        finally:
+            h.set_option('gram_impl', 0)
+    for i, (a, b) in enumerate(zip(out[0], out[1])):
+        # Gram entries: same arithmetic; sums (values, gradients): different summation order
+        assert_close(a, b, 1e-13 if i < 2 else 1e-10, '%s d=%d fast vs interpreter [%d]' % (cls, d, i))
