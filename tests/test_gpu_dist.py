@@ -28,7 +28,8 @@ def _spd(n, seed=0):
     return A @ A.T / (n + 3) + 0.5 * np.eye(n)
 
 
-@pytest.mark.parametrize('m,n,k,coff', [(300, 517, 128, 0), (1000, 900, 256, 130), (129, 64, 512, 5)])
+@pytest.mark.parametrize('m,n,k,coff', [(300, 517, 128, 0), (1000, 900, 256, 130), (129, 64, 512, 5),
+                                        (2600, 2300, 128, 130)])
 def test_gemm_rowmap_masks_by_global_row(m, n, k, coff):
     rng = np.random.default_rng(m + n)
     A, B, C = rng.standard_normal((m, k)), rng.standard_normal((n, k)), rng.standard_normal((m, n))
@@ -42,7 +43,7 @@ def test_gemm_rowmap_masks_by_global_row(m, n, k, coff):
     assert_close(Cd, ref, 1e-13, 'rowmap gemm')
 
 
-@pytest.mark.parametrize('n,bs', [(384, 128), (1000, 256), (1500, 384)])
+@pytest.mark.parametrize('n,bs', [(384, 128), (1000, 256), (1500, 384), (4000, 512)])
 def test_prefix_triangular_solves(n, bs):
     """Rows of U = L^-T and of K^-1 for a subset of block rows, against dense inverses."""
     S = _spd(n, seed=n)

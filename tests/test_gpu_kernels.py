@@ -26,7 +26,7 @@ def _spd(n, seed=0, cond_shift=None):
 @pytest.mark.parametrize('m,n,k', [(1, 1, 1), (5, 3, 2), (128, 128, 128), (129, 127, 65),
                                    (300, 200, 17), (257, 513, 384), (1000, 1, 1000),
                                    (130, 260, 16), (64, 64, 8), (200, 300, 50), (385, 129, 4098),
-                                   (1000, 2, 1000), (127, 1, 2)])
+                                   (1000, 2, 1000), (127, 1, 2), (2500, 2100, 80)])
 @pytest.mark.parametrize('impl', [0, 1, 2])
 def test_gemm_nt_matches_torch(m, n, k, impl):
     ops = _ops()
@@ -54,7 +54,7 @@ def test_gemm_nt_unaligned_views():
 
 
 @pytest.mark.parametrize('impl', [0, 2])
-@pytest.mark.parametrize('n', [260, 700])
+@pytest.mark.parametrize('n', [260, 700, 2200])
 def test_gemm_nt_triangular_modes(n, impl):
     """impl 0: TMA + mbarrier kernel (even n: operands qualify); impl 2: cp.async kernel."""
     ops = _ops()

@@ -18,7 +18,7 @@ for impl in (0, 2):
     h.set_option('gemm_impl', impl)
     worst = 0.0
     for (m, n, k) in [(128, 128, 16), (128, 128, 128), (257, 513, 384), (200, 300, 50), (385, 129, 4098),
-                      (1000, 2, 1000), (2048, 2048, 2048)]:
+                      (1000, 2, 1000), (2048, 2048, 2048), (3000, 2500, 144), (4100, 1700, 16)]:
         A = torch.randn(m, k, dtype=torch.float64, device=dev, generator=g)
         B = torch.randn(n, k, dtype=torch.float64, device=dev, generator=g)
         C = torch.randn(m, n, dtype=torch.float64, device=dev, generator=g)
@@ -52,11 +52,11 @@ def timeit(f, reps=5):
 for impl, name in ((0, 'TMA+mbarrier'), (2, 'cp.async')):
     h.set_option('gemm_impl', impl)
     ms = timeit(lambda: ops.gemm_nt(A, B, out=C, beta=0.0))
-    print('ours %-13s 8192^3: %.2f ms  %.2f TFLOP/s' % (name, ms, 2 * n ** 3 / ms / 1e9), flush=True)
-    for k in (128, 512, 2048):
+    print('ours %-14s 8192^3: %.2f ms  %.2f TFLOP/s' % (name, ms, 2 * n ** 3 / ms / 1e9), flush=True)
+    for k in (128, 256, 512, 1024, 2048):
         Ak, Bk = A[:, :k], B[:, :k]
         ms = timeit(lambda: ops.gemm_nt(Ak, Bk, out=C, beta=1.0, alpha=-1.0))
-        print('ours %-13s 8192x8192x%d (beta=1): %.3f ms  %.2f TFLOP/s' % (name, k, ms, 2 * n * n * k / ms / 1e9), flush=True)
+        print('ours %-14s 8192x8192x%d (beta=1): %.3f ms  %.2f TFLOP/s' % (name, k, ms, 2 * n * n * k / ms / 1e9), flush=True)
 h.set_option('gemm_impl', 0)
 ms = timeit(lambda: torch.matmul(A, B.t(), out=C))
 print('cuBLAS DGEMM       8192^3: %.2f ms  %.2f TFLOP/s' % (ms, 2 * n ** 3 / ms / 1e9))
