@@ -16,4 +16,4 @@ echo "ncu gemm exit $?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 echo "ncu bench exit $?"
 python tools/summarise_launches.py gpurun_out/launches_bench.csv > gpurun_out/launches_bench_summary.txt 2>&1; head -10 gpurun_out/launches_bench_summary.txt
-bash tools/gpu_s3e.sh
+bash tools/gpu_secondary.sh
