@@ -144,7 +144,12 @@ class CudaBackend(object):
     def _h(self):
         return self._L.handle_for(self.device)
 
+    poison = False      # tests set this: uninitialised buffers are filled with NaN, so a kernel that
+                        # reads what was never written or communicated cannot pass unnoticed
+
     def empty(self, *shape):
+        if self.poison:
+            return torch.full(tuple(shape), float('nan'), dtype=F64, device=self.device)
         return torch.empty(*shape, dtype=F64, device=self.device)
 
     # ---- streams / events for the look-ahead (CUDA streams, no tracing compiler)
@@ -199,6 +204,12 @@ class CudaBackend(object):
         va, vo = L.view(A), L.view(out)
         h.check(h.lib.gps_transpose(h.ptr, va.ref, vo.ref))
         return out
+
+    def transpose_into(self, A, out):
+        """out <- A^T (out is a view with its own leading dimension)."""
+        h, L = self._h(), self._L
+        va, vo = L.view(A), L.view(out)
+        h.check(h.lib.gps_transpose(h.ptr, va.ref, vo.ref))
 
     @staticmethod
     def _starts(row_start, rows):
@@ -304,7 +315,7 @@ def _layout_maps(lay, P, dev):
 
 def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
     """Distributed Gram + Cholesky.  Returns (Lfull [N, ld] with the lower block triangle of
-    L -- identical on every rank --, alpha_t [R, N] = (L^-1 Yc)^T).
+    L -- identical on every rank --, Lt [N, ld] = its transpose, alpha_t [R, N] = (L^-1 Yc)^T).
 
     With `lookahead` the work of panel k is spread over three CUDA streams:
       chain  (high priority): factor diagonal block k -> broadcast -> solve my panel rows ->
@@ -335,7 +346,10 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
     Aloc[nloc:, :N] = Yc.t()
     _mark('gram')
 
-    Lfull = be.zeros(N, ld)
+    # L (lower block triangle) and L^T (upper), filled column block by column block; what lies
+    # outside those triangles is never written and never read
+    Lfull = be.empty(N, ld)
+    Lt = be.empty(N, ld)
     own_of_row, lrow_of_row, below_all, lo_table = _layout_maps(lay, P, dev)
 
     Lkk_buf = be.empty(bs * bs)
@@ -382,10 +396,12 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
         return Pn, mrows
 
     def gather_panel(k, Pn, mrows):
-        """all-gather of the solved panel k -> Lfull[r1:, r0:r1] on every rank."""
+        """all-gather of the solved panel k -> Lfull[r1:, r0:r1] on every rank; block column k
+        of L (diagonal block included) is then also stored transposed, as block row k of Lt."""
         r0, r1 = lay.rows(k)
         nb = r1 - r0
         if k == lay.nblk - 1:
+            be.transpose_into(Lfull[r0:r1, r0:r1], Lt[r0:r1, r0:r1])
             return
         if P > 1:
             mmax = max(m for _, m in below_all[k])
@@ -401,6 +417,7 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
             Lfull[r1:, r0:r1] = recv.view(P * mmax, nb).index_select(0, src)
         else:
             Lfull[r1:, r0:r1] = Pn[:mrows]
+        be.transpose_into(Lfull[r0:, r0:r1], Lt[r0:r1, r0:N])
         _mark('gather+unpack', fine=True)
 
     def top_block(k):
@@ -446,11 +463,11 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
                         be.wait(chain, ev_narrow[k - 1])      # column k+1 has seen panels <= k-1
                     update(k, *lay.rows(k + 1), Bsrc=T)
                 ev_c = be.record(chain)
+            with be.on(gath):
+                be.wait(gath, ev_trsm)
+                gather_panel(k, Pn, mrows)
+                ev_g = be.record(gath)
             if k + 1 < nblk:
-                with be.on(gath):
-                    be.wait(gath, ev_trsm)
-                    gather_panel(k, Pn, mrows)
-                    ev_g = be.record(gath)
                 with be.on(main):
                     be.wait(main, ev_g)
                     if k + 2 < nblk:
@@ -463,7 +480,7 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
         _FINE = True
         _mark('factor(lookahead)')
     alpha_t = Aloc[nloc:, :N]
-    return Lfull, alpha_t
+    return Lfull, Lt, alpha_t
 
 
 def nlml_and_grad(prog, theta, noise, X, Yc, block=512, group=None, backend=None, want_grad=True,
@@ -480,7 +497,7 @@ def nlml_and_grad(prog, theta, noise, X, Yc, block=512, group=None, backend=None
         raise ValueError('1..16 output columns supported')
     noise = float(noise)
     lay = BlockRowLayout(N, block, comm.world)
-    Lfull, alpha_t = factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=lookahead)
+    Lfull, Ltf, alpha_t = factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=lookahead)
     Lsq = Lfull[:, :N]
     logdet = be.sum_log_diag(Lsq)
     nlml = 0.5 * N * R * math.log(2.0 * math.pi) + R * logdet + 0.5 * (alpha_t ** 2).sum()
@@ -511,7 +528,7 @@ def nlml_and_grad(prog, theta, noise, X, Yc, block=512, group=None, backend=None
     start_u = np.concatenate([np.full(nr, r0, dtype=np.int64) for (r0, _, nr) in starts]
                              or [np.zeros(0, dtype=np.int64)])
     start_all = np.concatenate([np.zeros(R, dtype=np.int64), start_u])
-    Lt = be.transpose(Lsq)
+    Lt = Ltf[:, :N]
     _mark('nlml+inv_setup')
     if m > R:
         be.trsm_rlt_prefix_(Lsq, B[R:], start_u)          # rows of U = L^-T

@@ -103,11 +103,14 @@ def test_distributed_path_world1_equals_fused_and_oracle(n, r, block):
     params = [p.unconstrained_tensor for p in m.parameters]
     obj = m.objective
     g = torch.autograd.grad(obj, params)
+    from gpflowSlim._backend.dist_gpr import CudaBackend
     gpf.parallel.init(block=block)
+    CudaBackend.poison = True       # NaN-fill every uninitialised buffer of the distributed path
     try:
         obj2 = m.objective
         g2 = torch.autograd.grad(obj2, params)
     finally:
+        CudaBackend.poison = False
         gpf.parallel.shutdown()
     raw = [torch.tensor(R.softplus_inv(v), dtype=torch.float64, requires_grad=True)
            for v in (1.0, 2.0 * np.ones(d), 0.1)]

@@ -39,9 +39,12 @@ def main():
     params = [p.unconstrained_tensor for p in m.parameters]
     obj = m.objective
     g = torch.autograd.grad(obj, params)
+    from gpflowSlim._backend.dist_gpr import CudaBackend
     gpf.parallel.init(block=args.block)
+    CudaBackend.poison = True       # NaN-fill uninitialised buffers: nothing unwritten may be read
     obj2 = m.objective
     g2 = torch.autograd.grad(obj2, params)
+    CudaBackend.poison = False
     gpf.parallel.shutdown()
     errs = [rel(obj2, obj)] + [rel(a, b) for a, b in zip(g2, g)]
     # every rank must hold the same answer
