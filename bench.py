@@ -320,8 +320,9 @@ def main():
                          'traffic_of': traffic_note,
                          'peak_source': peak['source'],
                          'gemm_share_of_step': gemm_ms / (prof_ms * prof_steps) if prof_ms > 0 else None,
-                         'scope': ('rank 0, separate profiled pass of %d step(s) after the timed region (three overlapping '
-                                   'streams: per-launch event time includes queueing behind the other streams)' % prof_steps)
+                         'scope': ('rank 0, separate profiled pass of %d step(s) after the timed region%s' % (
+                             prof_steps, ' (three overlapping streams: per-launch event time includes queueing '
+                             'behind the other streams)' if world > 1 else ''))
                          if not profile_in_region else 'the GPU, events inside the timed region',
                          'step_tflops_vs_n3': nprob * float(n) ** 3 / (ms * 1e-3) / 1e12},
         }
