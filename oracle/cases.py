@@ -225,6 +225,36 @@ def case_sgpr(gpf, conv):
     return out, [('objective', m)]
 
 
+def _make_fitc(gpf, *args, **kwargs):
+    """The reference's GPRFITC.__init__ reads self.name before GPModel.__init__ has set it
+    (models/sgpr.py:221) and so cannot be constructed as shipped; giving the instance its name
+    first lets the UNMODIFIED constructor run.  Harmless for an implementation without the bug."""
+    cls = gpf.models.GPRFITC
+    m = cls.__new__(cls)
+    m._name = kwargs.get('name', 'GPModel')
+    cls.__init__(m, *args, **kwargs)
+    return m
+
+
+def case_sparse_bounds(gpf, conv):
+    """the upper bound of SGPRUpperMixin (models/sgpr.py:55-82) on
+    SGPR and GPRFITC, and the FITC likelihood / predictions (models/sgpr.py:192-317)."""
+    n, d, mi = 500, 3, 40
+    X, Y, Z = synth_svgp(n, d, mi, seed=12)
+    rng = np.random.default_rng(13)
+    Y = np.concatenate([Y, rng.standard_normal((n, 1)) * 0.3], 1)
+    Xs = rng.standard_normal((17, d))
+    ks = gpf.kernels.Matern32(d, ARD=True, lengthscales=1.5, variance=1.2, name='ub_k')
+    sg = gpf.models.SGPR(conv(X), conv(Y), ks, Z=Z.copy(), obs_var=0.2, name='ub_sg')
+    kf = gpf.kernels.RBF(d, ARD=True, lengthscales=1.5, name='fitc_k')
+    fitc = _make_fitc(gpf, conv(X), conv(Y), kf, Z=Z.copy(), obs_var=0.2, name='fitc')
+    out = {'sgpr_upper': sg.compute_upper_bound(), 'sgpr_lower': sg.likelihood_tensor,
+           'fitc_upper': fitc.compute_upper_bound(), 'fitc_objective': fitc.objective}
+    out['fitc_mu'], out['fitc_var'] = fitc.predict_f(conv(Xs))
+    out['fitc_full_mu'], out['fitc_full_cov'] = fitc.predict_f_full_cov(conv(Xs))
+    return out, [('fitc_objective', fitc)]
+
+
 # --------------------------------------------------------------------------- free functions
 def case_functions(gpf, conv):
     """base_conditional (conditionals.py:81-121), conditional (:25-66), gauss_kl
@@ -271,6 +301,7 @@ CASES = {
     'svgp_white_diag': case_svgp_white_diag,
     'svgp_nonwhite_diag': case_svgp_nonwhite_diag,
     'sgpr': case_sgpr,
+    'sparse_bounds': case_sparse_bounds,
     'functions': case_functions,
 }
 

@@ -339,6 +339,72 @@ def sgpr_predict(spec, X, Y, Z, noise, Xnew, full_cov=False, jitter=1e-6):
     return mean, var
 
 
+def sgpr_upper_bound(spec, X, Y, Z, noise, jitter=1e-6):
+    """SGPRUpperMixin.compute_upper_bound, models/sgpr.py:55-82 (Titsias' trace bound)."""
+    M = Z.shape[0]
+    num_data = float(Y.shape[0])
+    kdiag = Kdiag(spec, X)
+    Kuu = K(spec, Z) + torch.eye(M, dtype=F64) * jitter
+    Kuf = K(spec, Z, X)
+    L = torch.linalg.cholesky(Kuu)
+    LB = torch.linalg.cholesky(Kuu + noise ** -1.0 * (Kuf @ Kuf.T))
+    LinvKuf = tri_solve(L, Kuf)
+    c = kdiag.sum() - (LinvKuf ** 2.0).sum()
+    corrected_noise = noise + c
+    const = -0.5 * num_data * torch.log(2 * math.pi * noise)
+    logdet = torch.log(torch.diagonal(L)).sum() - torch.log(torch.diagonal(LB)).sum()
+    LC = torch.linalg.cholesky(Kuu + corrected_noise ** -1.0 * (Kuf @ Kuf.T))
+    v = tri_solve(LC, corrected_noise ** -1.0 * (Kuf @ Y))
+    quad = -0.5 * corrected_noise ** -1.0 * (Y ** 2.0).sum() + 0.5 * (v ** 2.0).sum()
+    return const + logdet + quad
+
+
+def _fitc_common(spec, X, Y, Z, noise, jitter=1e-6):
+    """GPRFITC._build_common_terms, models/sgpr.py:227-247."""
+    M = Z.shape[0]
+    err = Y
+    kdiag = Kdiag(spec, X)
+    Kuf = K(spec, Z, X)
+    Kuu = K(spec, Z) + torch.eye(M, dtype=F64) * jitter
+    Luu = torch.linalg.cholesky(Kuu)
+    V = tri_solve(Luu, Kuf)
+    diagQff = (V ** 2).sum(0)
+    nu = kdiag - diagQff + noise
+    B = torch.eye(M, dtype=F64) + (V / nu) @ V.T
+    L = torch.linalg.cholesky(B)
+    beta = err / nu.unsqueeze(1)
+    alpha = V @ beta
+    gamma = tri_solve(L, alpha)
+    return err, nu, Luu, L, alpha, beta, gamma
+
+
+def gprfitc_objective(spec, X, Y, Z, noise, jitter=1e-6):
+    """GPRFITC._build_likelihood, models/sgpr.py:249-291 (negated: Model.objective)."""
+    err, nu, Luu, L, alpha, beta, gamma = _fitc_common(spec, X, Y, Z, noise, jitter)
+    num_data, num_latent = float(X.shape[0]), float(Y.shape[1])
+    mahalanobis = -0.5 * (err ** 2 / nu.unsqueeze(1)).sum() + 0.5 * (gamma ** 2).sum()
+    constant = -0.5 * num_data * LOG2PI
+    logdet = -0.5 * torch.log(nu).sum() - torch.log(torch.diagonal(L)).sum()
+    return -(mahalanobis + (constant + logdet) * num_latent)
+
+
+def gprfitc_predict(spec, X, Y, Z, noise, Xnew, full_cov=False, jitter=1e-6):
+    """GPRFITC._build_predict, models/sgpr.py:293-317."""
+    _, _, Luu, L, _, _, gamma = _fitc_common(spec, X, Y, Z, noise, jitter)
+    Kus = K(spec, Z, Xnew)
+    w = tri_solve(Luu, Kus)
+    tmp = tri_solve(L.T, gamma, lower=False)
+    mean = w.T @ tmp
+    inter = tri_solve(L, w)
+    if full_cov:
+        var = K(spec, Xnew) - w.T @ w + inter.T @ inter
+        var = var.unsqueeze(2).repeat(1, 1, Y.shape[1])
+    else:
+        var = Kdiag(spec, Xnew) - (w ** 2).sum(0) + (inter ** 2).sum(0)
+        var = var.unsqueeze(1).repeat(1, Y.shape[1])
+    return mean, var
+
+
 def tf_adam_step(params, grads, state, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
     """One step of tf.train.AdamOptimizer (TF 1.x semantics; examples/gpr.py:53-54): epsilon
     sits OUTSIDE the bias-corrected sqrt:  lr_t = lr*sqrt(1-b2^t)/(1-b1^t);

@@ -209,6 +209,44 @@ def test_sgpr(golden):
     close(cov, g['full_cov'], 1e-8, 'full_cov')
 
 
+def test_sparse_bounds(golden):
+    """SGPRUpperMixin.compute_upper_bound on SGPR and GPRFITC, and the FITC
+    likelihood, gradients and predictions (models/sgpr.py:30-82, 192-317)."""
+    g = golden('sparse_bounds')
+    n, d, mi = 500, 3, 40
+    X, Y, Z0 = cases.synth_svgp(n, d, mi, seed=12)
+    rng = np.random.default_rng(13)
+    Y = np.concatenate([Y, rng.standard_normal((n, 1)) * 0.3], 1)
+    Xs = torch.tensor(rng.standard_normal((17, d)))
+    X, Y = torch.tensor(X), torch.tensor(Y)
+    # SGPR (Matern32 ARD l=1.5 var=1.2, obs_var 0.2) at its initial state
+    ls = torch.full((d,), 1.5, dtype=torch.float64)
+    spec_s = dict(type='matern32', variance=torch.tensor(1.2, dtype=torch.float64), lengthscales=ls)
+    noise0 = torch.tensor(0.2, dtype=torch.float64)
+    Zt = torch.tensor(Z0)
+    up = R.sgpr_upper_bound(spec_s, X, Y, Zt, noise0)
+    lo = -R.sgpr_objective(spec_s, X, Y, Zt, noise0)
+    close(up, g['sgpr_upper'], RTOL, 'sgpr upper')
+    close(lo, g['sgpr_lower'], RTOL, 'sgpr lower')
+    assert float(lo) <= float(up)                      # lower bound <= log p(Y) <= upper bound
+    # FITC from the stored unconstrained parameters
+    raw = [leaf(g['param/fitc_objective/%d' % i]) for i in range(4)]
+    spec = dict(type='rbf', variance=R.softplus_fwd(raw[0]), lengthscales=R.softplus_fwd(raw[1]))
+    noise = R.softplus_fwd(raw[2])
+    Z = raw[3]
+    obj = R.gprfitc_objective(spec, X, Y, Z, noise)
+    close(obj, g['fitc_objective'], RTOL, 'fitc objective')
+    for i, gr in enumerate(grads_wrt(obj, raw)):
+        close(gr, g['grad/fitc_objective/%d' % i], 1e-8, 'fitc grad %d' % i)
+    close(R.sgpr_upper_bound(spec, X, Y, Z, noise), g['fitc_upper'], RTOL, 'fitc upper')
+    mu, var = R.gprfitc_predict(spec, X, Y, Z, noise, Xs)
+    close(mu, g['fitc_mu'], 1e-9, 'fitc mu')
+    close(var, g['fitc_var'], 1e-8, 'fitc var')
+    mu, cov = R.gprfitc_predict(spec, X, Y, Z, noise, Xs, full_cov=True)
+    close(mu, g['fitc_full_mu'], 1e-9, 'fitc full mu')
+    close(cov, g['fitc_full_cov'], 1e-8, 'fitc full cov')
+
+
 def test_functions(golden):
     g = golden('functions')
     rng = np.random.default_rng(11)
