@@ -11,6 +11,7 @@ from ._settings import SETTINGS as settings
 from . import misc
 from . import transforms
 from . import densities
+from . import quadrature
 from . import likelihoods
 from . import kernels
 from . import conditionals

@@ -26,3 +26,42 @@ def multivariate_normal(x, mu, L):
     ret = ret - num_col * torch.log(torch.diagonal(L)).sum()
     ret = ret - 0.5 * (alpha_t ** 2).sum()
     return ret
+
+
+# ---- densities behind the non-Gaussian likelihoods (reference densities.py:28-70); elementwise
+def lognormal(x, mu, var):
+    lnx = torch.log(x)
+    return gaussian(lnx, mu, var) - lnx
+
+
+def bernoulli(p, y):
+    return torch.log(torch.where(y == 1, p, 1 - p))
+
+
+def poisson(lamb, y):
+    return y * torch.log(lamb) - lamb - torch.lgamma(y + 1.0)
+
+
+def exponential(lamb, y):
+    return -y / lamb - torch.log(lamb)
+
+
+def gamma(shape, scale, x):
+    return -shape * torch.log(scale) - torch.lgamma(shape) + (shape - 1.0) * torch.log(x) - x / scale
+
+
+def student_t(x, mean, scale, deg_free):
+    df = torch.as_tensor(deg_free, dtype=x.dtype, device=x.device)
+    const = torch.lgamma((df + 1.0) * 0.5) - torch.lgamma(df * 0.5) \
+        - 0.5 * (torch.log(scale ** 2) + torch.log(df) + np.log(np.pi))
+    return const - 0.5 * (df + 1.0) * torch.log(1.0 + (1.0 / df) * ((x - mean) / scale) ** 2)
+
+
+def beta(alpha, beta, y):
+    y = torch.clamp(y, 1e-6, 1 - 1e-6)
+    return (alpha - 1.0) * torch.log(y) + (beta - 1.0) * torch.log(1.0 - y) \
+        + torch.lgamma(alpha + beta) - torch.lgamma(alpha) - torch.lgamma(beta)
+
+
+def laplace(mu, sigma, y):
+    return -torch.abs(mu - y) / sigma - torch.log(2.0 * sigma)

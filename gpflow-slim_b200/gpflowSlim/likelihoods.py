@@ -1,21 +1,69 @@
-"""Likelihoods on the hot path: Gaussian (reference likelihoods.py:30-46, :158-188).
-Elementwise [B, 1]-sized host-side maths; the closed-form variational expectation feeds the
-SVGP bound."""
+"""Likelihoods (reference likelihoods.py).  Gaussian (:158-188) is the one on the hot path: its
+closed-form variational expectation feeds the SVGP bound.  The others -- the Gauss-Hermite
+defaults of the base class (:47-151), Bernoulli / probit (:262-293), Poisson, Exponential,
+StudentT, Gamma, Beta (:190-376) and MultiClass with the RobustMax link (:379-489, the
+likelihood of examples/svgp.py) -- are O(B * 20) elementwise torch maths around the same SVGP
+kernels (`SURVEY.md` section 8(f) rank 3)."""
 import numpy as np
 import torch
 
 from . import densities, transforms
 from .params import Parameter
+from .quadrature import hermgauss
+
+
+def _const(a, like):
+    return torch.as_tensor(a, dtype=like.dtype, device=like.device)
 
 
 class Likelihood(object):
     def __init__(self, name=None):
         self.name = name or type(self).__name__
+        self.num_gauss_hermite_points = 20
         self._parameters = []
 
     @property
     def parameters(self):
         return self._parameters
+
+    def conditional_mean(self, F):
+        raise NotImplementedError
+
+    def conditional_variance(self, F):
+        raise NotImplementedError
+
+    def logp(self, F, Y):
+        raise NotImplementedError
+
+    def _gh_grid(self, Fmu, Fvar):
+        """X[n, h] = Fmu_n + x_h sqrt(2 Fvar_n) and the weights w_h / sqrt(pi) as a column."""
+        gh_x, gh_w = hermgauss(self.num_gauss_hermite_points)
+        Fmu, Fvar = Fmu.reshape(-1, 1), Fvar.reshape(-1, 1)
+        X = _const(gh_x, Fmu)[None, :] * torch.sqrt(2.0 * Fvar) + Fmu
+        return X, _const(gh_w / np.sqrt(np.pi), Fmu).reshape(-1, 1)
+
+    def predict_mean_and_var(self, Fmu, Fvar):
+        """E[y], Var[y] under q(f) = N(Fmu, Fvar) by Gauss-Hermite quadrature (:47-87)."""
+        shape = Fmu.shape
+        X, w = self._gh_grid(Fmu, Fvar)
+        E_y = (self.conditional_mean(X) @ w).reshape(shape)
+        integrand = self.conditional_variance(X) + self.conditional_mean(X) ** 2
+        V_y = (integrand @ w).reshape(shape) - E_y ** 2
+        return E_y, V_y
+
+    def predict_density(self, Fmu, Fvar, Y):
+        """log int p(y = Y | f) q(f) df (:89-118)."""
+        shape = Fmu.shape
+        X, w = self._gh_grid(Fmu, Fvar)
+        Yt = Y.reshape(-1, 1).expand(-1, self.num_gauss_hermite_points)
+        return torch.log(torch.exp(self.logp(X, Yt)) @ w).reshape(shape)
+
+    def variational_expectations(self, Fmu, Fvar, Y):
+        """int log p(y | f) q(f) df (:120-151)."""
+        shape = Fmu.shape
+        X, w = self._gh_grid(Fmu, Fvar)
+        Yt = Y.reshape(-1, 1).expand(-1, self.num_gauss_hermite_points)
+        return (self.logp(X, Yt) @ w).reshape(shape)
 
 
 class Gaussian(Likelihood):
@@ -48,3 +96,242 @@ class Gaussian(Likelihood):
         """likelihoods.py:186-188."""
         return -0.5 * np.log(2 * np.pi) - 0.5 * torch.log(self.variance) \
             - 0.5 * ((Y - Fmu) ** 2 + Fvar) / self.variance
+
+
+def _is_exp(fn):
+    return fn is torch.exp
+
+
+class Poisson(Likelihood):
+    """p(y | f) = Poisson(y | invlink(f) binsize)  (:190-222)."""
+
+    def __init__(self, invlink=torch.exp, binsize=1.0):
+        super().__init__()
+        self.invlink = invlink
+        self.binsize = float(binsize)
+
+    def logp(self, F, Y):
+        return densities.poisson(self.invlink(F) * self.binsize, Y)
+
+    def conditional_variance(self, F):
+        return self.invlink(F) * self.binsize
+
+    def conditional_mean(self, F):
+        return self.invlink(F) * self.binsize
+
+    def variational_expectations(self, Fmu, Fvar, Y):
+        if _is_exp(self.invlink):
+            return Y * Fmu - torch.exp(Fmu + Fvar / 2) * self.binsize - torch.lgamma(Y + 1) \
+                + Y * float(np.log(self.binsize))
+        return super().variational_expectations(Fmu, Fvar, Y)
+
+
+class Exponential(Likelihood):
+    """(:224-241)."""
+
+    def __init__(self, invlink=torch.exp):
+        super().__init__()
+        self.invlink = invlink
+
+    def logp(self, F, Y):
+        return densities.exponential(self.invlink(F), Y)
+
+    def conditional_mean(self, F):
+        return self.invlink(F)
+
+    def conditional_variance(self, F):
+        return self.invlink(F) ** 2
+
+    def variational_expectations(self, Fmu, Fvar, Y):
+        if _is_exp(self.invlink):
+            return -torch.exp(-Fmu + Fvar / 2) * Y - Fmu
+        return super().variational_expectations(Fmu, Fvar, Y)
+
+
+class StudentT(Likelihood):
+    """(:244-265)."""
+
+    def __init__(self, deg_free=3.0):
+        super().__init__()
+        self.deg_free = deg_free
+        self._scale = Parameter(1.0, transform=transforms.positive, name='scale')
+        self._parameters = self._parameters + [self._scale]
+
+    @property
+    def scale(self):
+        return self._scale.value
+
+    def logp(self, F, Y):
+        return densities.student_t(Y, F, self.scale, self.deg_free)
+
+    def conditional_mean(self, F):
+        return F
+
+    def conditional_variance(self, F):
+        return F * 0.0 + (self.deg_free / (self.deg_free - 2.0))
+
+
+def probit(x):
+    """(:268-269)."""
+    return 0.5 * (1.0 + torch.erf(x / np.sqrt(2.0))) * (1 - 2e-3) + 1e-3
+
+
+class Bernoulli(Likelihood):
+    """(:272-297)."""
+
+    def __init__(self, invlink=probit):
+        super().__init__()
+        self.invlink = invlink
+
+    def logp(self, F, Y):
+        return densities.bernoulli(self.invlink(F), Y)
+
+    def predict_mean_and_var(self, Fmu, Fvar):
+        if self.invlink is probit:
+            p = probit(Fmu / torch.sqrt(1 + Fvar))
+            return p, p - p ** 2
+        return Likelihood.predict_mean_and_var(self, Fmu, Fvar)
+
+    def predict_density(self, Fmu, Fvar, Y):
+        p = self.predict_mean_and_var(Fmu, Fvar)[0]
+        return densities.bernoulli(p, Y)
+
+    def conditional_mean(self, F):
+        return self.invlink(F)
+
+    def conditional_variance(self, F):
+        p = self.invlink(F)
+        return p - p ** 2
+
+
+class Gamma(Likelihood):
+    """The transformed GP gives the scale of the Gamma (:300-332)."""
+
+    def __init__(self, invlink=torch.exp):
+        super().__init__()
+        self.invlink = invlink
+        self._shape = Parameter(1.0, transform=transforms.positive, name='shape')
+        self._parameters = self._parameters + [self._shape]
+
+    @property
+    def shape(self):
+        return self._shape.value
+
+    def logp(self, F, Y):
+        return densities.gamma(self.shape, self.invlink(F), Y)
+
+    def conditional_mean(self, F):
+        return self.shape * self.invlink(F)
+
+    def conditional_variance(self, F):
+        return self.shape * self.invlink(F) ** 2
+
+    def variational_expectations(self, Fmu, Fvar, Y):
+        if _is_exp(self.invlink):
+            return -self.shape * Fmu - torch.lgamma(self.shape) + (self.shape - 1.0) * torch.log(Y) \
+                - Y * torch.exp(-Fmu + Fvar / 2.0)
+        return Likelihood.variational_expectations(self, Fmu, Fvar, Y)
+
+
+class Beta(Likelihood):
+    """Mean m = invlink(f), alpha = scale m, beta = scale (1 - m)  (:335-376)."""
+
+    def __init__(self, invlink=probit, scale=1.0):
+        super().__init__()
+        self._scale = Parameter(scale, transform=transforms.positive, name='scale')
+        self.invlink = invlink
+        self._parameters = self._parameters + [self._scale]
+
+    @property
+    def scale(self):
+        return self._scale.value
+
+    def logp(self, F, Y):
+        mean = self.invlink(F)
+        alpha = mean * self.scale
+        beta = self.scale - alpha
+        return densities.beta(alpha, beta, Y)
+
+    def conditional_mean(self, F):
+        return self.invlink(F)
+
+    def conditional_variance(self, F):
+        mean = self.invlink(F)
+        return (mean - mean ** 2) / (self.scale + 1.0)
+
+
+class RobustMax(object):
+    """Multi-class inverse link: y_i = 1 - eps if i = argmax f, else eps / (k - 1)  (:379-424)."""
+
+    def __init__(self, num_classes, epsilon=1e-3):
+        self.epsilon = epsilon
+        self.num_classes = num_classes
+        self._eps_K1 = self.epsilon / (self.num_classes - 1.0)
+
+    def __call__(self, F):
+        i = torch.argmax(F, 1)
+        hot = torch.nn.functional.one_hot(i, self.num_classes).to(F.dtype)
+        return hot * (1.0 - self.epsilon) + (1.0 - hot) * self._eps_K1
+
+    def prob_is_largest(self, Y, mu, var, gh_x, gh_w):
+        """P(f_Y is the largest latent) under independent N(mu_k, var_k): Gauss-Hermite over
+        f_Y of the product of the other latents' CDFs (:397-424)."""
+        Yi = Y.reshape(-1).to(torch.int64)
+        oh_on = torch.nn.functional.one_hot(Yi, self.num_classes).to(mu.dtype)
+        mu_selected = (oh_on * mu).sum(1)
+        var_selected = (oh_on * var).sum(1)
+        gx = _const(gh_x, mu)
+        X = mu_selected.reshape(-1, 1) + gx * torch.sqrt(torch.clamp(2.0 * var_selected, 1e-10, np.inf)).reshape(-1, 1)
+        dist = (X.unsqueeze(1) - mu.unsqueeze(2)) / torch.sqrt(torch.clamp(var, 1e-10, np.inf)).unsqueeze(2)
+        cdfs = 0.5 * (1.0 + torch.erf(dist / np.sqrt(2.0)))
+        cdfs = cdfs * (1 - 2e-4) + 1e-4
+        oh_off = 1.0 - oh_on
+        cdfs = cdfs * oh_off.unsqueeze(2) + oh_on.unsqueeze(2)
+        return cdfs.prod(1) @ _const(gh_w / np.sqrt(np.pi), mu).reshape(-1, 1)
+
+
+class MultiClass(Likelihood):
+    """Multi-way classification with the RobustMax link (:427-489)."""
+
+    def __init__(self, num_classes, invlink=None):
+        super().__init__()
+        self.num_classes = num_classes
+        if invlink is None:
+            invlink = RobustMax(self.num_classes)
+        elif not isinstance(invlink, RobustMax):
+            raise NotImplementedError
+        self.invlink = invlink
+
+    def logp(self, F, Y):
+        hits = torch.argmax(F, 1).unsqueeze(1) == Y.to(torch.int64)
+        yes = torch.ones(Y.shape, dtype=F.dtype, device=F.device) - self.invlink.epsilon
+        no = torch.zeros(Y.shape, dtype=F.dtype, device=F.device) + self.invlink._eps_K1
+        return torch.log(torch.where(hits, yes, no))
+
+    def variational_expectations(self, Fmu, Fvar, Y):
+        gh_x, gh_w = hermgauss(self.num_gauss_hermite_points)
+        p = self.invlink.prob_is_largest(Y, Fmu, Fvar, gh_x, gh_w)
+        return p * float(np.log(1 - self.invlink.epsilon)) + (1.0 - p) * float(np.log(self.invlink._eps_K1))
+
+    def predict_mean_and_var(self, Fmu, Fvar):
+        n = Fmu.shape[0]
+        ps = [self._predict_non_logged_density(
+            Fmu, Fvar, torch.full((n, 1), i, dtype=torch.int64, device=Fmu.device)).reshape(-1)
+            for i in range(self.num_classes)]
+        ps = torch.stack(ps).t()
+        return ps, ps - ps ** 2
+
+    def predict_density(self, Fmu, Fvar, Y):
+        return torch.log(self._predict_non_logged_density(Fmu, Fvar, Y))
+
+    def _predict_non_logged_density(self, Fmu, Fvar, Y):
+        gh_x, gh_w = hermgauss(self.num_gauss_hermite_points)
+        p = self.invlink.prob_is_largest(Y, Fmu, Fvar, gh_x, gh_w)
+        return p * (1 - self.invlink.epsilon) + (1.0 - p) * self.invlink._eps_K1
+
+    def conditional_mean(self, F):
+        return self.invlink(F)
+
+    def conditional_variance(self, F):
+        p = self.conditional_mean(F)
+        return p - p ** 2

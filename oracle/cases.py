@@ -255,6 +255,78 @@ def case_sparse_bounds(gpf, conv):
     return out, [('fitc_objective', fitc)]
 
 
+# --------------------------------------------------------------------------- likelihoods
+def _lik_zoo(gpf):
+    L = gpf.likelihoods
+    return [('bernoulli', L.Bernoulli(), 'binary'), ('poisson', L.Poisson(), 'count'),
+            ('poisson_bin', L.Poisson(binsize=0.5), 'count'), ('exponential', L.Exponential(), 'positive'),
+            ('studentt', L.StudentT(deg_free=4.0), 'real'), ('gamma', L.Gamma(), 'positive'),
+            ('beta', L.Beta(scale=2.0), 'unit'), ('gaussian', L.Gaussian(var=0.3), 'real')]
+
+
+def case_likelihoods(gpf, conv):
+    """every likelihood's logp / conditional moments / variational
+    expectations / predictive mean, variance and density on fixed (Fmu, Fvar, Y)
+    (likelihoods.py:47-151 Gauss-Hermite defaults and the closed forms of the subclasses), and
+    MultiClass with the RobustMax link (:379-489).  Pure elementwise functions: no model."""
+    rng = np.random.default_rng(31)
+    n = 23
+    Fmu, Fvar = rng.standard_normal((n, 1)) * 0.8, 0.05 + rng.random((n, 1))
+    F = rng.standard_normal((n, 1))
+    Ys = {'binary': (rng.random((n, 1)) < 0.5).astype(np.float64),
+          'count': rng.poisson(2.0, (n, 1)).astype(np.float64),
+          'positive': 0.1 + rng.gamma(2.0, 1.0, (n, 1)),
+          'unit': np.clip(rng.random((n, 1)), 0.05, 0.95),
+          'real': rng.standard_normal((n, 1))}
+    out = {}
+    for name, lik, kind in _lik_zoo(gpf):
+        Y = conv(Ys[kind])
+        out[name + '/logp'] = lik.logp(conv(F), Y)
+        out[name + '/cmean'] = lik.conditional_mean(conv(F))
+        out[name + '/cvar'] = lik.conditional_variance(conv(F))
+        out[name + '/varexp'] = lik.variational_expectations(conv(Fmu), conv(Fvar), Y)
+        out[name + '/pmean'], out[name + '/pvar'] = lik.predict_mean_and_var(conv(Fmu), conv(Fvar))
+        out[name + '/pdens'] = lik.predict_density(conv(Fmu), conv(Fvar), Y)
+    k = 4
+    mc = gpf.likelihoods.MultiClass(k)
+    Fk, Vk = rng.standard_normal((n, k)), 0.05 + rng.random((n, k))
+    lab = conv(rng.integers(0, k, (n, 1)).astype(np.float64))
+    out['multiclass/logp'] = mc.logp(conv(Fk), lab)
+    out['multiclass/cmean'] = mc.conditional_mean(conv(Fk))
+    out['multiclass/cvar'] = mc.conditional_variance(conv(Fk))
+    out['multiclass/varexp'] = mc.variational_expectations(conv(Fk), conv(Vk), lab)
+    out['multiclass/pmean'], out['multiclass/pvar'] = mc.predict_mean_and_var(conv(Fk), conv(Vk))
+    out['multiclass/pdens'] = mc.predict_density(conv(Fk), conv(Vk), lab)
+    return out, []
+
+
+def case_svgp_multiclass(gpf, conv):
+    """The model of examples/svgp.py:142-146 at test size: SVGP with the MultiClass likelihood,
+    one latent GP per class, whiten=False; bound, gradients, class probabilities and the
+    predictive log density the example reports (:151-155)."""
+    n, d, mi, k, batch = 400, 4, 30, 4, 160
+    X, _, Z = synth_svgp(n, d, mi, seed=21)
+    rng = np.random.default_rng(22)
+    W = rng.standard_normal((d, k))
+    lab = np.argmax(X @ W + 0.3 * rng.standard_normal((n, k)), 1).astype(np.float64)[:, None]
+    kern = gpf.kernels.RBF(d, ARD=True, lengthscales=1.7, name='mc_k')
+    lik = gpf.likelihoods.MultiClass(k)
+    m = gpf.models.SVGP(conv(X[:batch]), conv(lab[:batch]), kern, lik, Z=Z.copy(), num_latent=k,
+                        whiten=False, num_data=n, name='mc')
+    import torch
+    with torch.no_grad():
+        qm = m._q_mu.unconstrained_tensor
+        qm.copy_(torch.as_tensor(0.5 * rng.standard_normal(tuple(qm.shape))).to(qm))
+        qs = m._q_sqrt.unconstrained_tensor
+        qs.add_(torch.as_tensor(0.05 * rng.standard_normal(tuple(qs.shape))).to(qs))
+    Xs, labs = conv(X[batch:batch + 25]), conv(lab[batch:batch + 25])
+    out = {'objective': m.objective}
+    fmu, fvar = m._build_predict(Xs)
+    out['class_prob'], _ = m.likelihood.predict_mean_and_var(fmu, fvar)
+    out['pred_density'] = m.likelihood.predict_density(fmu, fvar, labs)
+    return out, [('objective', m)]
+
+
 # --------------------------------------------------------------------------- free functions
 def case_functions(gpf, conv):
     """base_conditional (conditionals.py:81-121), conditional (:25-66), gauss_kl
@@ -302,6 +374,8 @@ CASES = {
     'svgp_nonwhite_diag': case_svgp_nonwhite_diag,
     'sgpr': case_sgpr,
     'sparse_bounds': case_sparse_bounds,
+    'likelihoods': case_likelihoods,
+    'svgp_multiclass': case_svgp_multiclass,
     'functions': case_functions,
 }
 

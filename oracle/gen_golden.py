@@ -34,6 +34,23 @@ import gpflowSlim as gpf                            # noqa: E402  (the reference
 assert os.path.realpath(gpf.__file__).startswith(os.path.realpath(REF)), gpf.__file__
 gpf.settings.dtypes.float_type = np.float64
 
+# TensorFlow converts numpy operands of a tensor op on the fly (`gh_x * tf.sqrt(...)`,
+# likelihoods.py:147); torch does not multiply ndarray * Tensor.  The Gauss-Hermite nodes are
+# therefore handed to the reference as tensors -- same values, no reference source touched.
+import gpflowSlim.likelihoods as _ref_lik           # noqa: E402
+import gpflowSlim.quadrature as _ref_quad           # noqa: E402
+
+_np_hermgauss = _ref_quad.hermgauss
+
+
+def _hermgauss_as_tensors(n):
+    x, w = _np_hermgauss(n)
+    return torch.as_tensor(x), torch.as_tensor(w)
+
+
+_ref_quad.hermgauss = _hermgauss_as_tensors
+_ref_lik.hermgauss = _hermgauss_as_tensors
+
 from oracle import cases                            # noqa: E402
 
 

@@ -325,9 +325,30 @@ def reduce_sum(x, axis=None, keepdims=False, name=None, keep_dims=None):
     return x.sum() if axis is None else x.sum(dim=_axis(axis), keepdim=kd)
 
 
-def reduce_prod(x, axis=None, keepdims=False, name=None):
+def reduce_prod(x, axis=None, keepdims=False, name=None, reduction_indices=None):
     x = _t(x)
+    if axis is None and reduction_indices is not None:      # TF-1.x alias (likelihoods.py:424)
+        axis = reduction_indices[0] if isinstance(reduction_indices, (list, tuple)) else reduction_indices
     return x.prod() if axis is None else x.prod(dim=int(axis), keepdim=keepdims)
+
+
+def reduce_mean(x, axis=None, keepdims=False, name=None):
+    x = _t(x)
+    return x.mean() if axis is None else x.mean(dim=_axis(axis), keepdim=keepdims)
+
+
+def argmax(x, axis=0, output_type=None, name=None):
+    """tf.argmax: index of the largest entry along `axis` (first one on ties, like torch)."""
+    out = torch.argmax(_t(x), dim=int(axis))
+    return out if output_type is None else out.to(_dt(output_type))
+
+
+def one_hot(indices, depth, on_value=1.0, off_value=0.0, axis=-1, dtype=None, name=None):
+    """tf.one_hot with the new axis last: on_value at the index, off_value elsewhere."""
+    idx = _t(indices).to(torch.int64)
+    hot = torch.nn.functional.one_hot(idx, int(depth)).to(torch.float64)
+    out = hot * float(on_value) + (1.0 - hot) * float(off_value)
+    return out if dtype is None else out.to(_dt(dtype))
 
 
 def reduce_max(x, axis=None, keepdims=False, name=None):

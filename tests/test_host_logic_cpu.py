@@ -112,3 +112,19 @@ def test_adam_matches_oracle_adam():
         opt.apply_gradients([(gr, p)])
         q = R.tf_adam_step([q], [gr], state, lr=1e-2)[0]
     np.testing.assert_allclose(p.detach().numpy(), q.numpy(), rtol=1e-15)
+
+
+def test_likelihoods_match_reference_golden(golden):
+    """the likelihood zoo is elementwise torch maths with no library call, so
+    it can be held to the reference's golden vectors on CPU tensors as well (the GPU parity run
+    repeats it on the device)."""
+    import gpflowSlim as gpf
+    from oracle import cases
+    gold = golden('likelihoods')
+    res = cases.run_case(gpf, 'likelihoods', lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64)))
+    assert set(res) == set(gold)
+    for key in sorted(gold):
+        a, b = np.asarray(res[key], dtype=np.float64), np.asarray(gold[key], dtype=np.float64)
+        assert a.shape == b.shape, key
+        err = np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+        assert err < 1e-10, '%s: relative error %.2e' % (key, err)
