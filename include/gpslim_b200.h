@@ -108,7 +108,12 @@ int gps_destroy(gps_handle* h);
 int gps_set_stream(gps_handle* h, void* cuda_stream);      /* cudaStream_t, 0 = legacy default */
 const char* gps_last_error(gps_handle* h);
 int gps_version(void);
-/* options: "gemm_impl" 0 = DMMA tensor-core kernel (default), 1 = plain-FMA check kernel;
+/* options: "gemm_impl" 0 = DMMA tensor-core GEMM, operands staged by TMA when they are 16-byte
+ *                          aligned with even leading dimensions, else by cp.async (default);
+ *                      1 = plain-FMA check kernel; 2 = always the cp.async DMMA kernel;
+ *          "gram_impl" 0 = register-tiled Gram kernels for a single stationary covariance where
+ *                          they apply (default), 1 = the generic interpreter kernels only;
+ *          "leaf_impl" 0 = blocked DMMA 128x128 Cholesky leaf (default), 1 = scalar check kernel;
  *          "profile"   1 = bracket every GEMM-class launch with CUDA events. */
 int gps_set_option(gps_handle* h, const char* name, int64_t value);
 /* Sums since the last reset: milliseconds and algorithmic flops of the DMMA GEMM launches,
