@@ -36,13 +36,15 @@ class NeuralKernelNetwork(Kernel):
         return self._nknWrapper.forward(h).reshape(shape)
 
     def Kdiag(self, X, presliced=False):
-        if self._nknWrapper.fusable:
+        # `fusable` is False for Activation layers AND for composed primitive kernels
+        # (kernels.py: RatQuad, Polynomial, ...): both take the stacked-Gram route
+        if self.fusable:
             return super().Kdiag(X, presliced)
         vals = [k.Kdiag(X, presliced) for k in self._primitive_kernels]
         return self._unfused(vals, vals[0].shape)
 
     def K(self, X, X2=None, presliced=False):
-        if self._nknWrapper.fusable:
+        if self.fusable:
             return super().K(X, X2, presliced)
         vals = [k.K(X, X2, presliced) for k in self._primitive_kernels]
         return self._unfused(vals, vals[0].shape)

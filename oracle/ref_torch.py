@@ -21,6 +21,13 @@ Kernel specs are nested dicts of CONSTRAINED values (torch tensors, so autograd 
   {'type': 'periodic', 'variance': s2, 'lengthscales': l, 'period': p, 'active_dims': ...}
   {'type': 'sum'|'product', 'children': [spec | scalar tensor, ...]}
   {'type': 'nkn', 'prims': [spec...], 'layers': [('linear', W, b) | ('product', step), ...]}
+and, for SURVEY section 8(f) rank 4 (the reference's remaining covariances):
+  {'type': 'white'|'constant', 'variance': s2}
+  {'type': 'ratquad', 'variance', 'lengthscales', 'alpha', 'active_dims'}
+  {'type': 'polynomial', 'variance' (scalar or [D]), 'offset', 'degree', 'active_dims'}
+  {'type': 'cosine', 'variance', 'lengthscales', 'weights' [D, 1], 'active_dims'}
+  {'type': 'arccosine', 'order', 'variance', 'weight_variances', 'bias_variance', 'active_dims'}
+  {'type': 'tps', 'variance', 'active_dims'}
 """
 import math
 
@@ -100,9 +107,42 @@ def K(spec, X, X2=None):
         shp = prims[0].shape
         h = torch.stack([p.reshape(-1) for p in prims], 1)
         return nkn_forward(spec['layers'], h).reshape(shp)
+    if t == 'white':                                     # kernels.py:328-338
+        if X2 is None:
+            return torch.diag_embed(torch.ones(X.shape[0], dtype=F64) * spec['variance'])
+        return torch.zeros(X.shape[0], X2.shape[0], dtype=F64)
+    if t == 'constant':                                  # kernels.py:341-350
+        m = X.shape[0] if X2 is None else X2.shape[0]
+        return torch.ones(X.shape[0], m, dtype=F64) * spec['variance']
     Xa, X2a = _slice(spec, X), _slice(spec, X2)
     if t == 'linear':                                    # kernels.py:499-505
         return (Xa * spec['variance']) @ (Xa if X2a is None else X2a).T
+    if t == 'polynomial':                                # kernels.py:550-551
+        lin = (Xa * spec['variance']) @ (Xa if X2a is None else X2a).T
+        return (lin + spec['offset']) ** spec['degree']
+    if t == 'cosine':                                    # kernels.py:633-646
+        w = spec['weights']
+        prod = ((Xa / spec['lengthscales']) @ w).squeeze(-1)
+        prod2 = prod if X2a is None else ((X2a / spec['lengthscales']) @ w).squeeze(-1)
+        return spec['variance'] * torch.cos(prod[:, None] - prod2[None, :])
+    if t == 'arccosine':                                 # kernels.py:740-758
+        wv, bv, order = spec['weight_variances'], spec['bias_variance'], spec['order']
+        X2b = Xa if X2a is None else X2a
+        den = torch.sqrt((wv * Xa ** 2).sum(1) + bv)     # _weighted_product(X) :722-725
+        den2 = torch.sqrt((wv * X2b ** 2).sum(1) + bv)
+        num = (wv * Xa) @ X2b.T + bv
+        cos_theta = num / den[:, None] / den2[None, :]
+        jitter = 1e-15
+        theta = torch.acos(jitter + (1 - 2 * jitter) * cos_theta)
+        return spec['variance'] * (1. / math.pi) * arccos_J(order, theta) \
+            * den[:, None] ** order * den2[None, :] ** order
+    if t == 'tps':                                       # kernels.py:945-967 (lengthscales unused)
+        D = torch.sqrt(square_dist(Xa, X2a, 1.0))
+        R_ = 2.0
+        return spec['variance'] * (D ** 3 - 1.5 * R_ * D ** 2 + 0.5 * R_ ** 3)
+    if t == 'ratquad':                                   # kernels.py:467-471
+        d2 = square_dist(Xa, X2a, spec['lengthscales'])
+        return spec['variance'] * torch.pow(1.0 + 0.5 * d2 * (1.0 / spec['alpha']), -1.0 * spec['alpha'])
     if t == 'periodic':                                  # kernels.py:806-819
         X2b = Xa if X2a is None else X2a
         r = math.pi * (Xa[:, None, :] - X2b[None, :, :]) / spec['period']
@@ -141,7 +181,30 @@ def Kdiag(spec, X):
     if t == 'linear':
         Xa = _slice(spec, X)
         return (Xa ** 2 * spec['variance']).sum(1)
+    if t == 'polynomial':                                # kernels.py:553-554
+        Xa = _slice(spec, X)
+        return ((Xa ** 2 * spec['variance']).sum(1) + spec['offset']) ** spec['degree']
+    if t == 'arccosine':                                 # kernels.py:760-766
+        Xa = _slice(spec, X)
+        prod = (spec['weight_variances'] * Xa ** 2).sum(1) + spec['bias_variance']
+        return spec['variance'] * (1. / math.pi) * arccos_J(spec['order'], torch.zeros((), dtype=F64)) \
+            * prod ** spec['order']
+    if t == 'tps':                                       # kernels.py:969-970
+        return spec['variance'] * 0.5 * 2.0 ** 3 * torch.ones(X.shape[0], dtype=F64)
+    # white / constant (:324-325), stationary incl. ratquad / cosine (:428-429), periodic
     return torch.ones(X.shape[0], dtype=F64) * spec['variance']
+
+
+def arccos_J(order, theta):
+    """kernels.py:727-738: J_0 = pi - t; J_1 = sin t + (pi - t) cos t;
+    J_2 = 3 sin t cos t + (pi - t)(1 + 2 cos^2 t)."""
+    if order == 0:
+        return math.pi - theta
+    if order == 1:
+        return torch.sin(theta) + (math.pi - theta) * torch.cos(theta)
+    if order == 2:
+        return 3. * torch.sin(theta) * torch.cos(theta) + (math.pi - theta) * (1. + 2. * torch.cos(theta) ** 2)
+    raise ValueError(order)
 
 
 def nkn_forward(layers, h):

@@ -83,6 +83,18 @@ class _StaticShape(object):
 torch.Tensor.get_shape = lambda self: _StaticShape(self.shape)
 
 
+
+
+def _assign(self, value):
+    """tf.Variable.assign in eager mode (LBFGS.py:74): overwrite the variable's storage."""
+    with torch.no_grad():
+        self.copy_(_t(value).reshape(self.shape))
+    return self
+
+
+torch.Tensor.assign = _assign
+
+
 # ---------------------------------------------------------------- variables / scopes
 _VARIABLES = []  # every tf.get_variable, in creation order
 
@@ -279,6 +291,10 @@ def sin(x, name=None):
 
 def cos(x, name=None):
     return torch.cos(_t(x))
+
+
+def acos(x, name=None):
+    return torch.acos(_t(x))
 
 
 def abs(x, name=None):  # noqa: A001

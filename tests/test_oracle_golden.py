@@ -87,6 +87,91 @@ def test_kernels(golden):
         close(R.Kdiag(spec, X), g[name + '/Kdiag'], 1e-9, name + '/Kdiag')
 
 
+def _zoo_extra_specs(d):
+    """Oracle specs of oracle/cases.py:_kernel_zoo_extra with a leaf per reference parameter, in
+    the reference's parameter order; (spec, [(leaf, positive?)...])."""
+    ls = 0.7 + 0.15 * np.arange(d)
+    np.random.seed(5)
+    cw = np.random.normal(size=[d, 1])
+    out = {}
+
+    def add(name, build, vals):
+        leaves = [torch.tensor(np.asarray(v, dtype=np.float64), requires_grad=True) for v, _ in vals]
+        out[name] = (build(*leaves), leaves, [pos for _, pos in vals])
+    P, F = True, False
+    add('white', lambda v: dict(type='white', variance=v), [(0.7, P)])
+    add('constant', lambda v: dict(type='constant', variance=v), [(1.9, P)])
+    add('bias', lambda v: dict(type='constant', variance=v), [(0.3, P)])
+    rq = lambda v, l, a: dict(type='ratquad', variance=v, lengthscales=l, alpha=a, input_dim=d)
+    add('ratquad_iso', rq, [(1.2, P), (0.9, P), (1.7, P)])
+    add('ratquad_ard', rq, [(0.8, P), (ls, P), (0.6, P)])
+    add('poly3', lambda v, o: dict(type='polynomial', variance=v, offset=o, degree=3.0, input_dim=d),
+        [(0.4, P), (0.8, P)])
+    add('poly2_ard', lambda v, o: dict(type='polynomial', variance=v, offset=o, degree=2.0, input_dim=d),
+        [(0.3 + 0.1 * np.arange(d), P), (1.3, P)])
+    cs = lambda v, l, w: dict(type='cosine', variance=v, lengthscales=l, weights=w, input_dim=d)
+    add('cosine_iso', cs, [(1.1, P), (1.3, P), (cw, F)])
+    add('cosine_ard', cs, [(0.9, P), (ls, P), (cw, F)])
+    ac = lambda order: (lambda v, b, w: dict(type='arccosine', order=order, variance=v, bias_variance=b,
+                                             weight_variances=w, input_dim=d))
+    add('arccos0', ac(0), [(1.2, P), (0.4, P), (0.7, P)])
+    add('arccos1_ard', ac(1), [(0.8, P), (1.1, P), (0.5 + 0.2 * np.arange(d), P)])
+    add('arccos2', ac(2), [(0.6, P), (0.9, P), (1.3, P)])
+    add('tps', lambda v, l: dict(type='tps', variance=v, input_dim=d), [(0.5, P), (1.0, P)])
+    add('ratquad_active', lambda v, l, a: dict(type='ratquad', variance=v, lengthscales=l, alpha=a,
+                                               active_dims=[2, 0]),
+        [(1.0, P), ([0.5, 1.5], P), (2.0, P)])
+    st = lambda typ, v, l, ad=None, dim=d: dict(type=typ, variance=v, lengthscales=l, active_dims=ad,
+                                                input_dim=dim)
+    add('mixed_sum', lambda v1, l1, v2, l2, a2, v3, v4: dict(type='sum', children=[
+        st('rbf', v1, l1), rq(v2, l2, a2), dict(type='white', variance=v3),
+        dict(type='linear', variance=v4, input_dim=d), 0.11]),
+        [(1.0, P), (ls, P), (1.0, P), (1.0, P), (1.2, P), (0.05, P), (0.2, P)])
+    add('mixed_product', lambda v1, l1, v2, o2, v3: dict(type='product', children=[
+        st('matern32', v1, l1), dict(type='polynomial', variance=v2, offset=o2, degree=2.0, input_dim=d),
+        dict(type='constant', variance=v3)]),
+        [(1.0, P), (1.2, P), (1.0, P), (0.6, P), (1.4, P)])
+    add('sum_of_mixed_product', lambda v1, b1, w1, v2, l2, v3, l3, v4: dict(type='sum', children=[
+        dict(type='product', children=[
+            dict(type='arccosine', order=1, variance=v1, bias_variance=b1, weight_variances=w1,
+                 active_dims=[0, 1]),
+            st('rbf', v2, l2, [2], 1)]),
+        st('matern52', v3, l3), dict(type='constant', variance=v4)]),
+        [(1.0, P), (1.0, P), (1.0, P), (1.0, P), (1.0, P), (1.0, P), (1.0, P), (0.2, P)])
+    return out
+
+
+def test_kernels_extra(golden):
+    """SURVEY section 8(f) rank 4 covariances: Grams and parameter gradients of the oracle
+    restatement against the unmodified reference."""
+    g = golden('kernels_extra')
+    d = 3
+    rng = np.random.default_rng(40)
+    X = torch.tensor(rng.standard_normal((33, d)) * 1.2)
+    X2 = torch.tensor(rng.standard_normal((21, d)) * 1.2)
+    W, W2 = rng.standard_normal((33, 33)), rng.standard_normal((33, 21))
+    W = torch.tensor(W + W.T)
+    W2 = torch.tensor(W2)
+    specs = _zoo_extra_specs(d)
+    in_golden = {k.split('/')[0] for k in g} - {'coregion', 'kdim', 'dimwise'}
+    assert set(specs) == in_golden, sorted(set(specs) ^ in_golden)
+    for name, (spec, leaves, positive) in specs.items():
+        K, K2, Kd = R.K(spec, X), R.K(spec, X, X2), R.Kdiag(spec, X)
+        close(K, g[name + '/K'], 1e-9, name + '/K')
+        close(K2, g[name + '/K2'], 1e-9, name + '/K2')
+        close(Kd, g[name + '/Kdiag'], 1e-9, name + '/Kdiag')
+        val = (K2 * W2).sum() + (Kd * W[:, 0]).sum()
+        if name not in ('tps', 'arccos0'):
+            val = val + (K * W).sum()
+        gs = torch.autograd.grad(val, leaves, allow_unused=True)
+        for i, (leaf_, gr, pos) in enumerate(zip(leaves, gs, positive)):
+            gr = torch.zeros_like(leaf_) if gr is None else gr
+            if pos:   # d softplus(raw) / d raw = sigmoid(raw) = 1 - exp(-(y - 1e-6))
+                gr = gr * (1.0 - torch.exp(-(leaf_.detach() - 1e-6)))
+            close(gr.reshape(g['%s/grad%d' % (name, i)].shape), g['%s/grad%d' % (name, i)], 1e-8,
+                  '%s/grad%d' % (name, i))
+
+
 def _gpr_from_golden(g, d):
     raw = [leaf(g['param/objective/%d' % i]) for i in range(3)]
     spec = dict(type='rbf', variance=R.softplus_fwd(raw[0]), lengthscales=R.softplus_fwd(raw[1]))
