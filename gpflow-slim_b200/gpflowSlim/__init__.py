@@ -21,6 +21,7 @@ from . import mean_functions
 from . import models
 from . import neural_kernel_network
 from . import training
+from . import LBFGS as _LBFGS_module  # noqa: F401  (importable as gpflowSlim.LBFGS)
 from . import parallel
 
 from .params import Parameter as Param

@@ -23,7 +23,10 @@ class Model(object):
     def trainable_tensors(self):
         """The unconstrained leaves an optimiser steps (the reference trains
         tf.trainable_variables(), which also holds feature.Z: examples/svgp.py:160-163)."""
-        out = [p.unconstrained_tensor for p in self.parameters if p.trainable]
+        out = []
+        for p in self.parameters:       # a parameter may be listed twice (Polynomial, kernels.py:541)
+            if p.trainable and not any(p.unconstrained_tensor is q for q in out):
+                out.append(p.unconstrained_tensor)
         feat = getattr(self, 'feature', None)
         if feat is not None and getattr(feat, '_Z', None) is not None and feat._Z.trainable:
             out.append(feat._Z.unconstrained_tensor)
@@ -98,3 +101,18 @@ class GPModel(Model):
 
     def _build_predict(self, *args, **kwargs):
         raise NotImplementedError
+
+    def optimize(self, max_iter=1000):
+        """Eager L-BFGS on the objective (models/model.py:172-195): a fresh LBFGS with 20
+        correction pairs per call and the optimiser's own default of 100 iterations -- like the
+        reference, `max_iter` is accepted and not used.  If the run raises (a failed Cholesky,
+        'Very unstable, exit'), the objective history is printed and the parameters are reset to
+        the third-last recorded iterate (:180-187)."""
+        from ..LBFGS import LBFGS, model_opfunc
+        self.LBFGS_opt = LBFGS(model_opfunc(self), nCorrection=20)
+        try:
+            self.LBFGS_opt.run()
+        except Exception:
+            opt = self.LBFGS_opt
+            print([float(h[0]) for h in opt.history])
+            opt.update_vars(opt.history[0][3], opt.history[-3][2])

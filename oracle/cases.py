@@ -271,6 +271,51 @@ def case_gpr_misc(gpf, conv):
     return out, [('objective', m)]
 
 
+def case_lbfgs(gpf, conv):
+    """`GPModel.optimize` = the eager L-BFGS (LBFGS.py:44-338,
+    models/model.py:172-195) on a small ARD-RBF GPR: objective history, final iterate, and the
+    objective / predictions at the optimum."""
+    import torch
+    n, d = 150, 3
+    X, Y = synth_gpr(n, d, seed=16)
+    Xs = np.random.default_rng(17).standard_normal((15, d))
+    kern = gpf.kernels.RBF(d, ARD=True, name='lb_k')
+    m = gpf.models.GPR(conv(X), conv(Y), kern=kern, name='lb')
+    out = {'objective_before': m.objective}
+    m.optimize()
+    hist = m.LBFGS_opt.history
+    out['f_hist'] = torch.stack([h[0].detach().reshape(()) for h in hist])
+    out['x_final'] = hist[-1][2].detach()
+    out['objective_after'] = m.objective
+    out['pred_mu'], out['pred_var'] = m.predict_f(conv(Xs))
+    return out, []
+
+
+def case_lbfgs_rosenbrock(gpf, conv):
+    """The LBFGS class on its own (LBFGS.py:44-338) minimising a 6-D Rosenbrock function with 5
+    correction pairs: exercises memory eviction, both Zoom orientations and the iteration cap.
+    Pure host logic -- no Gram / Cholesky -- so it is a CPU-only case (HOST_ONLY_CASES)."""
+    import importlib
+    import torch
+    LBFGS = importlib.import_module(gpf.__name__ + '.LBFGS').LBFGS
+    out = {}
+    for tag, x0, kw in (('a', [-1.2, 1.0, 0.8, -0.5, 1.7, 0.3], dict(max_iter=60, nCorrection=5, tolFun=1e-10)),
+                        ('b', [0.5, -0.4, 2.0], dict(max_iter=25, nCorrection=100, tolFun=1e-7))):
+        w = conv(np.array(x0)).clone().requires_grad_(True)
+
+        def opfunc(w=w):
+            f = (100.0 * (w[1:] - w[:-1] ** 2) ** 2 + (1.0 - w[:-1]) ** 2).sum()
+            (g,) = torch.autograd.grad(f, [w])
+            return f, [(g, w)]
+        opt = LBFGS(opfunc, **kw)
+        ret = opt.run()
+        out[tag + '/f_hist'] = torch.stack([h[0].detach().reshape(()) for h in opt.history])
+        out[tag + '/x_hist'] = torch.stack([h[2].detach() for h in opt.history])
+        out[tag + '/x_end'] = w.detach().clone()
+        out[tag + '/n_eval'] = torch.tensor(float(ret[2]) if len(ret) > 2 else -1.0)
+    return out, []
+
+
 # --------------------------------------------------------------------------- SVGP / SGPR
 def _svgp(gpf, conv, n, d, minducing, batch, whiten, q_diag, latents, name, ls=None):
     X, Y, Z = synth_svgp(n, d, minducing, seed=0)
@@ -475,6 +520,8 @@ CASES = {
     'kernels': case_kernels,
     'kernels_extra': case_kernels_extra,
     'gpr_composed': case_gpr_composed,
+    'lbfgs': case_lbfgs,
+    'lbfgs_rosenbrock': case_lbfgs_rosenbrock,
     'nkn': case_nkn,
     'gpr_c1': case_gpr_c1,
     'gpr_c1_ls': case_gpr_c1_ls,
@@ -494,7 +541,9 @@ CASES = {
 # Cases added after the last session that had GPU time.  tests/test_gpu_parity.py runs the rest,
 # tests/test_gpu_zz_widened.py (sorted last, so a surprise there cannot mask the established
 # tests under `pytest -x`) runs these; once seen green on a B200 they simply leave this tuple.
-LATE_CASES = ('kernels_extra', 'gpr_composed')
+LATE_CASES = ('kernels_extra', 'gpr_composed', 'lbfgs')
+# Pure host logic (no library call): checked on the CPU only.
+HOST_ONLY_CASES = ('lbfgs_rosenbrock',)
 
 
 def run_case(gpf, name, conv):

@@ -20,7 +20,7 @@ def _gpf():
     return gpf
 
 
-@pytest.mark.parametrize('name', [c for c in cases.CASES if c not in cases.LATE_CASES])
+@pytest.mark.parametrize('name', [c for c in cases.CASES if c not in cases.LATE_CASES + cases.HOST_ONLY_CASES])
 def test_case_matches_reference_golden(golden, name):
     gold = golden(name)
     res = cases.run_case(_gpf(), name, conv)
