@@ -14,6 +14,7 @@ from . import densities
 from . import quadrature
 from . import likelihoods
 from . import kernels
+from . import kernel_kitchen_sink
 from . import conditionals
 from . import features
 from . import kullback_leiblers

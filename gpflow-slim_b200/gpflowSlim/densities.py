@@ -28,6 +28,28 @@ def multivariate_normal(x, mu, L):
     return ret
 
 
+def multivariate_normal_feature(x, mu, C, var):
+    """log N(x | mu, C C^T + var I) through the Woodbury identity: only the small
+    [n_small, n_small] matrix C^T C + var I is factored (densities.py:98-123; the reference tests
+    it against `multivariate_normal`, :159-174).  C is [n_big, n_small].  Op for op as the
+    reference, including its `+ jitter` inside the log-determinant and its treatment of a
+    multi-column x as one long vector."""
+    from ._settings import SETTINGS as settings
+    x = x - mu
+    dim1, dim2 = C.shape[0], C.shape[1]
+    Ct = _ops.t(C)
+    CtC = _ops.matmul_nt(Ct, Ct) + var * torch.eye(dim2, dtype=C.dtype, device=C.device)
+    L = _ops.cholesky(CtC)
+    logdet_L = torch.log(torch.diagonal(L) + settings.jitter).sum()
+    logdet_CCt = 2. * logdet_L + float(dim1 - dim2) * torch.log(var)
+    x_norm = (x ** 2).sum()
+    Ctx = _ops.matmul_nt(Ct, _ops.t(x))                # C^T x  [n_small, R]
+    L_inv_x = _ops.solve_lower(L, Ctx)
+    square_dist = (x_norm - (L_inv_x ** 2).sum()) / var
+    logp = square_dist + float(dim1) * LOG2PI + logdet_CCt
+    return -logp * 0.5
+
+
 # ---- densities behind the non-Gaussian likelihoods (reference densities.py:28-70); elementwise
 def lognormal(x, mu, var):
     lnx = torch.log(x)

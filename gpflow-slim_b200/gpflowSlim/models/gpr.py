@@ -9,7 +9,7 @@ import torch
 
 from .. import likelihoods
 from .._backend import ops as _ops
-from ..densities import multivariate_normal
+from ..densities import multivariate_normal, multivariate_normal_feature
 from ..misc import to_tensor
 from .model import GPModel
 
@@ -33,9 +33,21 @@ class GPR(GPModel):
             return False
         return True
 
+    def _feature_map(self):
+        """`kern.features` if the covariance is an explicit feature expansion K = C C^T
+        (kernel_kitchen_sink.SamplerKernel), else None (models/gpr.py:62-63, :85-86)."""
+        fn = getattr(self.kern, 'features', None)
+        return fn if fn is not None and callable(fn) else None
+
     def _build_likelihood(self):
         """log p(Y | theta) (models/gpr.py:55-72).  NOTE: no jitter, only + noise I (:69)."""
         m = self.mean_function(self.X)
+        features = self._feature_map()
+        if features is not None:                     # Woodbury form, no N x N matrix (:62-66)
+            var = self.likelihood.variance
+            var = var if isinstance(var, torch.Tensor) else torch.as_tensor(var, dtype=self.X.dtype,
+                                                                            device=self.X.device)
+            return multivariate_normal_feature(self.Y, m, features(self.X), var)
         if self._fusable(self.X):
             return _ops.gpr_loglik(self.kern.program(), self.X, self.Y - m, self.likelihood.variance)
         n = self.X.shape[0]
@@ -48,6 +60,9 @@ class GPR(GPModel):
         """p(F* | Y) (models/gpr.py:118-131)."""
         Xnew = to_tensor(Xnew)
         r = self.Y.shape[1]
+        features = self._feature_map()
+        if features is not None:
+            return self._build_predict_features(features, Xnew, full_cov)
         if self._fusable(self.X, Xnew) and not torch.is_grad_enabled():
             mean, var = _ops.gpr_predict(self.kern.program(), self.X, self.Y - self.mean_function(self.X),
                                          self.likelihood.variance, Xnew, full_cov=full_cov)
@@ -70,3 +85,32 @@ class GPR(GPModel):
             fvar = self.kern.Kdiag(Xnew) - (At ** 2).sum(1)
             fvar = fvar.reshape(-1, 1).expand(-1, r)
         return fmean, fvar
+
+    def _build_predict_features(self, features, Xnew, full_cov):
+        """Prediction through the feature expansion (models/gpr.py:84-114): with C = features(X),
+        B = features(Xnew) and S = C^T C + sigma^2 I (small), G = (C^T - C^T C S^-1 C^T) / sigma^2
+        = C^T (C C^T + sigma^2 I)^-1, fmean = B G (Y - m) + m*, fvar = B B^T - B G C B^T.
+        S^-1 comes from the Cholesky factor (U U^T, U = L^-T) instead of the reference's
+        tf.matrix_inverse; all products run on the tensor-core GEMM."""
+        from .._backend.lib import TRI_UPPER
+        r = self.Y.shape[1]
+        var = self.likelihood.variance
+        mX, m_new = self.mean_function(self.X), self.mean_function(Xnew)
+        feat, feat_new = features(self.X), features(Xnew)
+        Ct = _ops.t(feat)                                         # [d, N]
+        CtC = _ops.matmul_nt(Ct, Ct)                              # [d, d]
+        S = CtC + torch.eye(CtC.shape[0], dtype=CtC.dtype, device=CtC.device) * var
+        U = _ops._TriInvT.apply(_ops.cholesky(S))
+        S_inv = _ops.matmul_nt(U, U, a_tri=TRI_UPPER, b_tri=TRI_UPPER)
+        tmp = _ops.matmul(CtC, _ops.matmul(S_inv, Ct))
+        G = (Ct - tmp) / var                                      # [d, N]
+        fmean = _ops.matmul(feat_new, _ops.matmul(G, self.Y - mX)) + m_new
+        GC = _ops.matmul(G, feat)                                 # [d, d]
+        if full_cov:
+            BBt = _ops.matmul_nt(feat_new, feat_new)
+            fvar = BBt - _ops.matmul(feat_new, _ops.matmul_nt(GC, feat_new))
+            return fmean, fvar.unsqueeze(2).expand(-1, -1, r)
+        tmp = _ops.matmul(feat_new, GC)
+        fvar = (feat_new ** 2.).sum(-1) - (tmp * feat_new).sum(-1)
+        return fmean, fvar.reshape(-1, 1).expand(-1, r)
+

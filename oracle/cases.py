@@ -316,6 +316,46 @@ def case_lbfgs_rosenbrock(gpf, conv):
     return out, []
 
 
+def case_gpr_features(gpf, conv):
+    """GPR's feature path (models/gpr.py:62-66, :84-114): a random-feature kernel
+    (kernel_kitchen_sink.SamplerKernel over RBFSampler / LinearSampler) makes GPR use
+    densities.multivariate_normal_feature (densities.py:98-123) and the Woodbury predictor.
+    Also the two functions the reference's own tests compare (densities.py:159-174,
+    models/gpr.py:135-203): the feature path against the Cholesky path on the same K = C C^T."""
+    import torch
+    ks = gpf.kernel_kitchen_sink
+    n, d, nc = 90, 3, 12
+    X, Y = synth_gpr(n, d, seed=18)
+    Y = np.concatenate([Y, 0.5 * Y ** 2], 1)
+    Xs = np.random.default_rng(19).standard_normal((14, d))
+    out = {}
+    for tag, make in (('rbf', lambda: ks.RBFSampler(d, ls=1.3, var=0.9, n_components=nc)),
+                      ('lin', lambda: ks.LinearSampler(d, var=0.7, n_components=6))):
+        np.random.seed(7)
+        sampler = make()
+        kern = ks.SamplerKernel(sampler)
+        m = gpf.models.GPR(conv(X), conv(Y), kern=kern, obs_var=0.4, name='gf_' + tag)
+        obj = m.objective
+        out[tag + '/objective'] = obj
+        out[tag + '/K'] = kern.K(conv(X[:20]), conv(Xs))
+        out[tag + '/Kdiag'] = kern.Kdiag(conv(Xs))
+        out[tag + '/pred_mu'], out[tag + '/pred_var'] = m.predict_f(conv(Xs))
+        out[tag + '/full_mu'], out[tag + '/full_cov'] = m.predict_f_full_cov(conv(Xs))
+        params = [sampler._variance] + ([sampler._ls] if tag == 'rbf' else []) + list(m.likelihood.parameters)
+        gs = torch.autograd.grad(obj, [p.unconstrained_tensor for p in params])
+        for i, g in enumerate(gs):
+            out['%s/grad%d' % (tag, i)] = g
+        # the same density through the N x N Cholesky (densities.py:73-95)
+        C = kern.features(conv(X))
+        var = m.likelihood.variance
+        Kfull = kern.K(conv(X)) + var * conv(np.eye(n))
+        out[tag + '/mvn_feature'] = gpf.densities.multivariate_normal_feature(
+            conv(Y[:, :1]), conv(np.zeros((n, 1))), C, var)
+        out[tag + '/mvn_cholesky'] = gpf.densities.multivariate_normal(
+            conv(Y[:, :1]), conv(np.zeros((n, 1))), torch.linalg.cholesky(Kfull))
+    return out, []
+
+
 # --------------------------------------------------------------------------- SVGP / SGPR
 def _svgp(gpf, conv, n, d, minducing, batch, whiten, q_diag, latents, name, ls=None):
     X, Y, Z = synth_svgp(n, d, minducing, seed=0)
@@ -520,6 +560,7 @@ CASES = {
     'kernels': case_kernels,
     'kernels_extra': case_kernels_extra,
     'gpr_composed': case_gpr_composed,
+    'gpr_features': case_gpr_features,
     'lbfgs': case_lbfgs,
     'lbfgs_rosenbrock': case_lbfgs_rosenbrock,
     'nkn': case_nkn,
@@ -541,7 +582,7 @@ CASES = {
 # Cases added after the last session that had GPU time.  tests/test_gpu_parity.py runs the rest,
 # tests/test_gpu_zz_widened.py (sorted last, so a surprise there cannot mask the established
 # tests under `pytest -x`) runs these; once seen green on a B200 they simply leave this tuple.
-LATE_CASES = ('kernels_extra', 'gpr_composed', 'lbfgs')
+LATE_CASES = ('kernels_extra', 'gpr_composed', 'lbfgs', 'gpr_features')
 # Pure host logic (no library call): checked on the CPU only.
 HOST_ONLY_CASES = ('lbfgs_rosenbrock',)
 

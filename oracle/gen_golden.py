@@ -51,6 +51,30 @@ def _hermgauss_as_tensors(n):
 _ref_quad.hermgauss = _hermgauss_as_tensors
 _ref_lik.hermgauss = _hermgauss_as_tensors
 
+# Same on-the-fly conversion in kernel_kitchen_sink.py:90 (`np.random.normal(...) / tf.reshape(ls)`):
+# that module sees a numpy stand-in whose random draws (same global RNG stream, same values) come
+# back as tensors; every other attribute is numpy's.
+import gpflowSlim.kernel_kitchen_sink as _ref_ks    # noqa: E402
+
+
+class _RandomAsTensors(object):
+    def normal(self, *a, **kw):
+        return torch.as_tensor(np.random.normal(*a, **kw))
+
+    def uniform(self, *a, **kw):
+        return torch.as_tensor(np.random.uniform(*a, **kw))
+
+
+class _NumpyWithTensorDraws(object):
+    random = _RandomAsTensors()
+
+    def __getattr__(self, name):
+        return getattr(np, name)
+
+
+_ref_ks.np = _NumpyWithTensorDraws()
+torch.Tensor.astype = lambda self, dtype: self.to(tf._dt(dtype))
+
 from oracle import cases                            # noqa: E402
 
 

@@ -431,6 +431,12 @@ def einsum(eq, *ops):
     return torch.einsum(eq, *[_t(o) for o in ops])
 
 
+def assert_equal(x, y, message=None, **kw):
+    if not bool(torch.all(_t(x) == _t(y))):
+        raise ValueError('tf.assert_equal failed: %r' % (message,))
+    return None
+
+
 def cond(pred, true_fn, false_fn, **kw):
     return true_fn() if bool(pred) else false_fn()
 

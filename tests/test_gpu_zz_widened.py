@@ -47,3 +47,41 @@ def test_composed_kernels_run_on_the_library():
         assert h.profile_read(reset=False)[2] > before, type(kern).__name__
         assert K.shape == (300, 300) and bool(torch.isfinite(K).all())
         assert_close(K, K.t(), 1e-12, type(kern).__name__ + ' symmetry')
+
+
+def test_reference_own_tests_on_the_gpu():
+    """densities.py:159-174 and models/gpr.py:135-203 of the reference (see
+    tests/reference_own_tests.py)."""
+    import gpflowSlim as gpf
+    import reference_own_tests as rot
+    a, b = rot.mvn_feature_vs_cholesky(gpf, conv)
+    assert abs(a - b) < 1e-6 + 1e-6 * abs(b)
+    for got, want in rot.predict_feature_vs_standard(gpf, conv):
+        np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-9)
+
+
+def _load_example(name):
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('example_' + name, os.path.join(root, 'examples', name + '.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_example_scripts_run_on_the_gpu():
+    """examples/gpr.py (Adam steps, then the L-BFGS trainer) and examples/svgp.py (network +
+    multi-class SVGP trained jointly; the gradient reaches the network through the Gram
+    kernels' d/dX path) on the real kernels."""
+    ex = _load_example('gpr')
+    first, _, _ = ex.main(iters=1, quiet=True)
+    last, _, _ = ex.main(iters=25, quiet=True)
+    assert last < first
+    obj, rmse, ll = ex.main(lbfgs=True, quiet=True)
+    assert obj < last and rmse < 6.0 and ll > -3.5
+    sv = _load_example('svgp')
+    loss, acc, ll = sv.main(iters=12, quiet=True, n_train=600, n_test=200, num_inducing=20,
+                            minibatch_size=100, num_h=8)
+    assert loss == loss and 0.0 <= acc <= 1.0 and ll == ll
+
