@@ -19,6 +19,7 @@ from . import conditionals
 from . import features
 from . import kullback_leiblers
 from . import mean_functions
+from . import priors
 from . import models
 from . import neural_kernel_network
 from . import training

@@ -73,6 +73,22 @@ class _NumpyWithTensorDraws(object):
 
 
 _ref_ks.np = _NumpyWithTensorDraws()
+
+# ... and in priors.py:34-100, whose hyper-parameters are numpy arrays multiplied into tensors
+# (`-shape * tf.log(scale)`, densities.py:46): they are stored as tensors of the same values.
+import gpflowSlim.priors as _ref_priors             # noqa: E402
+
+
+class _NumpyWithTensorHyper(object):
+    @staticmethod
+    def atleast_1d(a):
+        return torch.as_tensor(np.atleast_1d(a))
+
+    def __getattr__(self, name):
+        return getattr(np, name)
+
+
+_ref_priors.np = _NumpyWithTensorHyper()
 torch.Tensor.astype = lambda self, dtype: self.to(tf._dt(dtype))
 
 from oracle import cases                            # noqa: E402
