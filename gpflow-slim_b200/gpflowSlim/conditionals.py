@@ -16,7 +16,7 @@ from .misc import to_tensor
 def conditional(Xnew, X, kern, f, *, full_cov=False, q_sqrt=None, white=False):
     """conditionals.py:25-66."""
     Xnew, X = to_tensor(Xnew), to_tensor(X)
-    Kmm = _ops.gram(kern.program(), X, None, diag_add=float(settings.numerics.jitter_level))
+    Kmm = kern.K_jittered(X, settings.numerics.jitter_level)
     Kmn = kern.K(X, Xnew)
     Knn = kern.K(Xnew) if full_cov else kern.Kdiag(Xnew)
     return base_conditional(Kmn, Kmm, Knn, f, full_cov=full_cov, q_sqrt=q_sqrt, white=white)

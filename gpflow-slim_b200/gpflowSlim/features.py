@@ -37,10 +37,57 @@ class InducingPoints(InducingFeature):
     def Kuu(self, kern, jitter=0.0):
         """K(Z) + jitter I -- the jitter lands in the Gram kernel's diagonal epilogue
         (features.py:74-77)."""
-        return _ops.gram(kern.program(), self.Z, None, diag_add=float(jitter))
+        return kern.K_jittered(self.Z, jitter)
 
     def Kuf(self, kern, Xnew):
         return kern.K(self.Z, Xnew)
+
+
+class Multiscale(InducingPoints):
+    """Multi-scale inducing features (Lazaro-Gredilla & Figueiras-Vidal 2009; features.py:89-150):
+    each inducing point carries its own Gaussian widths `scales` [M, D]; defined for the RBF
+    kernel only.  O(N M D) elementwise device work (the per-pair lengthscales rule out the
+    inner-product form of the fused Gram kernel)."""
+
+    def __init__(self, Z, scales):
+        super().__init__(Z)
+        from . import transforms
+        self._scales = Parameter(scales, transform=transforms.positive)
+        if tuple(self.Z.shape) != tuple(np.shape(scales)):
+            raise ValueError('Input locations `Z` and `scales` must have the same shape.')
+
+    @property
+    def scales(self):
+        return self._scales.value
+
+    def _cust_square_dist(self, A, B, sc):
+        """sum_d ((a_d - b_d) / sc_d)^2 with per-pair scales sc [N, M, D] (or broadcastable)."""
+        return (((A.unsqueeze(1) - B.unsqueeze(0)) / sc) ** 2).sum(2)
+
+    @staticmethod
+    def _check(kern):
+        from . import kernels
+        if not isinstance(kern, kernels.RBF):
+            raise NotImplementedError('Multiscale features not implemented for `%s`.' % str(type(kern)))
+
+    def Kuf(self, kern, Xnew):
+        self._check(kern)
+        from .misc import to_tensor
+        Xnew, _ = kern._slice(to_tensor(Xnew), None)
+        Zmu, Zlen = kern._slice(self.Z, self.scales)
+        idlengthscales = kern.lengthscales + Zlen
+        d = self._cust_square_dist(Xnew, Zmu, idlengthscales)
+        return (kern.variance * torch.exp(-d / 2) *
+                (kern.lengthscales / idlengthscales).prod(1).reshape(1, -1)).t()
+
+    def Kuu(self, kern, jitter=0.0):
+        self._check(kern)
+        Zmu, Zlen = kern._slice(self.Z, self.scales)
+        idlengthscales2 = (kern.lengthscales + Zlen) ** 2
+        sc = torch.sqrt(idlengthscales2.unsqueeze(0) + idlengthscales2.unsqueeze(1) - kern.lengthscales ** 2)
+        d = self._cust_square_dist(Zmu, Zmu, sc)
+        Kzz = kern.variance * torch.exp(-d / 2) * (kern.lengthscales / sc).prod(2)
+        return Kzz + jitter * torch.eye(len(self), dtype=Kzz.dtype, device=Kzz.device)
 
 
 @singledispatch

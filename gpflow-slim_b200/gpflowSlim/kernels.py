@@ -145,6 +145,14 @@ class Kernel(object):
     def Kdiag(self, X, presliced=False):
         return _ops.kdiag(self.program(presliced), to_tensor(X))
 
+    def K_jittered(self, X, jitter):
+        """K(X) + jitter I (features.py:74-77, conditionals.py:60).  Fused kernels add the
+        jitter in the Gram kernel's diagonal epilogue; composed kernels add it elementwise."""
+        X = to_tensor(X)
+        if self.fusable:
+            return _ops.gram(self.program(), X, None, diag_add=float(jitter))
+        return self.K(X) + torch.eye(X.shape[0], dtype=X.dtype, device=X.device) * float(jitter)
+
     # -- compilation ---------------------------------------------------------------------
     def _dims(self, presliced=False):
         """Columns of X this kernel reads (kernels.py:217-253)."""
