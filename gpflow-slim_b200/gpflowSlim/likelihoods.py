@@ -335,3 +335,52 @@ class MultiClass(Likelihood):
     def conditional_variance(self, F):
         p = self.conditional_mean(F)
         return p - p ** 2
+
+
+class SwitchedLikelihood(Likelihood):
+    """Declared but not implemented in the reference (likelihoods.py:491-551)."""
+    pass
+
+
+class Ordinal(Likelihood):
+    """Ordinal regression (Chu & Ghahramani 2005; likelihoods.py:554-631): labels 0..K with
+    K-1... bin edges a_k, p(Y = k | F) = phi((a_k - F) / sigma) - phi((a_{k-1} - F) / sigma)."""
+
+    def __init__(self, bin_edges):
+        Likelihood.__init__(self)
+        self.bin_edges = np.asarray(bin_edges, dtype=np.float64)
+        self.num_bins = self.bin_edges.size + 1
+        self._sigma = Parameter(1.0, transform=transforms.positive, name='sigma')
+        self._parameters = self._parameters + [self._sigma]
+
+    @property
+    def sigma(self):
+        return self._sigma.value
+
+    def _scaled_bins(self, like):
+        edges = _const(self.bin_edges, like) / self.sigma
+        inf = _const(np.array([np.inf]), like)
+        return torch.cat([edges, inf], 0), torch.cat([-inf, edges], 0)
+
+    def logp(self, F, Y):
+        left, right = self._scaled_bins(F)
+        idx = Y.to(torch.int64)
+        return torch.log(probit(left[idx] - F / self.sigma) - probit(right[idx] - F / self.sigma) + 1e-6)
+
+    def _make_phi(self, F):
+        """[numel(F), num_bins] label probabilities, F flattened (:600-611)."""
+        left, right = self._scaled_bins(F)
+        Fs = F.reshape(-1, 1) / self.sigma
+        return probit(left - Fs) - probit(right - Fs)
+
+    def conditional_mean(self, F):
+        phi = self._make_phi(F)
+        Ys = _const(np.arange(self.num_bins, dtype=np.float64), F).reshape(-1, 1)
+        return (phi @ Ys).reshape(F.shape)
+
+    def conditional_variance(self, F):
+        phi = self._make_phi(F)
+        Ys = _const(np.arange(self.num_bins, dtype=np.float64), F).reshape(-1, 1)
+        E_y = phi @ Ys
+        E_y2 = phi @ Ys ** 2
+        return (E_y2 - E_y ** 2).reshape(F.shape)

@@ -587,6 +587,36 @@ def case_likelihoods(gpf, conv):
     return out, []
 
 
+def case_likelihoods_extra(gpf, conv):
+    """The Ordinal likelihood (likelihoods.py:554-631) through every base-class entry point, and
+    the multivariate Gauss-Hermite helper mvnquad (quadrature.py:30-77)."""
+    import torch
+    rng = np.random.default_rng(33)
+    n = 19
+    Fmu, Fvar = rng.standard_normal((n, 1)) * 1.2, 0.05 + rng.random((n, 1))
+    F = rng.standard_normal((n, 1)) * 1.5
+    Y = conv(rng.integers(0, 4, (n, 1)).astype(np.float64))
+    lik = gpf.likelihoods.Ordinal(np.array([-1.0, 0.2, 1.1]))
+    # TensorFlow converts the numpy bin edges on the fly in `bin_edges / sigma` (:600); torch does
+    # not divide ndarray by Tensor, so the attribute is handed over as a tensor of the same values
+    lik.bin_edges = conv(lik.bin_edges)
+    out = {'ordinal/logp': lik.logp(conv(F), Y),
+           'ordinal/cmean': lik.conditional_mean(conv(F)),
+           'ordinal/cvar': lik.conditional_variance(conv(F)),
+           'ordinal/varexp': lik.variational_expectations(conv(Fmu), conv(Fvar), Y),
+           'ordinal/pdens': lik.predict_density(conv(Fmu), conv(Fvar), Y)}
+    out['ordinal/pmean'], out['ordinal/pvar'] = lik.predict_mean_and_var(conv(Fmu), conv(Fvar))
+    D = 2
+    means = rng.standard_normal((5, D))
+    A = rng.standard_normal((5, D, D))
+    covs = A @ A.transpose(0, 2, 1) + 0.3 * np.eye(D)
+    out['mvnquad/scalar'] = gpf.quadrature.mvnquad(lambda x: torch.sin(x[:, 0]) * torch.exp(0.3 * x[:, 1]),
+                                                   conv(means), conv(covs), 7, D)
+    out['mvnquad/vector'] = gpf.quadrature.mvnquad(lambda x: torch.stack([x[:, 0] ** 2, x[:, 0] * x[:, 1], x[:, 1]], 1),
+                                                   conv(means), conv(covs), 5, D, Dout=(3,))
+    return out, []
+
+
 def case_svgp_multiclass(gpf, conv):
     """The model of examples/svgp.py:142-146 at test size: SVGP with the MultiClass likelihood,
     one latent GP per class, whiten=False; bound, gradients, class probabilities and the
@@ -670,13 +700,14 @@ CASES = {
     'sparse_bounds': case_sparse_bounds,
     'likelihoods': case_likelihoods,
     'svgp_multiclass': case_svgp_multiclass,
+    'likelihoods_extra': case_likelihoods_extra,
     'functions': case_functions,
 }
 
 # Cases added after the last session that had GPU time.  tests/test_gpu_parity.py runs the rest,
 # tests/test_gpu_zz_widened.py (sorted last, so a surprise there cannot mask the established
 # tests under `pytest -x`) runs these; once seen green on a B200 they simply leave this tuple.
-LATE_CASES = ('kernels_extra', 'gpr_composed', 'lbfgs', 'gpr_features', 'priors', 'mc_models')
+LATE_CASES = ('kernels_extra', 'gpr_composed', 'lbfgs', 'gpr_features', 'priors', 'mc_models', 'likelihoods_extra')
 # Pure host logic (no library call): checked on the CPU only.
 HOST_ONLY_CASES = ('lbfgs_rosenbrock',)
 

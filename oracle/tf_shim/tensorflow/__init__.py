@@ -234,8 +234,11 @@ def tile(x, multiples, name=None):
 
 
 def gather(x, indices, axis=0, name=None):
+    # tf.gather: result shape = x.shape[:axis] + indices.shape + x.shape[axis+1:]
     idx = torch.as_tensor(np.asarray(indices), dtype=torch.int64)
-    return torch.index_select(_t(x), int(axis), idx)
+    x, axis = _t(x), int(axis)
+    out = torch.index_select(x, axis, idx.reshape(-1))
+    return out.reshape(tuple(x.shape[:axis]) + tuple(idx.shape) + tuple(x.shape[axis + 1:]))
 
 
 def scatter_nd(indices, updates, shape, name=None):  # noqa: A002
