@@ -505,6 +505,267 @@ gram_bwd_kernel(const Plan pl, const PlanDims pd, const double* __restrict__ the
   }
 }
 
+
+// --------------------------------------------------------------------------- backward, v2
+// EXPERIMENTAL (gps_set_option("gram_impl", 2); not the default until measured on a B200).
+// Same arithmetic as gram_bwd_kernel, different storage: the interpreter's per-thread arrays
+// (theta-gradient accumulators, slot values and slot adjoints) are indexed by RUNTIME program
+// data, so in gram_bwd_kernel they live in local memory -- ~120 read-modify-writes of local
+// memory per matrix element for the NKN config, which is what makes that config spend more
+// time in the Gram backward than in the factorisation.  Here they live in SHARED memory in a
+// [index][thread] layout: consecutive threads touch consecutive 8-byte words, so every access
+// is a conflict-free LDS/STS, whatever the (warp-uniform) index is.  To make room the CTA is
+// 128 threads on a 32 x 32 tile (8 elements per thread).
+constexpr int T2 = 32;          // tile edge
+constexpr int NT2 = 128;        // threads per CTA
+
+struct SmemSlots {
+  double* base;                 // [n][NT2]
+  int tid;
+  __device__ __forceinline__ double& operator[](int i) const { return base[i * NT2 + tid]; }
+};
+
+__device__ __forceinline__ void program_fwd_s(const Plan& pl, const double* __restrict__ th, const SmemSlots& v) {
+  for (int q = 0; q < pl.n_ops; ++q) {
+    const OpC o = pl.ops[q];
+    switch (o.op) {
+      case GPS_OP_CONST: v[o.dst] = th[o.a]; break;
+      case GPS_OP_ADD: v[o.dst] = v[o.a] + v[o.b]; break;
+      case GPS_OP_MUL: v[o.dst] = v[o.a] * v[o.b]; break;
+      case GPS_OP_COPY: v[o.dst] = v[o.a]; break;
+      case GPS_OP_LINEAR:
+        for (int r = 0; r < o.n; ++r) {
+          double s = 0.0;
+          for (int c = 0; c < o.b; ++c) s = fma(v[o.a + c], th[o.c + r * o.b + c], s);
+          v[o.dst + r] = s + th[o.d + r];
+        }
+        break;
+      case GPS_OP_PRODUCT:
+        for (int g = 0; g < o.n; ++g) {
+          double s = v[o.a + g * o.b];
+          for (int c = 1; c < o.b; ++c) s *= v[o.a + g * o.b + c];
+          v[o.dst + g] = s;
+        }
+        break;
+    }
+  }
+}
+
+__device__ __forceinline__ void program_bwd_s(const Plan& pl, const double* __restrict__ th, const SmemSlots& v,
+                                              const SmemSlots& vb, const SmemSlots& acc) {
+  for (int q = pl.n_ops - 1; q >= 0; --q) {
+    const OpC o = pl.ops[q];
+    switch (o.op) {
+      case GPS_OP_CONST: acc[o.a] += vb[o.dst]; break;
+      case GPS_OP_ADD: { double g = vb[o.dst]; vb[o.a] += g; vb[o.b] += g; } break;
+      case GPS_OP_MUL: {
+        double g = vb[o.dst];
+        double va = v[o.a], vbv = v[o.b];
+        vb[o.a] += g * vbv;
+        vb[o.b] += g * va;
+      } break;
+      case GPS_OP_COPY: vb[o.a] += vb[o.dst]; break;
+      case GPS_OP_LINEAR:
+        for (int r = 0; r < o.n; ++r) {
+          double g = vb[o.dst + r];
+          acc[o.d + r] += g;
+          for (int c = 0; c < o.b; ++c) {
+            acc[o.c + r * o.b + c] = fma(g, v[o.a + c], acc[o.c + r * o.b + c]);
+            vb[o.a + c] = fma(g, th[o.c + r * o.b + c], vb[o.a + c]);
+          }
+        }
+        break;
+      case GPS_OP_PRODUCT:
+        for (int g = 0; g < o.n; ++g) {
+          double gg = vb[o.dst + g];
+          for (int c = 0; c < o.b; ++c) {
+            double s = gg;
+            for (int c2 = 0; c2 < o.b; ++c2)
+              if (c2 != c) s *= v[o.a + g * o.b + c2];
+            vb[o.a + g * o.b + c] += s;
+          }
+        }
+        break;
+    }
+  }
+}
+
+// number of slots a program touches (primitives + op results)
+int plan_nslots(const Plan& pl) {
+  int n = pl.n_prims;
+  if (pl.n_ops) {
+    const OpC last = pl.ops[pl.n_ops - 1];
+    n = last.dst + ((last.op == GPS_OP_LINEAR || last.op == GPS_OP_PRODUCT) ? last.n : 1);
+  }
+  return n;
+}
+
+// doubles of dynamic shared memory gram_bwd_smem_kernel needs
+size_t bwd_smem_doubles(const Plan& pl, int nslots, int mode, int R, int want_dx, int xcols) {
+  const size_t nacc = pl.n_theta + 1;
+  return (size_t)pl.n_theta + 2 * (size_t)T2 * pl.S + (mode == W_GPR ? 2 * (size_t)R * T2 : 0) +
+         (want_dx ? (size_t)T2 * xcols : 0) + nacc * NT2 + 2 * (size_t)nslots * NT2;
+}
+
+__global__ void __launch_bounds__(NT2)
+gram_bwd_smem_kernel(const Plan pl, const PlanDims pd, const int nslots, const double* __restrict__ theta,
+                     const double* __restrict__ FL, const double* __restrict__ FR, int64_t N, int64_t M,
+                     const BwdArgs w, double* __restrict__ part_theta, double* __restrict__ part_dx) {
+  extern __shared__ double sm[];
+  const int nacc = pl.n_theta + 1;
+  const int tid = threadIdx.x;
+  double* th = sm;                                 // [n_theta]
+  double* sl = th + pl.n_theta;                    // [T2][S]
+  double* sr = sl + T2 * pl.S;                     // [T2][S]
+  double* bi = sr + T2 * pl.S;                     // [R][T2]   beta rows (i side)
+  double* bj = bi + (w.mode == W_GPR ? w.R * T2 : 0);
+  double* dxs = bj + (w.mode == W_GPR ? w.R * T2 : 0);   // [T2][xcols]
+  double* accb = dxs + (w.want_dx ? T2 * w.xcols : 0);   // [nacc][NT2]
+  double* vbase = accb + nacc * NT2;                     // [nslots][NT2]
+  double* vbbase = vbase + nslots * NT2;                 // [nslots][NT2]
+  const SmemSlots acc{accb, tid}, v{vbase, tid}, vb{vbbase, tid};
+  const int tx = tid & 15, ty = tid >> 4;                // ty in 0..7
+  // lower-triangular problems: row tile i visits i / njc column tiles, so the heavy row tiles
+  // are scheduled FIRST (CTAs are dispatched in blockIdx order) and the light ones fill the tail
+  const int64_t itile = w.sym_lower ? (int64_t)gridDim.y - 1 - blockIdx.y : (int64_t)blockIdx.y;
+  const int64_t i0 = itile * T2;
+  const int64_t jtiles = (M + T2 - 1) / T2;
+
+  for (int t = 0; t < nacc; ++t) acc[t] = 0.0;
+  for (int t = tid; t < pl.n_theta; t += NT2) th[t] = theta[t];
+  for (int idx = tid; idx < T2 * pl.FT; idx += NT2) {
+    int r = idx / pl.FT, c = idx - r * pl.FT;
+    sl[r * pl.S + c] = (i0 + r < N) ? FL[(i0 + r) * pl.FT + c] : 0.0;
+  }
+  if (w.mode == W_GPR)
+    for (int idx = tid; idx < w.R * T2; idx += NT2) {
+      int r = idx / T2, c = idx - r * T2;
+      bi[idx] = (i0 + c < N) ? w.beta[(int64_t)r * N + i0 + c] : 0.0;
+    }
+  if (w.want_dx)
+    for (int idx = tid; idx < T2 * w.xcols; idx += NT2) dxs[idx] = 0.0;
+
+  double dxr[GPS_MAX_DIMS];
+  PrimEval ev[GPS_MAX_PRIMS];
+
+  for (int64_t jt = blockIdx.x; jt < jtiles; jt += w.njc) {
+    const int64_t j0 = jt * T2;
+    if (w.sym_lower && j0 > i0 + T2 - 1) break;
+    __syncthreads();   // previous tile fully consumed (and the prologue's smem writes visible)
+    for (int idx = tid; idx < T2 * pl.FT; idx += NT2) {
+      int r = idx / pl.FT, c = idx - r * pl.FT;
+      sr[r * pl.S + c] = (j0 + r < M) ? FR[(j0 + r) * pl.FT + c] : 0.0;
+    }
+    if (w.mode == W_GPR)
+      for (int idx = tid; idx < w.R * T2; idx += NT2) {
+        int r = idx / T2, c = idx - r * T2;
+        bj[idx] = (j0 + c < M) ? w.beta[(int64_t)r * N + j0 + c] : 0.0;
+      }
+    __syncthreads();
+    for (int a = 0; a < 4; ++a) {
+      const int il = ty + 8 * a;
+      const int64_t gi = i0 + il;
+      const bool rowok = gi < N;
+      if (w.want_dx)
+        for (int d = 0; d < w.xcols; ++d) dxr[d] = 0.0;
+      for (int b = 0; b < 2; ++b) {
+        const int jl = tx + 16 * b;
+        const int64_t gj = j0 + jl;
+        if (!rowok || gj >= M) continue;
+        if (w.sym_lower && gj > gi) continue;
+        double wij;
+        if (w.mode == W_GPR) {
+          double bb = 0.0;
+          for (int r = 0; r < w.R; ++r) bb = fma(bi[r * T2 + il], bj[r * T2 + jl], bb);
+          wij = 0.5 * ((double)w.R * w.W[gi * w.ldw + gj] - bb);
+          if (gi == gj) acc[pl.n_theta] += wij;          // tr W = d nlml / d noise
+        } else {
+          wij = w.W[gi * w.ldw + gj];
+        }
+        if (w.sym_lower && gj != gi) wij *= 2.0;
+        const double* fi = sl + il * pl.S;
+        const double* fj = sr + jl * pl.S;
+        for (int p = 0; p < pl.n_prims; ++p) {
+          const PrimC P = pl.prims[p];
+          ev[p] = prim_eval(P, th, fi + P.feat_off, fj + P.feat_off);
+          v[p] = ev[p].k;
+        }
+        if (pl.n_ops) program_fwd_s(pl, th, v);
+        for (int s = 0; s < nslots; ++s) vb[s] = 0.0;
+        vb[pl.out_slot] = wij;
+        program_bwd_s(pl, th, v, vb, acc);
+        for (int p = 0; p < pl.n_prims; ++p) {
+          const PrimC P = pl.prims[p];
+          const double g = vb[p];
+          const double* t = th + P.theta_off;
+          const double* fip = fi + P.feat_off;
+          const double* fjp = fj + P.feat_off;
+          if (is_stationary(P.type)) {
+            acc[P.theta_off] += g * ev[p].k / t[0];
+            const double G = g * ev[p].dk;               // dObj / d(d2)
+            if (P.ard) {
+              for (int k = 0; k < P.ndims; ++k) {
+                double df = fip[k] - fjp[k];
+                acc[P.theta_off + 1 + k] += G * (-2.0) * df * df / t[1 + k];
+                if (w.want_dx) dxr[pd.dims[p][k]] += 2.0 * G * df / t[1 + k];
+              }
+            } else {
+              acc[P.theta_off + 1] += G * (-2.0) * ev[p].d2 / t[1];
+              if (w.want_dx)
+                for (int k = 0; k < P.ndims; ++k)
+                  dxr[pd.dims[p][k]] += 2.0 * G * (fip[k] - fjp[k]) / t[1];
+            }
+          } else if (P.type == GPS_LINEAR) {
+            for (int k = 0; k < P.ndims; ++k) {
+              acc[P.theta_off + (P.ard ? k : 0)] += g * fip[k] * fjp[k];
+              if (w.want_dx) dxr[pd.dims[p][k]] += g * t[P.ard ? k : 0] * fjp[k];
+            }
+          } else {
+            const int nd = P.ndims;
+            const double kk = ev[p].k, r = ev[p].dk, ls = t[1], per = t[2];
+            acc[P.theta_off] += g * kk / t[0];
+            acc[P.theta_off + 1] += g * kk * r / ls;
+            double dcs = 0.0;   // d(sum cos)/dp
+            for (int k = 0; k < nd; ++k) {
+              double sind = fip[nd + k] * fjp[k] - fip[k] * fjp[nd + k];   // sin(a_i - a_j)
+              dcs += sind * (fip[2 * nd + k] - fjp[2 * nd + k]) / per;
+              if (w.want_dx) dxr[pd.dims[p][k]] += -g * kk * sind * M_PI / (2.0 * per * ls * ls);
+            }
+            acc[P.theta_off + 2] += g * kk * dcs / (4.0 * ls * ls);
+          }
+        }
+      }
+      if (w.want_dx) {
+        // the 16 tx-lanes of a half warp share row il
+        for (int d = 0; d < w.xcols; ++d) {
+          double s = dxr[d];
+          s += __shfl_xor_sync(0xffffffffu, s, 8);
+          s += __shfl_xor_sync(0xffffffffu, s, 4);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          if (tx == 0) dxs[il * w.xcols + d] += s;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // deterministic CTA reduction: thread t sums the NT2 per-thread partials of parameter t,
+  // starting at its own column so that the reads of a warp fall into different banks
+  const int64_t cta = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+  for (int t = tid; t < nacc; t += NT2) {
+    double s = 0.0;
+    for (int k = 0; k < NT2; ++k) s += accb[t * NT2 + ((k + tid) & (NT2 - 1))];
+    part_theta[cta * nacc + t] = s;
+  }
+  if (w.want_dx) {
+    for (int idx = tid; idx < T2 * w.xcols; idx += NT2) {
+      int r = idx / w.xcols;
+      if (i0 + r < N)
+        part_dx[((int64_t)blockIdx.x * N + i0 + r) * w.xcols + (idx - r * w.xcols)] = dxs[idx];
+    }
+  }
+}
+
 // --------------------------------------------------------------------------- fast path
 // One stationary primitive and no composition program (RBF / Matern / Exponential, ARD or not,
 // <= 16 active dimensions) -- the covariance of every GPR / SVGP config in BASELINE.json except
@@ -861,6 +1122,7 @@ void gram_attrs() {
   if (g_gram_attr) return;
   cudaFuncSetAttribute(gram_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(gram_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  cudaFuncSetAttribute(gram_bwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   g_gram_attr = true;
 }
 
@@ -926,7 +1188,12 @@ int gps_gram_bwd_mat(gps_handle* h, const gps_kernel_desc* desc, const double* t
   FR = FL;
   if (X2 && (rc = features(h, pl, pd, theta, *X2, WS_FEAT_R, &FR))) return rc;
   gram_attrs();
-  const int64_t itiles = (N + TILE - 1) / TILE, jtiles = (M + TILE - 1) / TILE;
+  // experimental shared-memory-accumulator interpreter (gram_impl == 2), when its arrays fit
+  const int nslots = plan_nslots(pl);
+  const size_t smem2 = bwd_smem_doubles(pl, nslots, w.mode, w.R, dX ? 1 : 0, (int)X.cols) * sizeof(double);
+  const bool use_smem_acc = h->gram_impl == 2 && smem2 <= 227 * 1024;
+  const int tile = use_smem_acc ? T2 : TILE;
+  const int64_t itiles = (N + tile - 1) / tile, jtiles = (M + tile - 1) / tile;
   int64_t njc = (4 * h->sm_count + itiles - 1) / itiles;
   if (njc < 1) njc = 1;
   if (njc > jtiles) njc = jtiles;
@@ -945,8 +1212,11 @@ int gps_gram_bwd_mat(gps_handle* h, const gps_kernel_desc* desc, const double* t
   }
   size_t smem = (size_t)(pl.n_theta + 2 * TILE * pl.S + (w.mode == W_GPR ? 2 * w.R * TILE : 0) +
                          8 * nacc + (dX ? TILE * X.cols : 0)) * sizeof(double);
-  if (smem > 220 * 1024) return gps_fail(h, -2, "gram_bwd: kernel too large for shared memory");
-  if (!dX && stat_fast(h, pl)) {
+  if (!use_smem_acc && smem > 220 * 1024) return gps_fail(h, -2, "gram_bwd: kernel too large for shared memory");
+  if (use_smem_acc) {
+    gram_bwd_smem_kernel<<<dim3((unsigned)njc, (unsigned)itiles), NT2, smem2, h->stream>>>(
+        pl, pd, nslots, theta, FL, FR, N, M, a, part, pdx);
+  } else if (!dX && stat_fast(h, pl)) {
     const PrimC P = pl.prims[0];
     const dim3 g2((unsigned)njc, (unsigned)itiles);
     if (P.ndims <= 4)

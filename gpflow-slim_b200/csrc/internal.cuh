@@ -50,7 +50,8 @@ struct gps_handle {
   std::string err;
   int gemm_impl = 0;
   int leaf_impl = 0;   // 0 = blocked DMMA leaf, 1 = simple check kernel
-  int gram_impl = 0;   // 0 = register-tiled fast path for single stationary kernels, 1 = interpreter only
+  int gram_impl = 0;   // 0 = register-tiled fast path for single stationary kernels, 1 = interpreter only,
+                       // 2 = experimental shared-memory-accumulator interpreter backward
   int profile = 0;
   void* ws_ptr[WS_COUNT] = {};
   size_t ws_bytes[WS_COUNT] = {};

@@ -112,7 +112,10 @@ int gps_version(void);
  *                          aligned with even leading dimensions, else by cp.async (default);
  *                      1 = plain-FMA check kernel; 2 = always the cp.async DMMA kernel;
  *          "gram_impl" 0 = register-tiled Gram kernels for a single stationary covariance where
- *                          they apply (default), 1 = the generic interpreter kernels only;
+ *                          they apply (default), 1 = the generic interpreter kernels only,
+ *                          2 = EXPERIMENTAL interpreter backward with its accumulators in shared
+ *                          memory (written blind at the end of round 1, not yet run on a GPU;
+ *                          tests/test_gpu_experimental.py holds it to the default path);
  *          "leaf_impl" 0 = blocked DMMA 128x128 Cholesky leaf (default), 1 = scalar check kernel;
  *          "profile"   1 = bracket every GEMM-class launch with CUDA events. */
 int gps_set_option(gps_handle* h, const char* name, int64_t value);

@@ -1,0 +1,101 @@
+"""Kernels written WITHOUT GPU access at the end of round 1 (gpurun budget exhausted) and
+therefore not the default path: they run only when GPSLIM_TEST_EXPERIMENTAL=1, so that the
+regular `pytest -m gpu` stays a statement about validated code.  First thing to run in round 2:
+
+    GPSLIM_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -q -s
+
+gram_impl = 2: interpreter Gram backward with the theta-gradient accumulators / slot values /
+slot adjoints in shared memory ([index][thread] layout) instead of local memory (csrc/gram.cu,
+gram_bwd_smem_kernel).  Must reproduce the default interpreter (gram_impl = 1) to rounding:
+same per-element arithmetic, different summation order."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases
+from util import assert_close, conv
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get('GPSLIM_TEST_EXPERIMENTAL') != '1',
+                                 reason='experimental kernels: set GPSLIM_TEST_EXPERIMENTAL=1')]
+
+
+def _grads(kern, X, X2, W, Ws, impl, want_dx):
+    from gpflowSlim._backend.lib import handle_for
+    h = handle_for(X)
+    h.set_option('gram_impl', impl)
+    try:
+        Xg = X.clone().requires_grad_(want_dx)
+        X2g = X2.clone().requires_grad_(want_dx)
+        val = (kern.K(Xg, X2g) * W).sum() + (kern.K(Xg) * Ws).sum()
+        params = [p.unconstrained_tensor for p in kern.parameters]
+        g = torch.autograd.grad(val, params + ([Xg, X2g] if want_dx else []), allow_unused=True)
+        return [torch.zeros_like(p) if gi is None else gi for gi, p in zip(g, params + [Xg, X2g])]
+    finally:
+        h.set_option('gram_impl', 0)
+
+
+@pytest.mark.parametrize('want_dx', [False, True])
+@pytest.mark.parametrize('n,m', [(75, 41), (33, 97), (257, 130)])
+def test_smem_accumulator_backward_equals_interpreter_on_the_zoo(n, m, want_dx):
+    import gpflowSlim as gpf
+    rng = np.random.default_rng(n + m)
+    X, X2 = conv(rng.standard_normal((n, 3)) * 1.2), conv(rng.standard_normal((m, 3)) * 1.2)
+    W, Ws = conv(rng.standard_normal((n, m))), conv(rng.standard_normal((n, n)))
+    for name, make in cases._kernel_zoo(gpf, 3):
+        kern = make()
+        ref = _grads(kern, X, X2, W, Ws, 1, want_dx)
+        got = _grads(kern, X, X2, W, Ws, 2, want_dx)
+        for i, (a, b) in enumerate(zip(got, ref)):
+            assert_close(a, b, 1e-11, '%s grad %d (n=%d m=%d dx=%s)' % (name, i, n, m, want_dx))
+
+
+def test_smem_accumulator_backward_nkn_gpr(golden):
+    """The NKN config through the fused GPR objective (W_GPR weights formed on the fly)."""
+    import gpflowSlim as gpf
+    from gpflowSlim._backend.lib import handle_for
+    gold = golden('nkn')
+    d, n = 3, 150
+    X, Y = cases.synth_gpr(n, d, seed=3)
+    kern = cases.nkn_c3_kernel(gpf, d)
+    m = gpf.models.GPR(conv(X), conv(Y), kern=kern, name='nkn_gpr')
+    h = handle_for(m.X)
+    h.set_option('gram_impl', 2)
+    try:
+        obj = m.objective
+        gs = torch.autograd.grad(obj, [p.unconstrained_tensor for p in m.parameters])
+    finally:
+        h.set_option('gram_impl', 0)
+    assert_close(obj, gold['objective'], 1e-8, 'objective')
+    for i, g in enumerate(gs):
+        assert_close(g, gold['grad/objective/%d' % i], 1e-8, 'grad %d' % i)
+
+
+def test_smem_accumulator_backward_speed_nkn():
+    """Not an assertion about speed -- prints the two timings for the NKN Gram backward."""
+    import gpflowSlim as gpf
+    from gpflowSlim._backend.lib import handle_for
+    n, d = 4096, 8
+    X, _ = cases.synth_gpr(n, d, seed=0)
+    kern = cases.nkn_c3_kernel(gpf, d)
+    Xc = conv(X)
+    W = conv(np.random.default_rng(0).standard_normal((n, n)))
+    h = handle_for(Xc)
+    for impl in (1, 2):
+        h.set_option('gram_impl', impl)
+        try:
+            params = [p.unconstrained_tensor for p in kern.parameters]
+            for it in range(3):
+                if it == 1:
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                val = (kern.K(Xc) * W).sum()
+                torch.autograd.grad(val, params)
+            e1.record()
+            torch.cuda.synchronize()
+            print('gram_impl=%d: NKN K + backward at N=%d: %.2f ms' % (impl, n, e0.elapsed_time(e1) / 2))
+        finally:
+            h.set_option('gram_impl', 0)

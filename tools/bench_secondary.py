@@ -72,6 +72,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     gpf.settings.device = dev
+    if os.environ.get('GPSLIM_GRAM_IMPL'):      # e.g. 2 = experimental smem-accumulator Gram backward
+        from gpflowSlim._backend import lib as _L
+        _L.handle_for(dev).set_option('gram_impl', int(os.environ['GPSLIM_GRAM_IMPL']))
     lines = []
     if args.what == 'c2':
         kern = gpf.kernels.RBF(8, ARD=True, lengthscales=math.sqrt(8))
