@@ -520,9 +520,9 @@ constexpr int T2 = 32;          // tile edge
 constexpr int NT2 = 128;        // threads per CTA
 
 struct SmemSlots {
-  double* base;                 // [n][NT2]
-  int tid;
-  __device__ __forceinline__ double& operator[](int i) const { return base[i * NT2 + tid]; }
+  double* base;                 // [n][nthreads]
+  int tid, nthreads;
+  __device__ __forceinline__ double& operator[](int i) const { return base[i * nthreads + tid]; }
 };
 
 __device__ __forceinline__ void program_fwd_s(const Plan& pl, const double* __restrict__ th, const SmemSlots& v) {
@@ -590,6 +590,50 @@ __device__ __forceinline__ void program_bwd_s(const Plan& pl, const double* __re
   }
 }
 
+// forward twin: gram_fwd_kernel with the slot values in shared memory ([slot][thread], 256 threads)
+__global__ void __launch_bounds__(GRAM_THREADS)
+gram_fwd_smem_kernel(const Plan pl, const int nslots, const double* __restrict__ theta,
+                     const double* __restrict__ FL, const double* __restrict__ FR, int64_t N, int64_t M,
+                     double diag_add, int sym, int uplo, double* __restrict__ K, int64_t ldk) {
+  extern __shared__ double sm[];
+  double* th = sm;
+  double* sl = th + pl.n_theta;
+  double* sr = sl + TILE * pl.S;
+  double* vbase = sr + TILE * pl.S;                // [nslots][GRAM_THREADS]
+  const int64_t i0 = (int64_t)blockIdx.y * TILE, j0 = (int64_t)blockIdx.x * TILE;
+  if (sym && uplo && j0 > i0 + TILE - 1) return;
+  const int tid = threadIdx.x;
+  const SmemSlots v{vbase, tid, GRAM_THREADS};
+  for (int t = tid; t < pl.n_theta; t += GRAM_THREADS) th[t] = theta[t];
+  for (int idx = tid; idx < TILE * pl.FT; idx += GRAM_THREADS) {
+    int r = idx / pl.FT, c = idx - r * pl.FT;
+    sl[r * pl.S + c] = (i0 + r < N) ? FL[(i0 + r) * pl.FT + c] : 0.0;
+    sr[r * pl.S + c] = (j0 + r < M) ? FR[(j0 + r) * pl.FT + c] : 0.0;
+  }
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  for (int a = 0; a < 4; ++a) {
+    const int il = ty + 16 * a;
+    const int64_t gi = i0 + il;
+    if (gi >= N) continue;
+    for (int b = 0; b < 4; ++b) {
+      const int jl = tx + 16 * b;
+      const int64_t gj = j0 + jl;
+      if (gj >= M) continue;
+      if (sym && uplo && gj > gi) continue;
+      for (int p = 0; p < pl.n_prims; ++p) {
+        const PrimC P = pl.prims[p];
+        v[p] = prim_eval(P, th, sl + il * pl.S + P.feat_off, sr + jl * pl.S + P.feat_off).k;
+      }
+      program_fwd_s(pl, th, v);
+      double out = v[pl.out_slot];
+      if (sym && gi == gj) out += diag_add;
+      K[gi * ldk + gj] = out;
+    }
+  }
+  (void)nslots;
+}
+
 // number of slots a program touches (primitives + op results)
 int plan_nslots(const Plan& pl) {
   int n = pl.n_prims;
@@ -623,7 +667,7 @@ gram_bwd_smem_kernel(const Plan pl, const PlanDims pd, const int nslots, const d
   double* accb = dxs + (w.want_dx ? T2 * w.xcols : 0);   // [nacc][NT2]
   double* vbase = accb + nacc * NT2;                     // [nslots][NT2]
   double* vbbase = vbase + nslots * NT2;                 // [nslots][NT2]
-  const SmemSlots acc{accb, tid}, v{vbase, tid}, vb{vbbase, tid};
+  const SmemSlots acc{accb, tid, NT2}, v{vbase, tid, NT2}, vb{vbbase, tid, NT2};
   const int tx = tid & 15, ty = tid >> 4;                // ty in 0..7
   // lower-triangular problems: row tile i visits i / njc column tiles, so the heavy row tiles
   // are scheduled FIRST (CTAs are dispatched in blockIdx order) and the light ones fill the tail
@@ -1123,6 +1167,7 @@ void gram_attrs() {
   cudaFuncSetAttribute(gram_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(gram_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(gram_bwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(gram_fwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   g_gram_attr = true;
 }
 
@@ -1155,6 +1200,15 @@ int gps_gram_fwd_mat(gps_handle* h, const gps_kernel_desc* desc, const double* t
       gram_fwd_stat_kernel<8><<<grid, GRAM_THREADS, 0, h->stream>>>(P.type, P.ndims, pl.FT, theta, FL, FR, N, M, diag_add, sym, up, K.p, K.ld);
     else
       gram_fwd_stat_kernel<16><<<grid, GRAM_THREADS, 0, h->stream>>>(P.type, P.ndims, pl.FT, theta, FL, FR, N, M, diag_add, sym, up, K.p, K.ld);
+    GPS_LAUNCH_CHECK(h);
+    return 0;
+  }
+  const int nslots = plan_nslots(pl);
+  const size_t smem2 = smem + (size_t)nslots * GRAM_THREADS * sizeof(double);
+  if (h->gram_impl == 2 && smem2 <= 227 * 1024) {
+    // experimental: slot values in shared memory instead of local memory (see gram_bwd_smem_kernel)
+    gram_fwd_smem_kernel<<<grid, GRAM_THREADS, smem2, h->stream>>>(pl, nslots, theta, FL, FR, N, M, diag_add,
+                                                                   X2 ? 0 : 1, X2 ? 0 : uplo, K.p, K.ld);
     GPS_LAUNCH_CHECK(h);
     return 0;
   }

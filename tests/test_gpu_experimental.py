@@ -4,9 +4,10 @@ regular `pytest -m gpu` stays a statement about validated code.  First thing to 
 
     GPSLIM_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -q -s
 
-gram_impl = 2: interpreter Gram backward with the theta-gradient accumulators / slot values /
-slot adjoints in shared memory ([index][thread] layout) instead of local memory (csrc/gram.cu,
-gram_bwd_smem_kernel).  Must reproduce the default interpreter (gram_impl = 1) to rounding:
+gram_impl = 2: interpreter Gram forward / backward with the slot values, slot adjoints and
+theta-gradient accumulators in shared memory ([index][thread] layout) instead of local memory
+(csrc/gram.cu: gram_fwd_smem_kernel, gram_bwd_smem_kernel).  Their source text already passes
+the CPU emulation test (tests/test_gram_kernel_emulation_cpu.py).  Must reproduce the default interpreter (gram_impl = 1) to rounding:
 same per-element arithmetic, different summation order."""
 import os
 
@@ -32,7 +33,8 @@ def _grads(kern, X, X2, W, Ws, impl, want_dx):
         val = (kern.K(Xg, X2g) * W).sum() + (kern.K(Xg) * Ws).sum()
         params = [p.unconstrained_tensor for p in kern.parameters]
         g = torch.autograd.grad(val, params + ([Xg, X2g] if want_dx else []), allow_unused=True)
-        return [torch.zeros_like(p) if gi is None else gi for gi, p in zip(g, params + [Xg, X2g])]
+        return [val.detach()] + [torch.zeros_like(p) if gi is None else gi
+                                 for gi, p in zip(g, params + [Xg, X2g])]
     finally:
         h.set_option('gram_impl', 0)
 

@@ -66,12 +66,12 @@ def _gpf():
     return gpf
 
 
-def emu_fwd(lib, prog, theta, X, X2=None, diag_add=0.0, uplo=0):
+def emu_fwd(lib, prog, theta, X, X2=None, diag_add=0.0, uplo=0, impl=1):
     N, M = X.shape[0], (X.shape[0] if X2 is None else X2.shape[0])
     K = np.full((N, M), np.nan)
     rc = lib.emu_gram_fwd(ctypes.byref(prog.desc), _ptr(theta), _ptr(X), ctypes.c_int64(N),
                           ctypes.c_int64(X.shape[1]), _ptr(X2), ctypes.c_int64(M), ctypes.c_double(diag_add),
-                          ctypes.c_int(uplo), _ptr(K))
+                          ctypes.c_int(uplo), ctypes.c_int(impl), _ptr(K))
     assert rc == 0
     return K
 
@@ -121,19 +121,17 @@ def test_interpreter_kernels_on_the_kernel_zoo(emu, impl):
         theta = prog.theta('cpu').detach().numpy().copy()
         # cross-covariance: forward, dtheta, dX
         Kref, (gth, gx, gx2) = _torch_reference(prog, theta, X, X2, W)
-        if impl == 1:
-            assert rel(emu_fwd(emu, prog, theta, X, X2), Kref) < 1e-12, name
+        assert rel(emu_fwd(emu, prog, theta, X, X2, impl=impl), Kref) < 1e-12, name
         dth, dX = emu_bwd(emu, prog, theta, X, X2, W, impl, want_dx=True)
         assert rel(dth[:-1], gth) < 1e-10, (name, 'dtheta')
         assert rel(dX, gx) < 1e-10, (name, 'dX')
         # symmetric problem with a dense (symmetrised) weight: dX gets the factor 2
         Wsym = 0.5 * (Ws + Ws.T)
         Kref, (gth, gx) = _torch_reference(prog, theta, X, None, Wsym)
-        if impl == 1:
-            Klow = emu_fwd(emu, prog, theta, X, None, diag_add=0.3, uplo=1)
-            il = np.tril_indices(75)
-            assert rel(Klow[il], (Kref + 0.3 * np.eye(75))[il]) < 1e-12, name
-            assert np.isnan(Klow[np.triu_indices(75, 1)]).all(), 'upper triangle must stay untouched'
+        Klow = emu_fwd(emu, prog, theta, X, None, diag_add=0.3, uplo=1, impl=impl)
+        il = np.tril_indices(75)
+        assert rel(Klow[il], (Kref + 0.3 * np.eye(75))[il]) < 1e-12, name
+        assert np.isnan(Klow[np.triu_indices(75, 1)]).all(), 'upper triangle must stay untouched'
         dth, dX = emu_bwd(emu, prog, theta, X, None, Wsym, impl, want_dx=True, njc=1)
         # Matern-type diagonals carry sqrt(d2 + 1e-12) with d2 = +-1e-16 of rounding noise in BOTH
         # implementations (kernels.py:424-426): 1e-8 is the floor there, as in the GPU tests
@@ -157,6 +155,8 @@ def test_interpreter_backward_nkn_fused_gpr_weights(emu, impl):
     beta = rng.standard_normal((R, n))
     Wfull = 0.5 * (R * Kinv - beta.T @ beta)
     _, (gth, _) = _torch_reference(prog, theta, X, None, Wfull)
+    Kref, _ = _torch_reference(prog, theta, X, None, Wfull)
+    assert rel(emu_fwd(emu, prog, theta, X, None, impl=impl), Kref) < 1e-12
     Klow = np.tril(Kinv) + np.triu(np.full((n, n), np.nan), 1)       # upper triangle must not be read
     dth, _ = emu_bwd(emu, prog, theta, X, None, Klow, impl, mode=1, beta=beta, sym_lower=1, njc=2)
     assert rel(dth[:-1], gth) < 1e-10
