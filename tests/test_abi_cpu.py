@@ -65,3 +65,40 @@ def test_first_handle_request_does_not_deadlock():
             '    print("RAISED")\n') % os.path.join(ROOT, 'gpflow-slim_b200')
     out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120)
     assert ('RAISED' in out.stdout) or ('HANDLE' in out.stdout), out.stderr[-2000:]
+
+
+def test_packed_view_equals_fieldwise_dltensor():
+    """lib.view() fills the DLTensor + shape/stride words with one struct.pack_into; the result
+    must be byte-identical to a DLTensor built field by field with ctypes (what the C side reads:
+    include/gpslim_b200.h, DLPack v0.8 layout)."""
+    from gpflowSlim._backend import lib
+    base = torch.arange(12 * 9, dtype=torch.float64).reshape(12, 9)
+    cases_ = [base, base[2:7, 1:6], base[:, :1], base[3], base[0:1], torch.zeros(0, 4, dtype=torch.float64),
+              torch.tensor(3.5, dtype=torch.float64), torch.arange(5, dtype=torch.int64)]
+    for t in cases_:
+        v = lib.view(t)
+        tt = v.tensor
+        nd = tt.dim()
+        shape = (ctypes.c_int64 * max(nd, 1))(*tt.shape)
+        strides = (ctypes.c_int64 * max(nd, 1))(*tt.stride())
+        want = lib.DLTensor(ctypes.c_void_p(tt.data_ptr()), lib.DLDevice(1, 0), nd,
+                            lib.DLDataType(2 if tt.dtype == torch.float64 else 0, 64, 1), shape, strides, 0)
+        got = v.dl
+        assert (got.data or 0) == (want.data or 0)          # None for an empty tensor's null pointer
+        assert (got.device.device_type, got.device.device_id) == (1, 0)
+        assert got.ndim == want.ndim == nd
+        assert (got.dtype.code, got.dtype.bits, got.dtype.lanes) == (want.dtype.code, 64, 1)
+        assert got.byte_offset == 0
+        assert [got.shape[i] for i in range(nd)] == list(tt.shape)
+        assert [got.strides[i] for i in range(nd)] == list(tt.stride())
+        # the pointers point INTO the view's own buffer, which the view keeps alive
+        a = ctypes.addressof(v.buf)
+        assert ctypes.cast(got.shape, ctypes.c_void_p).value == a + 48
+        assert ctypes.cast(got.strides, ctypes.c_void_p).value == a + 64
+        raw = bytes(v.buf)[:24] + bytes(v.buf)[40:48]
+        ref_raw = bytes(want)[:24] + bytes(want)[40:48]
+        assert raw == ref_raw
+    with pytest.raises(TypeError):
+        lib.view(torch.zeros(2, 2, dtype=torch.float32))
+    with pytest.raises(ValueError):
+        lib.view(torch.zeros(4, 4, dtype=torch.float64).t())
