@@ -53,12 +53,25 @@ def transpose(A):
     return out
 
 
+_GRAPH_CAPTURE = [False]
+
+
+def set_graph_capture(flag):
+    """While a CUDA graph is being captured (training.GraphedStep) nothing may synchronise the
+    stream: the Cholesky skips the device->host read of its `info` flag (a matrix that is not
+    positive definite then shows up as NaNs instead of a CholeskyError), and the cached L^-T
+    factors are dropped so that the graph records their kernels."""
+    _GRAPH_CAPTURE[0] = bool(flag)
+    _U_CACHE.clear()
+
+
 def potrf(K, zero_upper=True, check=True):
     """Returns the lower Cholesky factor of K (K is not modified)."""
     L = _prep(K).clone()
     h = handle_for(L)
     info = ctypes.c_int(0)
     vl = view(L)
+    check = check and not _GRAPH_CAPTURE[0]
     h.check(h.lib.gps_potrf(h.ptr, vl.ref, int(zero_upper), ctypes.byref(info) if check else None))
     return L
 

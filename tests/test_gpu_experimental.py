@@ -101,3 +101,49 @@ def test_smem_accumulator_backward_speed_nkn():
             print('gram_impl=%d: NKN K + backward at N=%d: %.2f ms' % (impl, n, e0.elapsed_time(e1) / 2))
         finally:
             h.set_option('gram_impl', 0)
+
+
+def test_graphed_svgp_step_equals_eager_steps():
+    """training.GraphedStep (CUDA-graph replay of objective + gradients + Adam) against the same
+    steps taken eagerly with AdamOptimizer, five minibatches; then the two step times."""
+    import gpflowSlim as gpf
+    n, d, m, batch = 20000, 8, 256, 2048
+    X, Y, Z = cases.synth_svgp(n, d, m, seed=0)
+    Xd, Yd = conv(X), conv(Y)
+
+    def make():
+        kern = gpf.kernels.RBF(d, ARD=True, lengthscales=2.0)
+        return gpf.models.SVGP(Xd[:batch], Yd[:batch], kern, gpf.likelihoods.Gaussian(var=0.1), Z=Z.copy(),
+                               num_data=n)
+    batches = [(Xd[i * batch:(i + 1) * batch], Yd[i * batch:(i + 1) * batch]) for i in range(5)]
+    eager = make()
+    opt = gpf.training.AdamOptimizer(1e-3)
+    objs_e = []
+    for Xb, Yb in batches:
+        eager.X, eager.Y = Xb, Yb
+        objs_e.append(float(opt.minimize(eager)))
+    graphed = make()
+    step = gpf.training.GraphedStep(graphed, batches[0][0], batches[0][1], learning_rate=1e-3)
+    objs_g = [float(step(Xb, Yb)) for Xb, Yb in batches]
+    np.testing.assert_allclose(objs_g, objs_e, rtol=1e-9)
+    for a, b in zip(graphed.trainable_tensors, eager.trainable_tensors):
+        assert_close(a, b, 1e-9, 'parameters after 5 steps')
+
+    def timed(fn, reps=20):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    Xb, Yb = batches[0]
+
+    def eager_step():
+        eager.X, eager.Y = Xb, Yb
+        opt.minimize(eager)
+    print('SVGP step (M=%d, B=%d): eager %.3f ms, graphed %.3f ms' % (m, batch, timed(eager_step),
+                                                                       timed(lambda: step(Xb, Yb))))
+
