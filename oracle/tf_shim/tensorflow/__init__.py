@@ -218,8 +218,11 @@ def squeeze(x, axis=None, name=None):
 
 
 def stack(values, axis=0, name=None):
-    if all(not isinstance(v, torch.Tensor) or v.dtype in (torch.int64, torch.int32)
-           for v in values):
+    def _int_scalar(v):
+        if isinstance(v, torch.Tensor):
+            return v.dim() == 0 and v.dtype in (torch.int64, torch.int32)
+        return isinstance(v, (int, np.integer))
+    if all(_int_scalar(v) for v in values):
         return torch.tensor([int(v) for v in values], dtype=torch.int64)  # shape vectors
     return torch.stack([_t(v) for v in values], dim=int(axis))
 
