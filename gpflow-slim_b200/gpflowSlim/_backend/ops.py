@@ -115,6 +115,36 @@ def row_sumsq(A):
 
 
 # ------------------------------------------------------------------------- autograd Functions
+# EXPERIMENTAL switch (off until seen green on a GPU; the CPU tests run both settings): let the
+# adjoint of a triangular-aware product skip the zero tiles too.  With C = tri_a(A) tri_b(B)^T:
+#   dA = G tri_b(B)      -> NT product with B^T, which is triangular the other way round;
+#   dB = tri_b(G^T tri_a(A)) -> only the wanted triangle is computed (lower-output GEMM; an upper
+#                           triangle is computed as the lower triangle of the transpose).
+# For the SVGP bound with a full q_sqrt (conditionals.py:109-111) this halves two of the four
+# N M^2 products of the backward pass.
+TRI_AWARE_ADJOINTS = [False]
+_FLIP = {TRI_NONE: TRI_NONE, TRI_LOWER: TRI_UPPER, TRI_UPPER: TRI_LOWER}
+
+
+def _matmul_nt_backward_tri(ctx, A, B, G, a_tri, b_tri):
+    dA = dB = None
+    if ctx.needs_input_grad[0]:
+        dA = gemm_nt(G, transpose(B), b_tri=_FLIP[b_tri])
+        if a_tri == TRI_LOWER:
+            dA = torch.tril(dA)
+        elif a_tri == TRI_UPPER:
+            dA = torch.triu(dA)
+    if ctx.needs_input_grad[1]:
+        if b_tri == TRI_LOWER:
+            dB = gemm_nt(transpose(G), transpose(A), b_tri=_FLIP[a_tri], c_uplo=1)
+        elif b_tri == TRI_UPPER:
+            # upper triangle of G^T A  ==  transpose of the lower triangle of A^T G
+            dB = transpose(gemm_nt(transpose(A), transpose(G), a_tri=_FLIP[a_tri], c_uplo=1))
+        else:
+            dB = gemm_nt(transpose(G), transpose(A), b_tri=_FLIP[a_tri])
+    return dA, dB, None, None
+
+
 class _MatmulNT(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A, B, a_tri, b_tri):
@@ -129,6 +159,8 @@ class _MatmulNT(torch.autograd.Function):
         a_tri, b_tri = ctx.tri
         G = _prep(G)
         dA = dB = None
+        if TRI_AWARE_ADJOINTS[0] and (a_tri != TRI_NONE or b_tri != TRI_NONE):
+            return _matmul_nt_backward_tri(ctx, A, B, G, a_tri, b_tri)
         if ctx.needs_input_grad[0]:
             # dA = G B   ==  G (B^T)^T
             dA = gemm_nt(G, transpose(B))

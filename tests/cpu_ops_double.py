@@ -201,11 +201,22 @@ NAMES = ['gemm_nt', 'transpose', 'potrf', 'trsm_rlt_', 'tri_inv_t', 'row_sumsq',
          'kdiag', 'gpr_loglik', 'gpr_predict']
 
 
-def install(monkeypatch):
+# 'raw' level: only the entry points that touch the library directly are replaced; the package's
+# own torch.autograd Functions (_MatmulNT, _Cholesky, _TrsmRLT, _TriInvT, _Transpose: the
+# HAND-WRITTEN adjoints of ops.py) stay in place and run on top of the CPU gemm / transpose /
+# potrf / trsm / inverse stand-ins -- so their backward formulas, and the triangular-structure
+# flags they pass, are exercised on the CPU as well.
+RAW_NAMES = ['gemm_nt', 'transpose', 'potrf', 'trsm_rlt_', 'tri_inv_t', 'row_sumsq', 'gram', 'kdiag',
+             'gpr_loglik', 'gpr_predict']
+
+
+def install(monkeypatch, level='ops'):
     """Swap the stand-ins into gpflowSlim._backend.ops for the duration of one test."""
     from gpflowSlim._backend import ops
     g = globals()
-    for name in NAMES:
+    for name in (NAMES if level == 'ops' else RAW_NAMES):
         assert hasattr(ops, name), name
         monkeypatch.setattr(ops, name, g[name])
+    if level != 'ops':
+        ops._U_CACHE.clear()
     return ops

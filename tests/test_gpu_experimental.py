@@ -147,3 +147,19 @@ def test_graphed_svgp_step_equals_eager_steps():
     print('SVGP step (M=%d, B=%d): eager %.3f ms, graphed %.3f ms' % (m, batch, timed(eager_step),
                                                                        timed(lambda: step(Xb, Yb))))
 
+
+@pytest.mark.parametrize('name', ['svgp_white_full', 'svgp_nonwhite_full', 'sgpr', 'functions'])
+def test_tri_aware_adjoints_match_reference_golden(golden, name, monkeypatch):
+    """ops.TRI_AWARE_ADJOINTS: the adjoint of a triangular-aware product skips the zero tiles as
+    well (new flag combinations of the DMMA GEMM: b_tri + lower-only output, flipped a_tri).  The
+    CPU double already holds it to these goldens; this is the same check on the real kernels."""
+    import gpflowSlim as gpf
+    from gpflowSlim._backend import ops
+    from util import relerr
+    monkeypatch.setattr(ops, 'TRI_AWARE_ADJOINTS', [True])
+    gold = golden(name)
+    res = cases.run_case(gpf, name, conv)
+    for key in sorted(gold):
+        e = relerr(res[key], gold[key])
+        assert e < (1e-12 if key.startswith('param/') else 1e-8), '%s:%s %.3e' % (name, key, e)
+
