@@ -28,6 +28,11 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(x)
+#define __shared__ static              /* static __shared__ arrays: one per block == one per process here */
+#define __align__(n) __attribute__((aligned(n)))
+
+struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
 struct EmuDim3 { unsigned x = 1, y = 1, z = 1; };
 static thread_local EmuDim3 threadIdx, blockIdx;

@@ -3,7 +3,8 @@ gram_fwd_kernel, gram_bwd_kernel and the experimental gram_bwd_smem_kernel) exec
 and held to the oracle -- a check of the kernels' indexing, masking, program interpreter and
 reductions that needs no GPU.
 
-How: the region of gram.cu between `#include "internal.cuh"` and the fast-path marker is copied
+How: the region of gram.cu between `#include "internal.cuh"` and the first host launch function
+(all kernels: interpreter, experimental shared-memory variants, register-tiled fast path, Kdiag) is copied
 verbatim into a host translation unit between tests/emu/harness_prelude.h (CUDA keywords defined
 away, threadIdx / blockIdx as thread-locals, one std::thread per CUDA thread, __syncthreads and
 warp shuffles as barriers) and tests/emu/harness_driver.inc (launch loops + the fixed-order
@@ -36,7 +37,7 @@ GRAM_CU = os.path.join(ROOT, 'gpflow-slim_b200', 'csrc', 'gram.cu')
 def emu(tmp_path_factory):
     src = open(GRAM_CU).read()
     start = src.index('#include "internal.cuh"') + len('#include "internal.cuh"')
-    end = src.index('// --------------------------------------------------------------------------- fast path')
+    end = src.index('int features(gps_handle* h')          # everything up to the host launch code
     region = src[start:end]
     region, n1 = re.subn(r'extern __shared__ double sm\[\];', 'double* sm = emu_smem;', region)
     region, n2 = re.subn(r'__syncthreads\(\)', 'emu_barrier()', region)
@@ -178,3 +179,75 @@ def test_smem_variant_fits_the_c3_program():
     nslots = last.dst + (last.n if last.op in (4, 5) else 1)
     doubles = d.n_theta + 2 * 32 * S + 2 * 1 * 32 + (d.n_theta + 1) * 128 + 2 * nslots * 128
     assert doubles * 8 <= 227 * 1024, doubles * 8
+
+
+def emu_kdiag(lib, prog, theta, X, w=None, want_dx=False):
+    N = X.shape[0]
+    out = np.full(N, np.nan)
+    dth = np.full(prog.n_theta, np.nan)
+    dX = np.full(X.shape, np.nan) if want_dx else None
+    rc = lib.emu_kdiag(ctypes.byref(prog.desc), _ptr(theta), _ptr(X), ctypes.c_int64(N),
+                       ctypes.c_int64(X.shape[1]), _ptr(w), _ptr(out), _ptr(dth), _ptr(dX))
+    assert rc == 0
+    return out, dth, dX
+
+
+def test_kdiag_kernel_on_the_kernel_zoo(emu):
+    gpf = _gpf()
+    rng = np.random.default_rng(9)
+    X = rng.standard_normal((300, 3)) * 1.2                # two blocks of 256 threads, ragged
+    w = rng.standard_normal(300)
+    zoo = cases._kernel_zoo(gpf, 3) + [('nkn', lambda: cases.nkn_c3_kernel(gpf, 3))]
+    for name, make in zoo:
+        prog = make().program()
+        theta = prog.theta('cpu').detach().numpy().copy()
+        th = torch.tensor(theta, requires_grad=True)
+        Xt = torch.tensor(X, requires_grad=True)
+        kd = cpu_ops_double._kdiag_desc(prog, th, Xt)
+        g = torch.autograd.grad((kd * torch.tensor(w)).sum(), [th, Xt], allow_unused=True)
+        gth = np.zeros_like(theta) if g[0] is None else g[0].numpy()
+        gx = np.zeros_like(X) if g[1] is None else g[1].numpy()
+        out, _, _ = emu_kdiag(emu, prog, theta, X)
+        assert rel(out, kd.detach().numpy()) < 1e-13, name
+        _, dth, dX = emu_kdiag(emu, prog, theta, X, w=w, want_dx=True)
+        assert rel(dth, gth) < 1e-11, (name, 'dtheta')
+        assert np.abs(dX - gx).max() <= 1e-11 * max(np.abs(gx).max(), 1.0), (name, 'dX')
+
+
+@pytest.mark.parametrize('cls,d,ard', [('RBF', 1, False), ('RBF', 8, True), ('Matern32', 3, True),
+                                       ('Matern52', 11, True), ('Exponential', 5, False),
+                                       ('Matern12', 16, True)])
+def test_fast_path_kernels_equal_interpreter_and_oracle(emu, cls, d, ard):
+    """gram_fwd_stat_kernel<D> / gram_bwd_stat_kernel<D> (the kernels of every BASELINE GPR / SVGP
+    config except the NKN one), all three template widths, dense and fused-GPR weight modes."""
+    gpf = _gpf()
+    rng = np.random.default_rng(d * 7 + ard)
+    n, m, R = 150, 70, 2
+    X, X2 = rng.standard_normal((n, d)), rng.standard_normal((m, d))
+    ls = (0.8 + 0.1 * np.arange(d)) * np.sqrt(d) if ard else 1.1 * np.sqrt(d)
+    prog = getattr(gpf.kernels, cls)(d, variance=1.3, lengthscales=ls, ARD=ard).program()
+    theta = prog.theta('cpu').detach().numpy().copy()
+    W = rng.standard_normal((n, m))
+    Kref, (gth, _, _) = _torch_reference(prog, theta, X, X2, W)
+    assert rel(emu_fwd(emu, prog, theta, X, X2, impl=0), Kref) < 1e-12
+    dth, _ = emu_bwd(emu, prog, theta, X, X2, W, 0)
+    assert rel(dth[:-1], gth) < 1e-10
+    # symmetric, lower triangle only, + diag_add
+    Ksym, _ = _torch_reference(prog, theta, X, None, np.zeros((n, n)))
+    Klow = emu_fwd(emu, prog, theta, X, None, diag_add=0.2, uplo=1, impl=0)
+    il = np.tril_indices(n)
+    # sqrt(d2 + 1e-12) with d2 = +-1e-16 of rounding noise on the diagonal of the Matern family
+    assert rel(Klow[il], (Ksym + 0.2 * np.eye(n))[il]) < (1e-12 if cls == 'RBF' else 2e-9)
+    assert np.isnan(Klow[np.triu_indices(n, 1)]).all()
+    # fused-GPR weights from the lower triangle of K^-1
+    A = rng.standard_normal((n, n))
+    Kinv = A @ A.T / n + np.eye(n)
+    beta = rng.standard_normal((R, n))
+    Wfull = 0.5 * (R * Kinv - beta.T @ beta)
+    _, (gth, _) = _torch_reference(prog, theta, X, None, Wfull)
+    Kl = np.tril(Kinv) + np.triu(np.full((n, n), np.nan), 1)
+    dth, _ = emu_bwd(emu, prog, theta, X, None, Kl, 0, mode=1, beta=beta, sym_lower=1, njc=2)
+    tol = 1e-10 if cls == 'RBF' else 1e-8          # sqrt(d2 + 1e-12) noise on Matern-type diagonals
+    assert rel(dth[:-1], gth) < tol
+    assert abs(dth[-1] - np.trace(Wfull)) < 1e-10 * abs(np.trace(Wfull))
+
