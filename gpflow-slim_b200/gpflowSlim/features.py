@@ -6,7 +6,7 @@ import torch
 
 from . import conditionals
 from ._backend import ops as _ops
-from .params import Parameter
+from .params import Parameter, param_value
 
 
 class InducingFeature(object):
@@ -27,9 +27,7 @@ class InducingPoints(InducingFeature):
         super().__init__()
         self._Z = Parameter(Z, name='Z')
 
-    @property
-    def Z(self):
-        return self._Z.value
+    Z = param_value('Z')
 
     def __len__(self):
         return self.Z.shape[0]
@@ -56,9 +54,7 @@ class Multiscale(InducingPoints):
         if tuple(self.Z.shape) != tuple(np.shape(scales)):
             raise ValueError('Input locations `Z` and `scales` must have the same shape.')
 
-    @property
-    def scales(self):
-        return self._scales.value
+    scales = param_value('scales')
 
     def _cust_square_dist(self, A, B, sc):
         """sum_d ((a_d - b_d) / sc_d)^2 with per-pair scales sc [N, M, D] (or broadcastable)."""

@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 from . import densities, transforms
-from .params import Parameter
+from .params import Parameter, Parameterized, param_value
 from .quadrature import hermgauss
 
 
@@ -16,7 +16,7 @@ def _const(a, like):
     return torch.as_tensor(a, dtype=like.dtype, device=like.device)
 
 
-class Likelihood(object):
+class Likelihood(Parameterized):
     def __init__(self, name=None):
         self.name = name or type(self).__name__
         self.num_gauss_hermite_points = 20
@@ -67,15 +67,13 @@ class Likelihood(object):
 
 
 class Gaussian(Likelihood):
+    """y = f + N(0, variance): every expectation in closed form (:158-188); the likelihood of
+    the GPR / SGPR / SVGP hot path."""
+    variance = param_value('variance')
+
     def __init__(self, var=1.0, min_var=None):
         super().__init__()
-        trans = transforms.positive if min_var is None else transforms.Log1pe(min_var)
-        self._variance = Parameter(var, transform=trans, name='variance')
-        self._parameters = self._parameters + [self._variance]
-
-    @property
-    def variance(self):
-        return self._variance.value
+        self._param('variance', var, transforms.positive if min_var is None else transforms.Log1pe(min_var))
 
     def logp(self, F, Y):
         return densities.gaussian(F, Y, self.variance)
@@ -93,73 +91,154 @@ class Gaussian(Likelihood):
         return densities.gaussian(Fmu, Y, Fvar + self.variance)
 
     def variational_expectations(self, Fmu, Fvar, Y):
-        """likelihoods.py:186-188."""
-        return -0.5 * np.log(2 * np.pi) - 0.5 * torch.log(self.variance) \
-            - 0.5 * ((Y - Fmu) ** 2 + Fvar) / self.variance
+        s2 = self.variance
+        return -0.5 * np.log(2 * np.pi) - 0.5 * torch.log(s2) - 0.5 * ((Y - Fmu) ** 2 + Fvar) / s2
 
 
-def _is_exp(fn):
-    return fn is torch.exp
+class _LinkLikelihood(Likelihood):
+    """Likelihoods of the form p(y | rate), rate = invlink(f).  A subclass states three rules in
+    terms of the rate -- `_logdensity(rate, Y)`, `_mean(rate)`, `_var(rate)` -- and, optionally,
+    `_varexp_exp(Fmu, Fvar, Y)`: the closed-form variational expectation that exists when the
+    link is exp (used only then; every other case falls back to Gauss-Hermite quadrature)."""
+    _varexp_exp = None
+
+    def __init__(self, invlink):
+        super().__init__()
+        self.invlink = invlink
+
+    def logp(self, F, Y):
+        return self._logdensity(self.invlink(F), Y)
+
+    def conditional_mean(self, F):
+        return self._mean(self.invlink(F))
+
+    def conditional_variance(self, F):
+        return self._var(self.invlink(F))
+
+    def variational_expectations(self, Fmu, Fvar, Y):
+        if self._varexp_exp is not None and self.invlink is torch.exp:
+            return self._varexp_exp(Fmu, Fvar, Y)
+        return Likelihood.variational_expectations(self, Fmu, Fvar, Y)
 
 
-class Poisson(Likelihood):
-    """p(y | f) = Poisson(y | invlink(f) binsize)  (:190-222)."""
+class Poisson(_LinkLikelihood):
+    """Counts in bins of width `binsize`: y ~ Poisson(invlink(f) binsize)  (:190-222)."""
 
     def __init__(self, invlink=torch.exp, binsize=1.0):
-        super().__init__()
-        self.invlink = invlink
+        super().__init__(invlink)
         self.binsize = float(binsize)
 
-    def logp(self, F, Y):
-        return densities.poisson(self.invlink(F) * self.binsize, Y)
+    def _logdensity(self, rate, Y):
+        return densities.poisson(rate * self.binsize, Y)
 
-    def conditional_variance(self, F):
-        return self.invlink(F) * self.binsize
+    def _mean(self, rate):
+        return rate * self.binsize
 
-    def conditional_mean(self, F):
-        return self.invlink(F) * self.binsize
+    _var = _mean
 
-    def variational_expectations(self, Fmu, Fvar, Y):
-        if _is_exp(self.invlink):
-            return Y * Fmu - torch.exp(Fmu + Fvar / 2) * self.binsize - torch.lgamma(Y + 1) \
-                + Y * float(np.log(self.binsize))
-        return super().variational_expectations(Fmu, Fvar, Y)
+    def _varexp_exp(self, Fmu, Fvar, Y):
+        return Y * Fmu - torch.exp(Fmu + Fvar / 2) * self.binsize - torch.lgamma(Y + 1) \
+            + Y * float(np.log(self.binsize))
 
 
-class Exponential(Likelihood):
-    """(:224-241)."""
+class Exponential(_LinkLikelihood):
+    """y ~ Exponential with mean invlink(f)  (:224-241)."""
 
     def __init__(self, invlink=torch.exp):
-        super().__init__()
-        self.invlink = invlink
+        super().__init__(invlink)
 
-    def logp(self, F, Y):
-        return densities.exponential(self.invlink(F), Y)
+    def _logdensity(self, rate, Y):
+        return densities.exponential(rate, Y)
 
-    def conditional_mean(self, F):
-        return self.invlink(F)
+    def _mean(self, rate):
+        return rate
 
-    def conditional_variance(self, F):
-        return self.invlink(F) ** 2
+    def _var(self, rate):
+        return rate ** 2
 
-    def variational_expectations(self, Fmu, Fvar, Y):
-        if _is_exp(self.invlink):
-            return -torch.exp(-Fmu + Fvar / 2) * Y - Fmu
-        return super().variational_expectations(Fmu, Fvar, Y)
+    def _varexp_exp(self, Fmu, Fvar, Y):
+        return -torch.exp(-Fmu + Fvar / 2) * Y - Fmu
+
+
+class Gamma(_LinkLikelihood):
+    """y ~ Gamma(shape, scale = invlink(f))  (:300-332)."""
+    shape = param_value('shape')
+
+    def __init__(self, invlink=torch.exp):
+        super().__init__(invlink)
+        self._param('shape', 1.0, transforms.positive)
+
+    def _logdensity(self, rate, Y):
+        return densities.gamma(self.shape, rate, Y)
+
+    def _mean(self, rate):
+        return self.shape * rate
+
+    def _var(self, rate):
+        return self.shape * rate ** 2
+
+    def _varexp_exp(self, Fmu, Fvar, Y):
+        k = self.shape
+        return -k * Fmu - torch.lgamma(k) + (k - 1.0) * torch.log(Y) - Y * torch.exp(-Fmu + Fvar / 2.0)
+
+
+def probit(x):
+    """Standard normal CDF squeezed into [1e-3, 1 - 1e-3]  (:268-269)."""
+    return 0.5 * (1.0 + torch.erf(x / np.sqrt(2.0))) * (1 - 2e-3) + 1e-3
+
+
+class Bernoulli(_LinkLikelihood):
+    """y in {0, 1} with p(y = 1) = invlink(f); probit link: closed-form predictions (:272-297)."""
+
+    def __init__(self, invlink=probit):
+        super().__init__(invlink)
+
+    def _logdensity(self, p, Y):
+        return densities.bernoulli(p, Y)
+
+    def _mean(self, p):
+        return p
+
+    def _var(self, p):
+        return p - p ** 2
+
+    def predict_mean_and_var(self, Fmu, Fvar):
+        if self.invlink is not probit:
+            return Likelihood.predict_mean_and_var(self, Fmu, Fvar)
+        p = probit(Fmu / torch.sqrt(1 + Fvar))
+        return p, p - p ** 2
+
+    def predict_density(self, Fmu, Fvar, Y):
+        return densities.bernoulli(self.predict_mean_and_var(Fmu, Fvar)[0], Y)
+
+
+class Beta(_LinkLikelihood):
+    """y in (0, 1) ~ Beta(scale m, scale (1 - m)) with mean m = invlink(f)  (:335-376)."""
+    scale = param_value('scale')
+
+    def __init__(self, invlink=probit, scale=1.0):
+        super().__init__(invlink)
+        self._param('scale', scale, transforms.positive)
+
+    def _logdensity(self, m, Y):
+        a = m * self.scale
+        return densities.beta(a, self.scale - a, Y)
+
+    def _mean(self, m):
+        return m
+
+    def _var(self, m):
+        return (m - m ** 2) / (self.scale + 1.0)
 
 
 class StudentT(Likelihood):
-    """(:244-265)."""
+    """y = f + scale * t_{deg_free}  (:244-265)."""
+    scale = param_value('scale')
 
     def __init__(self, deg_free=3.0):
         super().__init__()
         self.deg_free = deg_free
-        self._scale = Parameter(1.0, transform=transforms.positive, name='scale')
-        self._parameters = self._parameters + [self._scale]
-
-    @property
-    def scale(self):
-        return self._scale.value
+        self._param('scale', 1.0, transforms.positive)
 
     def logp(self, F, Y):
         return densities.student_t(Y, F, self.scale, self.deg_free)
@@ -169,95 +248,6 @@ class StudentT(Likelihood):
 
     def conditional_variance(self, F):
         return F * 0.0 + (self.deg_free / (self.deg_free - 2.0))
-
-
-def probit(x):
-    """(:268-269)."""
-    return 0.5 * (1.0 + torch.erf(x / np.sqrt(2.0))) * (1 - 2e-3) + 1e-3
-
-
-class Bernoulli(Likelihood):
-    """(:272-297)."""
-
-    def __init__(self, invlink=probit):
-        super().__init__()
-        self.invlink = invlink
-
-    def logp(self, F, Y):
-        return densities.bernoulli(self.invlink(F), Y)
-
-    def predict_mean_and_var(self, Fmu, Fvar):
-        if self.invlink is probit:
-            p = probit(Fmu / torch.sqrt(1 + Fvar))
-            return p, p - p ** 2
-        return Likelihood.predict_mean_and_var(self, Fmu, Fvar)
-
-    def predict_density(self, Fmu, Fvar, Y):
-        p = self.predict_mean_and_var(Fmu, Fvar)[0]
-        return densities.bernoulli(p, Y)
-
-    def conditional_mean(self, F):
-        return self.invlink(F)
-
-    def conditional_variance(self, F):
-        p = self.invlink(F)
-        return p - p ** 2
-
-
-class Gamma(Likelihood):
-    """The transformed GP gives the scale of the Gamma (:300-332)."""
-
-    def __init__(self, invlink=torch.exp):
-        super().__init__()
-        self.invlink = invlink
-        self._shape = Parameter(1.0, transform=transforms.positive, name='shape')
-        self._parameters = self._parameters + [self._shape]
-
-    @property
-    def shape(self):
-        return self._shape.value
-
-    def logp(self, F, Y):
-        return densities.gamma(self.shape, self.invlink(F), Y)
-
-    def conditional_mean(self, F):
-        return self.shape * self.invlink(F)
-
-    def conditional_variance(self, F):
-        return self.shape * self.invlink(F) ** 2
-
-    def variational_expectations(self, Fmu, Fvar, Y):
-        if _is_exp(self.invlink):
-            return -self.shape * Fmu - torch.lgamma(self.shape) + (self.shape - 1.0) * torch.log(Y) \
-                - Y * torch.exp(-Fmu + Fvar / 2.0)
-        return Likelihood.variational_expectations(self, Fmu, Fvar, Y)
-
-
-class Beta(Likelihood):
-    """Mean m = invlink(f), alpha = scale m, beta = scale (1 - m)  (:335-376)."""
-
-    def __init__(self, invlink=probit, scale=1.0):
-        super().__init__()
-        self._scale = Parameter(scale, transform=transforms.positive, name='scale')
-        self.invlink = invlink
-        self._parameters = self._parameters + [self._scale]
-
-    @property
-    def scale(self):
-        return self._scale.value
-
-    def logp(self, F, Y):
-        mean = self.invlink(F)
-        alpha = mean * self.scale
-        beta = self.scale - alpha
-        return densities.beta(alpha, beta, Y)
-
-    def conditional_mean(self, F):
-        return self.invlink(F)
-
-    def conditional_variance(self, F):
-        mean = self.invlink(F)
-        return (mean - mean ** 2) / (self.scale + 1.0)
 
 
 class RobustMax(object):
@@ -350,12 +340,9 @@ class Ordinal(Likelihood):
         Likelihood.__init__(self)
         self.bin_edges = np.asarray(bin_edges, dtype=np.float64)
         self.num_bins = self.bin_edges.size + 1
-        self._sigma = Parameter(1.0, transform=transforms.positive, name='sigma')
-        self._parameters = self._parameters + [self._sigma]
+        self._param('sigma', 1.0, transforms.positive)
 
-    @property
-    def sigma(self):
-        return self._sigma.value
+    sigma = param_value('sigma')
 
     def _scaled_bins(self, like):
         edges = _const(self.bin_edges, like) / self.sigma

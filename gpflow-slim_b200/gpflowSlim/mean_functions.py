@@ -4,10 +4,10 @@ O(N D) elementwise work on the device; gradients by torch autograd."""
 import numpy as np
 import torch
 
-from .params import Parameter
+from .params import Parameterized, param_value
 
 
-class MeanFunction(object):
+class MeanFunction(Parameterized):
     """Base class: `__call__(X)` maps [N, D] inputs to [N, Q] means (mean_functions.py:24-54)."""
 
     def __init__(self, name='MeanFunction'):
@@ -50,13 +50,9 @@ class Customized(MeanFunction):
 
     def __init__(self):
         super().__init__()
-        self._W1 = Parameter(np.ones((1, 20)), name='W1')
-        self._b1 = Parameter(np.zeros(20), name='b1')
-        self._W2 = Parameter(np.ones((20, 20)), name='W2')
-        self._b2 = Parameter(np.zeros(20), name='b2')
-        self._W3 = Parameter(np.ones((20, 1)), name='W3')
-        self._b3 = Parameter(np.zeros(1), name='b3')
-        self._parameters = self._parameters + [self._W1, self._b1, self._W2, self._b2, self._W3, self._b3]
+        for i, (fan_in, fan_out) in enumerate(((1, 20), (20, 20), (20, 1)), start=1):
+            self._param('W%d' % i, np.ones((fan_in, fan_out)))
+            self._param('b%d' % i, np.zeros(fan_out))
 
     def __call__(self, X):
         h = torch.relu(X @ self._W1.value + self._b1.value)
@@ -71,17 +67,11 @@ class Linear(MeanFunction):
         A = np.ones((1, 1)) if A is None else A
         b = np.zeros(1) if b is None else b
         super().__init__()
-        self._A = Parameter(np.atleast_2d(A), name='A')
-        self._b = Parameter(b, name='b')
-        self._parameters = self._parameters + [self._A, self._b]
+        self._param('A', np.atleast_2d(A))
+        self._param('b', b)
 
-    @property
-    def A(self):
-        return self._A.value
-
-    @property
-    def b(self):
-        return self._b.value
+    A = param_value('A')
+    b = param_value('b')
 
     def __call__(self, X):
         return X @ self.A + self.b
@@ -93,12 +83,9 @@ class Constant(MeanFunction):
     def __init__(self, c=None):
         super().__init__()
         c = np.zeros(1) if c is None else c
-        self._c = Parameter(c, name='c')
-        self._parameters = self._parameters + [self._c]
+        self._param('c', c)
 
-    @property
-    def c(self):
-        return self._c.value
+    c = param_value('c')
 
     def __call__(self, X):
         return self.c.reshape(1, -1).repeat(X.shape[0], 1)

@@ -5,7 +5,7 @@ import torch
 from .. import conditionals, features, kullback_leiblers, transforms
 from .._settings import SETTINGS as settings
 from ..misc import to_tensor
-from ..params import Parameter
+from ..params import Parameter, param_value
 from .model import GPModel
 
 
@@ -29,13 +29,8 @@ class SVGP(GPModel):
                                      name='q_sqrt')
         self._parameters = self._parameters + [self._q_mu, self._q_sqrt]
 
-    @property
-    def q_mu(self):
-        return self._q_mu.value
-
-    @property
-    def q_sqrt(self):
-        return self._q_sqrt.value
+    q_mu = param_value('q_mu')
+    q_sqrt = param_value('q_sqrt')
 
     def build_prior_KL(self):
         """svgp.py:101-106."""

@@ -75,3 +75,27 @@ class Parameter(object):
 
     def __repr__(self):
         return 'Parameter(%s, shape=%s, transform=%s)' % (self.name, self.shape, self.transform)
+
+
+class param_value(object):
+    """Class-level descriptor: `variance = param_value('variance')` exposes the CONSTRAINED value
+    of the Parameter stored as `self._variance` (what the reference spells out as a four-line
+    @property per parameter)."""
+
+    def __init__(self, name):
+        self.attr = '_' + name
+
+    def __get__(self, obj, owner=None):
+        return self if obj is None else getattr(obj, self.attr).value
+
+
+class Parameterized(object):
+    """Mixin: `_param(name, value, transform)` creates the Parameter, stores it as `_<name>` and
+    appends it to `_parameters` (the list models collect, models/model.py:119)."""
+
+    def _param(self, name, value, transform=None):
+        prm = Parameter(value, transform=transform, name=name)
+        setattr(self, '_' + name, prm)
+        self._parameters = list(getattr(self, '_parameters', [])) + [prm]
+        return prm
+
