@@ -130,6 +130,7 @@ class Handle(object):
         self.lib = load()
         self.device_index = device_index
         self.ptr = _H()
+        self._stream = None
         rc = self.lib.gps_create(device_index, ctypes.byref(self.ptr))
         if rc != 0:
             raise RuntimeError('gps_create(device=%d) failed (rc=%d): an sm_100 (B200) GPU is '
@@ -145,8 +146,12 @@ class Handle(object):
         raise ValueError('libgpslim_b200: %s (rc=%d)' % (msg, rc))
 
     def sync_stream(self):
+        """Make the library launch on torch's current stream (only this method sets the handle's
+        stream, so the call is skipped while the stream has not changed)."""
         s = torch.cuda.current_stream(self.device_index).cuda_stream
-        self.lib.gps_set_stream(self.ptr, ctypes.c_void_p(s))
+        if s != self._stream:
+            self.lib.gps_set_stream(self.ptr, ctypes.c_void_p(s))
+            self._stream = s
 
     def set_option(self, name, value):
         self.check(self.lib.gps_set_option(self.ptr, name.encode(), int(value)))
