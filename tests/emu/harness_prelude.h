@@ -27,7 +27,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __restrict__
-#define __launch_bounds__(x)
+#define __launch_bounds__(...)
 #define __shared__ static              /* static __shared__ arrays: one per block == one per process here */
 #define __align__(n) __attribute__((aligned(n)))
 
