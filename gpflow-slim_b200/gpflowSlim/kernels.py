@@ -34,6 +34,16 @@ from .misc import to_tensor
 from .params import Parameter
 
 
+class KernelTooLarge(NotImplementedError):
+    """The expression does not fit the fused Gram kernel's static tables (include/gpslim_b200.h:
+    GPS_MAX_PRIMS / DIMS / OPS / SLOTS, 160 features per point, 191 hyper-parameters, column
+    indices <= 255).  A NotImplementedError on purpose: callers then evaluate the expression on
+    the composed path (tensor-core GEMM + elementwise) instead of failing."""
+
+
+_MAX_FEATURES, _MAX_THETA_FUSED, _MAX_COLUMN = 160, 191, 255
+
+
 class _Builder(object):
     """Collects primitives / theta pieces / ops while a kernel expression is walked."""
 
@@ -68,8 +78,17 @@ class _Builder(object):
         if P < 1:
             raise ValueError('a kernel expression needs at least one kernel')
         if P > _lib.GPS_MAX_PRIMS or len(self.ops) > _lib.GPS_MAX_OPS \
-                or P + self.n_results > _lib.GPS_MAX_SLOTS:
-            raise ValueError('kernel expression too large for the fused Gram kernel')
+                or P + self.n_results > _lib.GPS_MAX_SLOTS or self.n_theta > _MAX_THETA_FUSED:
+            raise KernelTooLarge('kernel expression too large for the fused Gram kernel')
+        nfeat = 0
+        for ptype, dims, _, _ in self.prims:
+            nfeat += len(dims) + 1 if ptype <= _lib.GPS_MATERN52 else \
+                (len(dims) if ptype == _lib.GPS_LINEAR else 3 * len(dims))
+            if len(dims) > _lib.GPS_MAX_DIMS or (dims and max(dims) > _MAX_COLUMN):
+                raise KernelTooLarge('more than %d active dimensions (or a column index above %d) in one '
+                                     'primitive' % (_lib.GPS_MAX_DIMS, _MAX_COLUMN))
+        if nfeat > _MAX_FEATURES:
+            raise KernelTooLarge('more than %d features per point' % _MAX_FEATURES)
 
         def slot(ref):
             return ref[1] if ref[0] == 'p' else P + ref[1]
@@ -80,8 +99,6 @@ class _Builder(object):
         for i, (ptype, dims, ard, off) in enumerate(self.prims):
             pr = desc.prims[i]
             pr.type, pr.ndims, pr.ard, pr.theta_off = ptype, len(dims), ard, off
-            if len(dims) > _lib.GPS_MAX_DIMS:
-                raise ValueError('at most %d active dimensions per primitive' % _lib.GPS_MAX_DIMS)
             for k, dd in enumerate(dims):
                 pr.dims[k] = dd
         for i, (op, rid, a, b, c, d, n) in enumerate(self.ops):
@@ -135,21 +152,42 @@ class Kernel(object):
     def compute_Kdiag(self, X):
         return self.Kdiag(X)
 
+    def _use_fused(self, X, X2=None):
+        """The fused Gram kernel applies when the expression compiles AND, if a gradient w.r.t.
+        the inputs is wanted, X has at most GPS_MAX_DIMS columns (the d/dX accumulators of the
+        backward kernel are per column)."""
+        if not self.fusable:
+            return False
+        wants_dx = X.requires_grad or (X2 is not None and X2.requires_grad)
+        return not (wants_dx and X.shape[1] > _lib.GPS_MAX_DIMS)
+
     def K(self, X, X2=None, presliced=False):
-        """Gram matrix [N, M] (one fused kernel launch; `presliced` is accepted for API
-        compatibility -- slicing happens inside the CUDA kernel via the active-dims table)."""
+        """Gram matrix [N, M]: one fused kernel launch (`presliced` is accepted for API
+        compatibility -- slicing happens inside the CUDA kernel via the active-dims table), or
+        the composed evaluation when the expression does not fit the fused kernel."""
         X = to_tensor(X)
         X2 = None if X2 is None else to_tensor(X2)
-        return _ops.gram(self.program(presliced), X, X2)
+        if self._use_fused(X, X2):
+            return _ops.gram(self.program(presliced), X, X2)
+        return self._K_composed(X, X2, presliced)
 
     def Kdiag(self, X, presliced=False):
-        return _ops.kdiag(self.program(presliced), to_tensor(X))
+        X = to_tensor(X)
+        if self._use_fused(X):
+            return _ops.kdiag(self.program(presliced), X)
+        return self._Kdiag_composed(X, presliced)
+
+    def _K_composed(self, X, X2, presliced):
+        raise NotImplementedError('%s has no composed evaluation' % type(self).__name__)
+
+    def _Kdiag_composed(self, X, presliced):
+        raise NotImplementedError('%s has no composed evaluation' % type(self).__name__)
 
     def K_jittered(self, X, jitter):
         """K(X) + jitter I (features.py:74-77, conditionals.py:60).  Fused kernels add the
         jitter in the Gram kernel's diagonal epilogue; composed kernels add it elementwise."""
         X = to_tensor(X)
-        if self.fusable:
+        if self._use_fused(X):
             return _ops.gram(self.program(), X, None, diag_add=float(jitter))
         return self.K(X) + torch.eye(X.shape[0], dtype=X.dtype, device=X.device) * float(jitter)
 
@@ -304,6 +342,18 @@ class Stationary(Kernel):
     def euclid_dist(self, X, X2):
         return torch.sqrt(self.square_dist(X, X2) + 1e-12)
 
+    # composed evaluation of the fused primitives (expressions that do not fit the fused kernel,
+    # e.g. the 100 network features of the reference's examples/svgp.py): the squared distance via
+    # the tensor-core GEMM, the radial profile elementwise -- op for op kernels.py:408-439, :562-610
+    _profile = None          # k(d2) / variance
+
+    def _K_composed(self, X, X2, presliced):
+        X, X2 = self._sliced(X, X2, presliced)
+        return self.variance * type(self)._profile(self.square_dist(X, X2))
+
+    def _Kdiag_composed(self, X, presliced):
+        return torch.ones_like(X[:, 0]) * self.variance
+
     def _sliced(self, X, X2, presliced):
         X = to_tensor(X)
         X2 = None if X2 is None else to_tensor(X2)
@@ -318,6 +368,7 @@ class Stationary(Kernel):
 class RBF(Stationary):
     """sigma^2 exp(-d^2/2) (kernels.py:432-439)."""
     _ptype = _lib.GPS_RBF
+    _profile = staticmethod(lambda d2: torch.exp(-d2 / 2))
 
     def dimwise(self, dim):
         """One-dimensional factor of the product form (kernels.py:441-444)."""
@@ -352,11 +403,13 @@ class RatQuad(Stationary):
 class Exponential(Stationary):
     """sigma^2 exp(-r/2) (kernels.py:555-566)."""
     _ptype = _lib.GPS_EXPONENTIAL
+    _profile = staticmethod(lambda d2: (lambda r: torch.exp(-0.5 * r))(torch.sqrt(d2 + 1e-12)))
 
 
 class Matern12(Stationary):
     """sigma^2 exp(-r) (kernels.py:569-577)."""
     _ptype = _lib.GPS_MATERN12
+    _profile = staticmethod(lambda d2: (lambda r: torch.exp(-r))(torch.sqrt(d2 + 1e-12)))
 
     def dimwise(self, dim):
         return self._dimwise(Matern12, dim)
@@ -365,6 +418,7 @@ class Matern12(Stationary):
 class Matern32(Stationary):
     """sigma^2 (1 + sqrt3 r) exp(-sqrt3 r) (kernels.py:585-594)."""
     _ptype = _lib.GPS_MATERN32
+    _profile = staticmethod(lambda d2: (lambda r: (1. + np.sqrt(3.) * r) * torch.exp(-np.sqrt(3.) * r))(torch.sqrt(d2 + 1e-12)))
 
     def dimwise(self, dim):
         return self._dimwise(Matern32, dim)
@@ -373,6 +427,7 @@ class Matern32(Stationary):
 class Matern52(Stationary):
     """sigma^2 (1 + sqrt5 r + 5/3 r^2) exp(-sqrt5 r) (kernels.py:601-610)."""
     _ptype = _lib.GPS_MATERN52
+    _profile = staticmethod(lambda d2: (lambda r: (1.0 + np.sqrt(5.) * r + 5. / 3. * r ** 2) * torch.exp(-np.sqrt(5.) * r))(torch.sqrt(d2 + 1e-12)))
 
     def dimwise(self, dim):
         return self._dimwise(Matern52, dim)
@@ -511,6 +566,16 @@ class Linear(Kernel):
         return b.prim(_lib.GPS_LINEAR, self._dims(presliced), self.ARD,
                       [(lambda: self.variance, self.input_dim if self.ARD else 1)])
 
+    def _K_composed(self, X, X2, presliced):
+        if not presliced:
+            X, X2 = self._slice(X, X2)
+        return _ops.matmul_nt(X * self.variance, X if X2 is None else X2)       # kernels.py:503-505
+
+    def _Kdiag_composed(self, X, presliced):
+        if not presliced:
+            X, _ = self._slice(X, None)
+        return (X ** 2 * self.variance).sum(1)                                   # kernels.py:510
+
     def dimwise(self, dim):
         """kernels.py:512-515."""
         var = self.variance[dim] if self.ARD else self.variance ** (1. / self.input_dim)
@@ -579,6 +644,21 @@ class Periodic(Kernel):
     @property
     def period(self):
         return self._period.value
+
+    def _K_composed(self, X, X2, presliced):
+        """sum_d sin^2(pi (x_d - x'_d) / p) = (D - sum_d cos(a_d - a'_d)) / 2 with a = 2 pi x / p
+        (the identity the fused kernel uses): two tensor-core GEMMs on cos / sin features
+        instead of the reference's N x M x D broadcast (kernels.py:806-819)."""
+        if not presliced:
+            X, X2 = self._slice(X, X2)
+        a = 2.0 * np.pi * X / self.period
+        a2 = a if X2 is None else 2.0 * np.pi * X2 / self.period
+        cs = _ops.matmul_nt(torch.cos(a), torch.cos(a2)) + _ops.matmul_nt(torch.sin(a), torch.sin(a2))
+        r = 0.5 * (float(X.shape[1]) - cs) / self.lengthscales ** 2
+        return self.variance * torch.exp(-0.5 * r)
+
+    def _Kdiag_composed(self, X, presliced):
+        return torch.ones_like(X[:, 0]) * self.variance
 
     def _emit(self, b, presliced=False):
         return b.prim(_lib.GPS_PERIODIC, self._dims(presliced), False,
@@ -731,8 +811,12 @@ class Combination(Kernel):
             part = None
             if len(fus) == 1:
                 part = fus[0]
+            elif fus and not rest and not self.fusable:
+                part = self             # children fuse one by one, their combination does not fit
             elif fus:
                 part = self.__class__(fus)
+                if not part.fusable:    # the fusable children together are too large: one by one
+                    part, rest = None, list(self.kern_list)
             self._fused_part = (part, rest)
         return self._fused_part
 
@@ -742,21 +826,20 @@ class Combination(Kernel):
                         torch.as_tensor(float(c), dtype=like.dtype, device=like.device))
         return reduce(self._torch_op, vals)
 
-    def K(self, X, X2=None, presliced=False):
-        if self.fusable:
-            return super().K(X, X2, presliced)
-        X = to_tensor(X)
-        X2 = None if X2 is None else to_tensor(X2)
+    def _K_composed(self, X, X2, presliced):
         part, rest = self._split()
-        vals = ([part.K(X, X2)] if part is not None else []) + [k.K(X, X2) for k in rest]
+        if part is self:          # everything is fusable in principle, but the whole is too large / needs d/dX
+            vals = [k.K(X, X2) for k in self.kern_list]
+        else:
+            vals = ([part.K(X, X2)] if part is not None else []) + [k.K(X, X2) for k in rest]
         return self._combine(vals, X)
 
-    def Kdiag(self, X, presliced=False):
-        if self.fusable:
-            return super().Kdiag(X, presliced)
-        X = to_tensor(X)
+    def _Kdiag_composed(self, X, presliced):
         part, rest = self._split()
-        vals = ([part.Kdiag(X)] if part is not None else []) + [k.Kdiag(X) for k in rest]
+        if part is self:
+            vals = [k.Kdiag(X) for k in self.kern_list]
+        else:
+            vals = ([part.Kdiag(X)] if part is not None else []) + [k.Kdiag(X) for k in rest]
         return self._combine(vals, X)
 
 

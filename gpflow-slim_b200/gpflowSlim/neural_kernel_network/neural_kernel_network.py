@@ -35,16 +35,13 @@ class NeuralKernelNetwork(Kernel):
         h = torch.stack([v.reshape(-1) for v in vals], 1)
         return self._nknWrapper.forward(h).reshape(shape)
 
-    def Kdiag(self, X, presliced=False):
-        # `fusable` is False for Activation layers AND for composed primitive kernels
-        # (kernels.py: RatQuad, Polynomial, ...): both take the stacked-Gram route
-        if self.fusable:
-            return super().Kdiag(X, presliced)
+    # `fusable` is False for Activation layers, for composed primitive kernels (kernels.py: RatQuad,
+    # Polynomial, ...) and for networks too large for the fused kernel's tables: all take the
+    # stacked-Gram route (neural_kernel_network.py:35-47 of the reference, on the device)
+    def _Kdiag_composed(self, X, presliced):
         vals = [k.Kdiag(X, presliced) for k in self._primitive_kernels]
         return self._unfused(vals, vals[0].shape)
 
-    def K(self, X, X2=None, presliced=False):
-        if self.fusable:
-            return super().K(X, X2, presliced)
+    def _K_composed(self, X, X2, presliced):
         vals = [k.K(X, X2, presliced) for k in self._primitive_kernels]
         return self._unfused(vals, vals[0].shape)

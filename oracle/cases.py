@@ -182,6 +182,55 @@ def case_gpr_composed(gpf, conv):
     return out, [('objective', m)]
 
 
+def case_large_d(gpf, conv):
+    """Inputs wider than the fused Gram kernel's per-primitive table (40 columns; the reference's
+    examples/svgp.py feeds 100 network features): Grams, parameter and input gradients of the
+    hot-path primitives and a composition, a GPR and an SVGP on them."""
+    import torch
+    d = 40
+    rng = np.random.default_rng(60)
+    X = rng.standard_normal((31, d)) * 0.6
+    X2 = rng.standard_normal((19, d)) * 0.6
+    W, W2 = rng.standard_normal((31, 31)), rng.standard_normal((31, 19))
+    W = W + W.T
+    k = gpf.kernels
+    ls = 3.0 + 0.05 * np.arange(d)
+    zoo = [('rbf_ard', lambda: k.RBF(d, variance=1.2, lengthscales=ls, ARD=True, name='la')),
+           ('m32_iso', lambda: k.Matern32(d, variance=0.7, lengthscales=5.0, name='lb')),
+           ('lin_ard', lambda: k.Linear(d, variance=0.02 + 0.001 * np.arange(d), ARD=True, name='lc')),
+           ('periodic', lambda: k.Periodic(d, period=2.3, variance=1.1, lengthscales=3.0, name='ld')),
+           ('composite', lambda: k.RBF(d, lengthscales=ls, ARD=True, name='le1')
+            + k.Linear(d, variance=0.03, name='le2') * k.Matern52(d, lengthscales=6.0, name='le3') + 0.2)]
+    out = {}
+    for name, make in zoo:
+        kern = make()
+        Xg = conv(X).requires_grad_(True)
+        K, K2, Kd = kern.K(Xg), kern.K(Xg, conv(X2)), kern.Kdiag(Xg)
+        out[name + '/K'], out[name + '/K2'], out[name + '/Kdiag'] = K, K2, Kd
+        val = (K * conv(W)).sum() + (K2 * conv(W2)).sum() + (Kd * conv(W[:, 0])).sum()
+        params = [p.unconstrained_tensor for p in kern.parameters]
+        gs = torch.autograd.grad(val, params + [Xg])
+        for i, g in enumerate(gs[:-1]):
+            out['%s/grad%d' % (name, i)] = g
+        out[name + '/dX'] = gs[-1]
+    n = 150
+    Xr = rng.standard_normal((n, d)) * 0.6
+    Yr = np.sin(Xr[:, :3].sum(1, keepdims=True)) + 0.1 * rng.standard_normal((n, 1))
+    Xs = rng.standard_normal((11, d)) * 0.6
+    m = gpf.models.GPR(conv(Xr), conv(Yr), kern=k.RBF(d, ARD=True, lengthscales=ls, name='lg_k'), name='lg')
+    out['gpr/objective'] = m.objective
+    out['gpr/pred_mu'], out['gpr/pred_var'] = m.predict_f(conv(Xs))
+    Z = Xr[:20].copy()
+    sv = gpf.models.SVGP(conv(Xr), conv(Yr), k.Matern52(d, ARD=True, lengthscales=ls, name='ls_k'),
+                         gpf.likelihoods.Gaussian(var=0.2), Z=Z, name='ls')
+    with torch.no_grad():
+        qm = sv._q_mu.unconstrained_tensor
+        qm.copy_(torch.as_tensor(0.3 * rng.standard_normal(tuple(qm.shape))).to(qm))
+    out['svgp/objective'] = sv.objective
+    out['svgp/pred_mu'], out['svgp/pred_var'] = sv.predict_f(conv(Xs))
+    return out, [('gpr/objective', m), ('svgp/objective', sv)]
+
+
 def nkn_c3_kernel(gpf, d, weights=None):
     """The section-8(d) NKN topology: k=6 primitives, Linear 6->8, Product 2, Linear 4->4,
     Product 2, Linear 2->1 (neural_kernel_network_wrapper.py:38-40 hparams schema).  The
@@ -682,6 +731,7 @@ CASES = {
     'kernels': case_kernels,
     'kernels_extra': case_kernels_extra,
     'gpr_composed': case_gpr_composed,
+    'large_d': case_large_d,
     'gpr_features': case_gpr_features,
     'priors': case_priors,
     'mc_models': case_mc_models,
@@ -707,7 +757,7 @@ CASES = {
 # Cases added after the last session that had GPU time.  tests/test_gpu_parity.py runs the rest,
 # tests/test_gpu_zz_widened.py (sorted last, so a surprise there cannot mask the established
 # tests under `pytest -x`) runs these; once seen green on a B200 they simply leave this tuple.
-LATE_CASES = ('kernels_extra', 'gpr_composed', 'lbfgs', 'gpr_features', 'priors', 'mc_models', 'likelihoods_extra')
+LATE_CASES = ('kernels_extra', 'gpr_composed', 'lbfgs', 'gpr_features', 'priors', 'mc_models', 'likelihoods_extra', 'large_d')
 # Pure host logic (no library call): checked on the CPU only.
 HOST_ONLY_CASES = ('lbfgs_rosenbrock',)
 

@@ -128,3 +128,49 @@ def test_likelihoods_match_reference_golden(golden):
         assert a.shape == b.shape, key
         err = np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
         assert err < 1e-10, '%s: relative error %.2e' % (key, err)
+
+
+def test_expressions_too_large_for_the_fused_kernel_fall_back_to_composed(monkeypatch):
+    """More than 32 active dimensions in a primitive, more than 16 primitives or more than 160
+    features per point do not fit the fused Gram kernel's tables: `fusable` turns False (no
+    exception) and K / Kdiag take the composed route -- checked here against the oracle on the CPU
+    test double, with the fused `gram` entry point booby-trapped for the oversized parts."""
+    import cpu_ops_double
+    g = gpf()
+    k = g.kernels
+    ops = cpu_ops_double.install(monkeypatch)
+    g.settings.device = 'cpu'
+    rng = np.random.default_rng(1)
+    wide = k.RBF(40, ARD=True, lengthscales=4.0)
+    assert not wide.fusable and k.RBF(32, ARD=True).fusable
+    many = k.Sum([k.RBF(2, active_dims=[i % 5, (i + 1) % 5], lengthscales=1.0 + 0.1 * i) for i in range(17)])
+    assert not many.fusable and all(c.fusable for c in many.kern_list)
+    fat = k.Sum([k.Periodic(30, period=1.0 + 0.1 * i) for i in range(2)])          # 2 x 90 features
+    assert not fat.fusable
+    X40, X5, X30 = (torch.tensor(rng.standard_normal((23, d)) * 0.7) for d in (40, 5, 30))
+
+    real_gram = ops.gram
+
+    def trapped(prog, X, X2=None, diag_add=0.0):
+        assert prog.desc.n_prims <= 16 and max(prog.desc.prims[i].ndims for i in range(prog.desc.n_prims)) <= 32
+        return real_gram(prog, X, X2, diag_add)
+    monkeypatch.setattr(ops, 'gram', trapped)
+    spec = dict(type='rbf', variance=torch.tensor(1.0, dtype=torch.float64),
+                lengthscales=torch.full((40,), 4.0, dtype=torch.float64))
+    np.testing.assert_allclose(wide.K(X40).detach().numpy(), R.K(spec, X40).numpy(), rtol=1e-12)
+    np.testing.assert_allclose(wide.K_jittered(X40, 1e-6).detach().numpy(),
+                               (R.K(spec, X40) + 1e-6 * torch.eye(23)).numpy(), rtol=1e-12)
+    want = sum(R.K(dict(type='rbf', variance=torch.tensor(1.0), lengthscales=torch.tensor(1.0 + 0.1 * i, dtype=torch.float64),
+                        active_dims=[i % 5, (i + 1) % 5]), X5) for i in range(17))
+    np.testing.assert_allclose(many.K(X5).detach().numpy(), want.numpy(), rtol=1e-12)
+    np.testing.assert_allclose(many.Kdiag(X5).detach().numpy(), np.full(23, 17.0), rtol=1e-12)
+    want = sum(R.K(dict(type='periodic', variance=torch.tensor(1.0), lengthscales=torch.tensor(1.0),
+                        period=torch.tensor(1.0 + 0.1 * i, dtype=torch.float64)), X30) for i in range(2))
+    np.testing.assert_allclose(fat.K(X30).detach().numpy(), want.numpy(), rtol=1e-10)
+    # a gradient w.r.t. inputs wider than 32 columns also leaves the fused kernel, even if the
+    # kernel itself only looks at two of them
+    narrow = k.RBF(2, active_dims=[3, 38])
+    assert narrow.fusable
+    Xg = X40.clone().requires_grad_(True)
+    assert not narrow._use_fused(Xg) and narrow._use_fused(X40)
+    g.settings.device = None
