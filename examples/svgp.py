@@ -120,5 +120,8 @@ def main(iters=300, report=50, num_h=32, num_inducing=100, minibatch_size=250, q
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--iters', type=int, default=300)
+    ap.add_argument('--num_h', type=int, default=32,
+                    help='network features fed to the GP (the reference uses 100; above 32 the Gram '
+                         'matrices take the composed GEMM path instead of the fused kernel)')
     a = ap.parse_args()
-    main(iters=a.iters)
+    main(iters=a.iters, num_h=a.num_h)
