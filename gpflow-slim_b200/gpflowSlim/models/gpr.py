@@ -27,11 +27,7 @@ class GPR(GPModel):
             return False
         if any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
             return False
-        try:
-            self.kern.program()
-        except NotImplementedError:
-            return False
-        return True
+        return bool(getattr(self.kern, 'fusable', False))     # cached by the kernel object
 
     def _feature_map(self):
         """`kern.features` if the covariance is an explicit feature expansion K = C C^T
