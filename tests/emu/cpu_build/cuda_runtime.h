@@ -1,0 +1,191 @@
+// TEST INFRASTRUCTURE ONLY -- a stand-in for <cuda_runtime.h> (found first on the include path of
+// the emulation build, tests/test_library_on_cpu.py) that lets the WHOLE of libgpslim_b200 --
+// host orchestration and kernel source -- compile with g++ and run on the CPU:
+//   * device memory is host memory; streams do not exist: every launch runs to completion at its
+//     call site, which is one legal serialisation of the stream order;
+//   * a kernel launch `k<<<grid, block, smem, stream>>>(args)` is rewritten textually into
+//     EMU_LAUNCH(grid, block, smem, k(args)) by the build script: one std::thread per CUDA thread
+//     of a block, blocks one after the other, __syncthreads = block barrier, warp collectives =
+//     per-warp barriers + exchange buffer, mma.sync.m8n8k4.f64 emulated per the PTX fragment
+//     layout, cp.async = copy with zero fill;
+//   * the TMA / mbarrier GEMM kernel is cut out (inline PTX): the cp.async tensor-core kernel
+//     serves every product, as it does on the GPU for operands TMA cannot address.
+// Nothing here is shipped or used by the product.
+#pragma once
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+using std::max;
+using std::min;
+
+// ---------------------------------------------------------------- keywords
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+
+// ---------------------------------------------------------------- runtime API
+typedef int cudaError_t;
+enum { cudaSuccess = 0 };
+typedef void* cudaStream_t;
+struct EmuEvent { double t; };
+typedef EmuEvent* cudaEvent_t;
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
+struct cudaDeviceProp { int major, minor, multiProcessorCount; };
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->major = 10; p->minor = 0; p->multiProcessorCount = 4; return cudaSuccess; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaMalloc(void** p, size_t n) {
+  *p = aligned_alloc(256, (n + 255) / 256 * 256);
+  if (*p) memset(*p, 0xFF, (n + 255) / 256 * 256);     // NaN-poison: unwritten workspace reads show up
+  return *p ? cudaSuccess : 2;
+}
+inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemset2DAsync(void* p, size_t pitch, int v, size_t w, size_t h, cudaStream_t) {
+  for (size_t r = 0; r < h; ++r) memset((char*)p + r * pitch, v, w);
+  return cudaSuccess;
+}
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
+template <class F>
+inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new EmuEvent{0.0}; return cudaSuccess; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
+
+// ---------------------------------------------------------------- execution model
+struct EmuIdx { unsigned x = 0, y = 0, z = 0; };
+inline thread_local EmuIdx threadIdx, blockIdx;
+inline thread_local unsigned emu_ltid = 0;                // linear thread id inside the block
+inline dim3 gridDim, blockDim;
+inline double* emu_smem = nullptr;
+inline double* emu_wx = nullptr;                          // [2][nthreads] exchange slots
+inline unsigned emu_nthreads = 0;
+inline pthread_barrier_t emu_bar;
+inline pthread_barrier_t emu_wbar[32];
+inline std::mutex emu_atomic_mutex;
+
+inline void emu_barrier() { pthread_barrier_wait(&emu_bar); }
+inline void emu_warp_barrier() { pthread_barrier_wait(&emu_wbar[emu_ltid >> 5]); }
+#define __syncthreads() emu_barrier()
+#define __syncwarp() emu_warp_barrier()
+
+inline double emu_shfl(double v, int src_lane) {
+  const unsigned t = emu_ltid;
+  emu_wx[t] = v;
+  emu_warp_barrier();
+  double r = emu_wx[(t & ~31u) + ((unsigned)src_lane & 31u)];
+  emu_warp_barrier();
+  return r;
+}
+#define __shfl_sync(mask, v, src) emu_shfl((v), (src))
+#define __shfl_xor_sync(mask, v, lm) emu_shfl((v), (int)((emu_ltid & 31u) ^ (unsigned)(lm)))
+inline double warp_sum(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+inline void dmma884(double& c0, double& c1, double a, double b) {
+  const unsigned t = emu_ltid, w0 = t & ~31u, lane = t & 31u;
+  emu_wx[t] = a;
+  emu_wx[emu_nthreads + t] = b;
+  emu_warp_barrier();
+  const unsigned row = lane >> 2, col0 = 2 * (lane & 3);
+  double s0 = c0, s1 = c1;
+  for (unsigned k = 0; k < 4; ++k) {
+    const double av = emu_wx[w0 + row * 4 + k];
+    s0 = fma(av, emu_wx[emu_nthreads + w0 + col0 * 4 + k], s0);
+    s1 = fma(av, emu_wx[emu_nthreads + w0 + (col0 + 1) * 4 + k], s1);
+  }
+  emu_warp_barrier();
+  c0 = s0;
+  c1 = s1;
+}
+inline double rsqrt(double x) { return 1.0 / sqrt(x); }
+inline int atomicCAS(int* addr, int cmp, int val) {
+  std::lock_guard<std::mutex> g(emu_atomic_mutex);
+  int old = *addr;
+  if (old == cmp) *addr = val;
+  return old;
+}
+inline int atomicMin(int* addr, int val) {
+  std::lock_guard<std::mutex> g(emu_atomic_mutex);
+  int old = *addr;
+  if (val < old) *addr = val;
+  return old;
+}
+inline void cp_async16(void* smem, const void* gmem, int n) { memset(smem, 0, 16); if (n > 0) memcpy(smem, gmem, (size_t)n); }
+inline void cp_async8(void* smem, const void* gmem, int n) { memset(smem, 0, 8); if (n > 0) memcpy(smem, gmem, (size_t)n); }
+inline void cp_async_commit() {}
+template <int N>
+inline void cp_async_wait() {}
+template <class T>
+inline T __ldcg(const T* p) { return *p; }
+struct double2 { double x, y; };
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
+
+inline int64_t emu_launch_count = 0;
+
+template <class Body>
+void emu_launch(dim3 grid, dim3 block, size_t smem_bytes, Body body) {
+  ++emu_launch_count;
+  const unsigned nthreads = block.x * block.y * block.z;
+  gridDim = grid;
+  blockDim = block;
+  emu_nthreads = nthreads;
+  std::vector<double> smem(smem_bytes / sizeof(double) + 8), wx(2 * (size_t)nthreads + 64);
+  emu_smem = smem.data();
+  emu_wx = wx.data();
+  pthread_barrier_init(&emu_bar, nullptr, nthreads);
+  const unsigned nwarps = (nthreads + 31) / 32;
+  for (unsigned w = 0; w < nwarps; ++w)
+    pthread_barrier_init(&emu_wbar[w], nullptr, std::min(32u, nthreads - 32 * w));
+  std::vector<std::thread> pool;
+  pool.reserve(nthreads);
+  for (unsigned t = 0; t < nthreads; ++t)
+    pool.emplace_back([=, &smem]() {
+      emu_ltid = t;
+      threadIdx.x = t % block.x;
+      threadIdx.y = (t / block.x) % block.y;
+      threadIdx.z = t / (block.x * block.y);
+      for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+          for (unsigned bx = 0; bx < grid.x; ++bx) {
+            blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
+            if (t == 0)
+              for (auto& v : smem) v = NAN;            // fresh block: stale shared memory cannot help
+            emu_barrier();
+            body();
+            emu_barrier();
+          }
+    });
+  for (auto& th : pool) th.join();
+  pthread_barrier_destroy(&emu_bar);
+  for (unsigned w = 0; w < nwarps; ++w) pthread_barrier_destroy(&emu_wbar[w]);
+}
+#define EMU_LAUNCH(grid, block, smem, call) emu_launch((grid), (block), (size_t)(smem), [&]() { call; })
