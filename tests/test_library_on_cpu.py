@@ -195,3 +195,32 @@ def test_fused_gpr_objective_gradient_and_prediction(gpf):
     rel = lambda a, b: float((a.detach().reshape(-1) - b.detach().reshape(-1)).abs().max() / b.detach().abs().max())
     errs = [rel(obj, o)] + [rel(a, b) for a, b in zip(grads, go)] + [rel(mu, mo), rel(var, vo)]
     assert max(errs) < 1e-9, errs
+
+
+@pytest.mark.skipif(not FULL, reason='GPSLIM_CPU_LIB_FULL=1')
+def test_experimental_switches_through_the_real_dispatch_code(gpf, golden):
+    """The switches that are still off by default (tests/test_gpu_experimental.py), through the
+    shipped host code on the CPU build: gram_impl = 2 (shared-memory interpreter kernels: their
+    launch configuration and shared-memory sizing are host code) on the NKN case, and the
+    triangular-aware matmul adjoints on a non-whitened SVGP."""
+    from gpflowSlim._backend import lib, ops
+
+    def check(name):
+        gold = golden(name)
+        res = cases.run_case(gpf, name, conv)
+        for key in sorted(gold):
+            a, b = np.asarray(res[key], dtype=np.float64), np.asarray(gold[key], dtype=np.float64)
+            e = float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)) if a.size else 0.0
+            assert e < (1e-12 if key.startswith('param/') else 1e-8), '%s/%s: %.3e' % (name, key, e)
+    h = lib.handle_for(None)
+    h.set_option('gram_impl', 2)
+    try:
+        check('nkn')
+    finally:
+        h.set_option('gram_impl', 0)
+    ops.TRI_AWARE_ADJOINTS[0] = True
+    try:
+        check('svgp_nonwhite_diag')
+    finally:
+        ops.TRI_AWARE_ADJOINTS[0] = False
+
