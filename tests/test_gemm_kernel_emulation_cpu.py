@@ -96,10 +96,10 @@ def test_general_product_with_beta_and_both_staging_widths(emu, m, n, k, ld_extr
 @pytest.mark.parametrize('b_tri', [TRI_NONE, TRI_LOWER, TRI_UPPER])
 @pytest.mark.parametrize('c_uplo', [C_ALL, C_LOWER])
 def test_every_triangular_combination(emu, a_tri, b_tri, c_uplo):
-    """Square n = 200 (two tile rows, ragged last tile; the three-tile-row case is the test
+    """Square n = 160 (two tile rows, ragged last tile; the three-tile-row case is the test
     below).  Operands are TRULY triangular (the kernel skips whole zero tiles but reads diagonal
     tiles in full); with c_uplo = lower only the lower triangle of C may be written."""
-    n = 200
+    n = 160
     rng = np.random.default_rng(a_tri * 9 + b_tri * 3 + c_uplo)
     A, B = tri(rng.standard_normal((n, n)), a_tri), tri(rng.standard_normal((n, n)), b_tri)
     C0 = rng.standard_normal((n, n))
