@@ -31,6 +31,13 @@ def _prep(t):
 def gemm_nt(A, B, alpha=1.0, beta=0.0, out=None, a_tri=TRI_NONE, b_tri=TRI_NONE, c_uplo=0):
     """out = alpha * A @ B.T + beta * out  (FP64 tensor-core GEMM)."""
     A, B = _prep(A), _prep(B)
+    if A.shape[0] == 0 or B.shape[0] == 0 or A.shape[1] == 0:
+        # empty product: nothing to launch (an empty tensor has no device pointer to hand over)
+        if out is None:
+            return torch.zeros((A.shape[0], B.shape[0]), dtype=F64, device=A.device)
+        if A.shape[1] == 0 and out.numel():
+            out.mul_(float(beta)) if beta != 0.0 else out.zero_()
+        return out
     h = handle_for(A)
     if out is None:
         out = torch.empty((A.shape[0], B.shape[0]), dtype=F64, device=A.device)
@@ -68,6 +75,8 @@ def set_graph_capture(flag):
 def potrf(K, zero_upper=True, check=True):
     """Returns the lower Cholesky factor of K (K is not modified)."""
     L = _prep(K).clone()
+    if L.numel() == 0:
+        return L
     h = handle_for(L)
     info = ctypes.c_int(0)
     vl = view(L)
@@ -78,6 +87,8 @@ def potrf(K, zero_upper=True, check=True):
 
 def trsm_rlt_(L, B):
     """In place B <- B L^-T."""
+    if B.numel() == 0:
+        return B
     h = handle_for(B)
     vl, vb = view(_prep(L)), view(B)
     h.check(h.lib.gps_trsm_rlt(h.ptr, vl.ref, vb.ref))
@@ -90,6 +101,8 @@ _U_CACHE = {}
 def tri_inv_t(L):
     """U = L^-T (upper triangular).  Cached per factor: backward passes reuse it."""
     L = _prep(L)
+    if L.numel() == 0:
+        return L.clone()
     key = (L.data_ptr(), L._version, tuple(L.shape))
     hit = _U_CACHE.get(key)
     if hit is not None and hit[0]() is L:
@@ -472,6 +485,8 @@ def gpr_predict(prog, X, Yc, noise, Xnew, full_cov=False):
     ns, r = Xnew.shape[0], Yc.shape[1]
     mean = torch.empty((ns, r), dtype=F64, device=X.device)
     var = torch.empty((ns, ns) if full_cov else (ns,), dtype=F64, device=X.device)
+    if ns == 0:
+        return mean, var
     info = ctypes.c_int(0)
     vt, vx, vy, vn, vm, vv = view(theta), view(X), view(Yc), view(Xnew), view(mean), view(var)
     h.check(h.lib.gps_gpr_predict(h.ptr, ctypes.byref(prog.desc), vt.ref, vx.ref, vy.ref,

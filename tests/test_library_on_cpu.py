@@ -108,6 +108,46 @@ def test_not_positive_definite_is_reported_through_the_abi(gpf):
         ops.potrf(S)
 
 
+def test_argument_checks_and_error_reporting_of_the_abi(gpf):
+    """Bad shapes / dtypes / layouts come back as -(argument index) with a message from
+    gps_last_error ("every function returns int status"), empty inputs are
+    no-ops, and the library never touches what it is not given."""
+    import ctypes
+    from gpflowSlim._backend import lib, ops
+    with pytest.raises(ValueError, match='K mismatch'):
+        ops.gemm_nt(conv(np.zeros((3, 4))), conv(np.zeros((3, 5))))
+    with pytest.raises(ValueError, match='column'):
+        gpf.kernels.RBF(4).K(conv(np.zeros((5, 2))))               # active dims beyond X's columns
+    with pytest.raises(TypeError):
+        lib.view(torch.zeros(2, 2, dtype=torch.float32))
+    h = lib.handle_for(None)
+    A = conv(np.eye(4))
+    va, vi = lib.view(A), lib.view(torch.zeros(4, dtype=torch.int64))
+    rc = h.lib.gps_potrf(h.ptr, vi.ref, 1, None)                    # int64 where float64 is required
+    assert rc == -2 and b'float64' in h.lib.gps_last_error(h.ptr)
+    rc = h.lib.gps_transpose(h.ptr, va.ref, lib.view(conv(np.zeros((3, 4)))).ref)
+    assert rc == -3 and b'shape' in h.lib.gps_last_error(h.ptr)
+    with pytest.raises(ValueError, match='unknown option'):
+        h.set_option('no_such_option', 1)
+    assert h.lib.gps_potrf(None, va.ref, 1, None) == -1             # null handle
+    # empty inputs
+    X = conv(np.random.default_rng(0).standard_normal((7, 2)))
+    k = gpf.kernels.Matern52(2) + gpf.kernels.Linear(2)
+    assert k.K(X[:0], X).shape == (0, 7) and k.K(X, X[:0]).shape == (7, 0) and k.Kdiag(X[:0]).shape == (0,)
+    assert ops.potrf(conv(np.zeros((0, 0)))).shape == (0, 0)
+    L = ops.potrf(conv(np.eye(5) * 4.0))
+    assert ops.trsm_rlt_(L, conv(np.zeros((0, 5)))).shape == (0, 5)
+    assert ops.gemm_nt(conv(np.zeros((0, 3))), conv(np.ones((4, 3)))).shape == (0, 4)
+    assert float(ops.gemm_nt(conv(np.zeros((2, 0))), conv(np.zeros((3, 0)))).abs().max()) == 0.0
+    # a model asked to predict at no points at all (models/gpr.py:118-131), fused and op-by-op
+    Xd, Yd = cases.synth_gpr(40, 2, seed=1)
+    for fused in (True, False):
+        m = gpf.models.GPR(conv(Xd), conv(Yd), kern=gpf.kernels.RBF(2), fused=fused)
+        with torch.no_grad():
+            mu, var = m.predict_f(conv(np.zeros((0, 2))))
+        assert mu.shape == (0, 1) and var.shape == (0, 1)
+
+
 def test_gemm_flags_through_the_launch_code(gpf):
     from gpflowSlim._backend import ops
     rng = np.random.default_rng(5)
