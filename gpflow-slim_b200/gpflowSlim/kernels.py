@@ -76,7 +76,8 @@ class _Builder(object):
     def finalize(self, out):
         P = len(self.prims)
         if P < 1:
-            raise ValueError('a kernel expression needs at least one kernel')
+            # e.g. a Constant on its own: nothing for the Gram kernel to evaluate per element
+            raise KernelTooLarge('an expression without any input-dependent kernel is not worth a fused launch')
         if P > _lib.GPS_MAX_PRIMS or len(self.ops) > _lib.GPS_MAX_OPS \
                 or P + self.n_results > _lib.GPS_MAX_SLOTS or self.n_theta > _MAX_THETA_FUSED:
             raise KernelTooLarge('kernel expression too large for the fused Gram kernel')
@@ -276,12 +277,24 @@ class White(Static):
 
 
 class Constant(Static):
-    """variance everywhere (kernels.py:341-350)."""
+    """variance everywhere (kernels.py:341-350).  Fusable: it compiles to the constant op of the
+    Gram program, exactly like the scalar in `kern + 0.37`."""
+
+    def _emit(self, b, presliced=False):
+        return b.op(_lib.GPS_OP_CONST, b.theta(lambda: self.variance, 1))
+
+    def _K_composed(self, X, X2, presliced):
+        m = X.shape[0] if X2 is None else X2.shape[0]
+        return X.new_ones((X.shape[0], m)) * self.variance.squeeze()
+
+    def _Kdiag_composed(self, X, presliced):
+        return torch.ones_like(X[:, 0]) * self.variance
 
     def K(self, X, X2=None, presliced=False):
-        X = to_tensor(X)
-        m = X.shape[0] if X2 is None else to_tensor(X2).shape[0]
-        return X.new_ones((X.shape[0], m)) * self.variance.squeeze()
+        return Kernel.K(self, X, X2, presliced)
+
+    def Kdiag(self, X, presliced=False):
+        return Kernel.Kdiag(self, X, presliced)
 
 
 class Bias(Constant):
@@ -846,6 +859,18 @@ class Combination(Kernel):
 class Sum(Combination):
     _op = _lib.GPS_OP_ADD
     _torch_op = staticmethod(torch.add)
+
+    def split_white(self):
+        """(kernel of everything but the top-level White terms or None, [White kernels]).  A
+        White term only adds its variance to the diagonal of K(X), so the fused GPR objective can
+        fold it into the noise it already adds there (models/gpr.py)."""
+        whites = [k for k in self.kern_list if type(k) is White]
+        rest = [k for k in self.kern_list if type(k) is not White]
+        if not whites or not rest:
+            return (self if not whites else None), whites
+        if len(rest) == 1 and not self.const_list:
+            return rest[0], whites
+        return Sum(rest + list(self.const_list)), whites
 
 
 class Product(Combination):

@@ -21,13 +21,28 @@ class GPR(GPModel):
         GPModel.__init__(self, X, Y, kern, likelihood, mean_function, **kwargs)
         self.num_latent = self.Y.shape[1] if num_latent is None else num_latent
         self.fused = fused
+        self._split = None
+
+    def _core_and_white(self):
+        """(covariance without its top-level White terms, summed White variance or None):
+        `RBF + White` is the RBF with the white variance added to the noise on the diagonal."""
+        core, whites = self.kern, []
+        if hasattr(self.kern, 'split_white'):
+            if self._split is None:
+                self._split = self.kern.split_white()
+            core, whites = self._split
+        extra = None
+        for w in whites:
+            extra = w.variance.reshape(()) if extra is None else extra + w.variance.reshape(())
+        return core, extra
 
     def _fusable(self, *tensors):
         if not self.fused or self.Y.shape[1] > 16:
             return False
         if any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
             return False
-        return bool(getattr(self.kern, 'fusable', False))     # cached by the kernel object
+        core, _ = self._core_and_white()
+        return bool(core is not None and getattr(core, 'fusable', False))     # cached by the kernel object
 
     def _feature_map(self):
         """`kern.features` if the covariance is an explicit feature expansion K = C C^T
@@ -45,7 +60,9 @@ class GPR(GPModel):
                                                                             device=self.X.device)
             return multivariate_normal_feature(self.Y, m, features(self.X), var)
         if self._fusable(self.X):
-            return _ops.gpr_loglik(self.kern.program(), self.X, self.Y - m, self.likelihood.variance)
+            core, white = self._core_and_white()
+            noise = self.likelihood.variance if white is None else self.likelihood.variance.reshape(()) + white
+            return _ops.gpr_loglik(core.program(), self.X, self.Y - m, noise)
         n = self.X.shape[0]
         K = self.kern.K(self.X) + torch.eye(n, dtype=self.X.dtype, device=self.X.device) \
             * self.likelihood.variance
@@ -60,8 +77,13 @@ class GPR(GPModel):
         if features is not None:
             return self._build_predict_features(features, Xnew, full_cov)
         if self._fusable(self.X, Xnew) and not torch.is_grad_enabled():
-            mean, var = _ops.gpr_predict(self.kern.program(), self.X, self.Y - self.mean_function(self.X),
-                                         self.likelihood.variance, Xnew, full_cov=full_cov)
+            core, white = self._core_and_white()
+            noise = self.likelihood.variance if white is None else self.likelihood.variance.reshape(()) + white
+            mean, var = _ops.gpr_predict(core.program(), self.X, self.Y - self.mean_function(self.X),
+                                         noise, Xnew, full_cov=full_cov)
+            if white is not None:        # K(X*, X*) / Kdiag(X*) of the full covariance include the white term
+                var = var + (torch.eye(var.shape[0], dtype=var.dtype, device=var.device) * white if full_cov
+                             else white)
             fmean = mean + self.mean_function(Xnew)
             if full_cov:
                 return fmean, var.unsqueeze(2).expand(-1, -1, r)

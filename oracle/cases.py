@@ -182,6 +182,26 @@ def case_gpr_composed(gpf, conv):
     return out, [('objective', m)]
 
 
+def case_gpr_white(gpf, conv):
+    """The common `RBF + White + Bias` covariance in a GPR (kernels.py:328-357, :1071-1077): the
+    White term puts its variance on the diagonal of K(X) only, the Bias term is a constant --
+    both are foldable into the fused one-call objective (White into the noise, Bias as a constant
+    op).  Objective, all five gradients, predictions incl. full covariance."""
+    n, d = 180, 3
+    X, Y = synth_gpr(n, d, seed=25)
+    Y = np.concatenate([Y, np.cos(X[:, :1]) + 0.05 * np.random.default_rng(26).standard_normal((n, 1))], 1)
+    Xs = np.random.default_rng(27).standard_normal((13, d))
+    k = gpf.kernels
+    kern = k.RBF(d, ARD=True, lengthscales=1.6, variance=1.1, name='gw_a') + k.White(d, variance=0.05, name='gw_b') \
+        + k.Bias(d, variance=0.3, name='gw_c')
+    m = gpf.models.GPR(conv(X), conv(Y), kern=kern, obs_var=0.07, name='gw')
+    out = {'objective': m.objective, 'K': kern.K(conv(X[:9])), 'K2': kern.K(conv(X[:9]), conv(Xs)),
+           'Kdiag': kern.Kdiag(conv(Xs))}
+    out['pred_mu'], out['pred_var'] = m.predict_f(conv(Xs))
+    out['full_mu'], out['full_cov'] = m.predict_f_full_cov(conv(Xs))
+    return out, [('objective', m)]
+
+
 def case_large_d(gpf, conv):
     """Inputs wider than the fused Gram kernel's per-primitive table (40 columns; the reference's
     examples/svgp.py feeds 100 network features): Grams, parameter and input gradients of the
@@ -732,6 +752,7 @@ CASES = {
     'kernels_extra': case_kernels_extra,
     'gpr_composed': case_gpr_composed,
     'large_d': case_large_d,
+    'gpr_white': case_gpr_white,
     'gpr_features': case_gpr_features,
     'priors': case_priors,
     'mc_models': case_mc_models,
@@ -757,7 +778,7 @@ CASES = {
 # Cases added after the last session that had GPU time.  tests/test_gpu_parity.py runs the rest,
 # tests/test_gpu_zz_widened.py (sorted last, so a surprise there cannot mask the established
 # tests under `pytest -x`) runs these; once seen green on a B200 they simply leave this tuple.
-LATE_CASES = ('kernels_extra', 'gpr_composed', 'lbfgs', 'gpr_features', 'priors', 'mc_models', 'likelihoods_extra', 'large_d')
+LATE_CASES = ('kernels_extra', 'gpr_composed', 'lbfgs', 'gpr_features', 'priors', 'mc_models', 'likelihoods_extra', 'large_d', 'gpr_white')
 # Pure host logic (no library call): checked on the CPU only.
 HOST_ONLY_CASES = ('lbfgs_rosenbrock',)
 

@@ -174,3 +174,47 @@ def test_expressions_too_large_for_the_fused_kernel_fall_back_to_composed(monkey
     Xg = X40.clone().requires_grad_(True)
     assert not narrow._use_fused(Xg) and narrow._use_fused(X40)
     g.settings.device = None
+
+
+def test_white_and_bias_terms_keep_the_gpr_on_the_fused_path(monkeypatch):
+    """`RBF + White + Bias`: the Bias compiles to a constant op, the White variance is folded into
+    the noise of the one-call objective -- ONE gpr_loglik call, no Cholesky op; a covariance made of
+    White terms only, or one containing a composed kernel, takes the op-by-op path."""
+    import cpu_ops_double
+    g = gpf()
+    k = g.kernels
+    ops = cpu_ops_double.install(monkeypatch)
+    g.settings.device = 'cpu'
+    calls = {'fused': 0, 'chol': 0}
+    real_ll, real_chol = ops.gpr_loglik, ops.cholesky
+
+    def ll(prog, X, Yc, noise):
+        calls['fused'] += 1
+        assert prog.desc.n_prims == 1 and prog.desc.n_ops == 2          # RBF, CONST, ADD
+        return real_ll(prog, X, Yc, noise)
+
+    def chol(K):
+        calls['chol'] += 1
+        return real_chol(K)
+    monkeypatch.setattr(ops, 'gpr_loglik', ll)
+    monkeypatch.setattr(ops, 'cholesky', chol)
+    X, Y = cases.synth_gpr(40, 2, seed=3)
+    kern = k.RBF(2, ARD=True) + k.White(2, variance=0.05) + k.Bias(2, variance=0.3)
+    m = g.models.GPR(X, Y, kern=kern)
+    obj = m.objective
+    grads = torch.autograd.grad(obj, [p.unconstrained_tensor for p in m.parameters])
+    assert calls == {'fused': 1, 'chol': 0}
+    white_grad, noise_grad = grads[2], grads[4]          # parameters: rbf var, ls, white var, bias var, noise
+    # d/d(white variance) and d/d(noise variance) are the same trace term, times each softplus slope
+    sig = lambda p: torch.sigmoid(p.unconstrained_tensor.detach())
+    np.testing.assert_allclose(float(white_grad / sig(m.parameters[2])), float(noise_grad / sig(m.parameters[4])),
+                               rtol=1e-12)
+    # same numbers as the op-by-op evaluation
+    m2 = g.models.GPR(X, Y, kern=k.RBF(2, ARD=True) + k.White(2, variance=0.05) + k.Bias(2, variance=0.3), fused=False)
+    np.testing.assert_allclose(float(obj), float(m2.objective), rtol=1e-12)
+    assert calls['chol'] == 1
+    for kern2 in (k.White(2), k.RBF(2) + k.RatQuad(2) + k.White(2)):
+        calls.update(fused=0, chol=0)
+        g.models.GPR(X, Y, kern=kern2).objective
+        assert calls == {'fused': 0, 'chol': 1}
+    g.settings.device = None

@@ -194,8 +194,8 @@ def test_autograd_adjoints_on_the_real_kernels(gpf):
 #   kernels 1 [8e-16], kernels_extra 8 [1e-13], svgp_white_diag 8 [4e-14], nkn 15 [2e-15],
 #   svgp_nonwhite_diag 16 [3e-12], functions 19 [4e-13], gpr_features 19 [1e-10], mc_models 32 [1e-10],
 #   sgpr 41 [1e-12], gpr_composed 65 [2e-14], gpr_misc 69 [2e-14], likelihoods_extra 0.2 [0], priors 5 [2e-15],
-#   large_d 43 [4e-15], lbfgs 225 [2e-12]  (mc_models, likelihoods_extra, large_d had never run on a GPU then)
-_DEFAULT_CASES = ['kernels', 'svgp_white_diag', 'nkn']
+#   large_d 43 [4e-15], lbfgs 225 [2e-12], gpr_white 15 [5e-14]  (mc_models, likelihoods_extra, large_d had never run on a GPU then)
+_DEFAULT_CASES = ['kernels', 'svgp_white_diag', 'nkn', 'gpr_white']
 _FULL_CASES = ['kernels_extra', 'svgp_nonwhite_diag', 'functions', 'gpr_features', 'mc_models', 'sgpr',
                'gpr_composed', 'gpr_misc', 'likelihoods_extra', 'priors', 'large_d', 'lbfgs']
 
