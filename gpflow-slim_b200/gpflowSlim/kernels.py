@@ -841,6 +841,12 @@ class Combination(Kernel):
 
     def _K_composed(self, X, X2, presliced):
         part, rest = self._split()
+        if X2 is not None and self._op == _lib.GPS_OP_ADD and len(self.kern_list) > 1:
+            # a White term of a SUM contributes an all-zero cross-covariance (kernels.py:336-338):
+            # skip the N x M zeros instead of allocating and adding them
+            keep = [k for k in rest if type(k) is not White]
+            if part is not None or keep:
+                rest = keep
         if part is self:          # everything is fusable in principle, but the whole is too large / needs d/dX
             vals = [k.K(X, X2) for k in self.kern_list]
         else:
