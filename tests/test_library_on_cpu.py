@@ -264,3 +264,95 @@ def test_experimental_switches_through_the_real_dispatch_code(gpf, golden):
     finally:
         ops.TRI_AWARE_ADJOINTS[0] = False
 
+
+# ----------------------------------------------------------------------------- distributed path
+def _dist_worker(rank, world, port, so_path, n, r, block, out_q):
+    """One rank of the REAL distributed GPR algorithm (_backend/dist_gpr.py: block-row layout,
+    look-ahead schedule, panel broadcasts / all-gathers, inverse rows, gradient contraction) on
+    the REAL kernels (gps_gemm_nt_rowmap, gps_trsm_rl{t,n}_prefix, gps_gpr_weight_rows, ...) of the
+    CPU build, with gloo instead of NCCL and issue-order execution instead of CUDA streams."""
+    import contextlib
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (here, os.path.dirname(here), os.path.join(os.path.dirname(here), 'gpflow-slim_b200')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    import gpflowSlim
+    from gpflowSlim._backend import dist_gpr, lib, ops
+    from oracle import ref_torch as R
+    torch.set_num_threads(1)
+    lib.LIB_PATH = so_path
+
+    class CpuHandle(lib.Handle):
+        def sync_stream(self):
+            pass
+    holder = []
+
+    def handle_for(_):
+        if not holder:
+            holder.append(CpuHandle(0))
+        return holder[0]
+    lib.handle_for = ops.handle_for = handle_for
+    gpflowSlim.settings.device = 'cpu'
+
+    class CpuLibBackend(dist_gpr.CudaBackend):
+        poison = True                      # NaN-filled buffers: reads of never-written data show up
+
+        def __init__(self):
+            self._L, self.device = lib, torch.device('cpu')
+
+        def streams(self):
+            return 'main', 'chain', 'gather'
+
+        def on(self, stream):
+            return contextlib.nullcontext()
+
+        def record(self, stream):
+            return None
+
+        def wait(self, stream, event):
+            pass
+    if world > 1:
+        dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
+    d = 3
+    X, Y = cases.synth_gpr(n, d)
+    rng = np.random.default_rng(5)
+    Y = np.concatenate([Y] + [rng.standard_normal((n, 1)) for _ in range(r - 1)], 1)
+    kern = gpflowSlim.kernels.RBF(d, ARD=True, lengthscales=1.7, variance=1.3)
+    prog = kern.program()
+    theta = prog.theta('cpu').detach()
+    nlml, dth, dnz, dY = dist_gpr.nlml_and_grad(prog, theta, 0.1, torch.tensor(X), torch.tensor(Y), block=block,
+                                                backend=CpuLibBackend(), lookahead=True)
+    th = theta.clone().requires_grad_(True)
+    nz = torch.tensor(0.1, dtype=torch.float64, requires_grad=True)
+    Yt = torch.tensor(Y, requires_grad=True)
+    obj = R.gpr_nlml(dict(type='rbf', variance=th[0], lengthscales=th[1:1 + d]), torch.tensor(X), Yt, nz)
+    g = torch.autograd.grad(obj, [th, nz, Yt])
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    out_q.put((rank, [rel(nlml, obj.detach()), rel(dth, g[0]), rel(dnz, g[1]), rel(dY, g[2])]))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,n,r,block', [(2, 300, 1, 128)] + ([(1, 330, 2, 128), (3, 420, 1, 128)] if FULL else []))
+def test_distributed_gpr_on_the_real_kernels_under_gloo(cpu_lib, world, n, r, block):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dist_worker, args=(i, world, port, cpu_lib, n, r, block, q)) for i in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=900) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, errs in res:
+        assert max(errs) < 1e-9, (rank, errs)
+
