@@ -39,6 +39,10 @@ enum WsSlot {
   WS_INVW,        // triangular inverse: W = -U11 L21^T of the current recursion node
   WS_INVT,        // triangular inverse: T22 = U22^T of the current recursion node
   WS_ROWLO,       // prefix solves: per-row first column (device copy)
+  WS_ADJ_U,       // adjoint entry points (adjoint.cu): U = L^-T when the caller does not supply it
+  WS_ADJ_A,       // ... three n x ld scratch matrices
+  WS_ADJ_B,
+  WS_ADJ_C,
   WS_COUNT
 };
 

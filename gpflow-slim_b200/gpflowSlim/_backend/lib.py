@@ -79,6 +79,9 @@ SIGNATURES = {
     'gps_kdiag_fwd': [_H, _D, _T, _T, _T],
     'gps_kdiag_bwd': [_H, _D, _T, _T, _T, _T, _T],
     'gps_potrf': [_H, _T, ctypes.c_int, _P(ctypes.c_int)],
+    'gps_potri': [_H, _T, _T],
+    'gps_chol_bwd': [_H, _T, _T, _T, _T],
+    'gps_trsm_bwd': [_H, _T, _T, _T, _T, _T, _T],
     'gps_trsm_rlt': [_H, _T, _T],
     'gps_tri_inv_t': [_H, _T, _T],
     'gps_gemm_nt': [_H, ctypes.c_double, _T, _T, ctypes.c_double, _T, ctypes.c_int, ctypes.c_int,

@@ -127,6 +127,49 @@ def row_sumsq(A):
     return out
 
 
+# ------------------------------------------------------------------------- library-side adjoints
+# gps_potri / gps_chol_bwd / gps_trsm_bwd (csrc/adjoint.cu) do in one call what the autograd
+# Functions below compose from gps_tri_inv_t + gps_gemm_nt + transposes.  EXPERIMENTAL switch, off
+# until seen green on a GPU (the CPU build of the library runs both settings): with it on, the
+# backward of `cholesky` and `trsm_rlt` is one ctypes round trip each.
+FUSED_ADJOINTS = [False]
+
+
+def potri(L):
+    """(L L^T)^-1, lower triangle (the strict upper part of the result is zero)."""
+    L = _prep(L)
+    out = torch.zeros_like(L, memory_format=torch.contiguous_format)
+    if L.numel():
+        h = handle_for(L)
+        vl, vo = view(L), view(out)
+        h.check(h.lib.gps_potri(h.ptr, vl.ref, vo.ref))
+    return out
+
+
+def chol_bwd(L, Lbar, U=None):
+    """Adjoint of L = chol(A): sym(L^-T Phi(L^T tril(Lbar)) L^-1)."""
+    L, Lbar = _prep(L), _prep(Lbar)
+    out = torch.empty_like(L, memory_format=torch.contiguous_format)
+    if L.numel():
+        h = handle_for(L)
+        vl, vb, vu, vo = view(L), view(Lbar), view(U), view(out)
+        h.check(h.lib.gps_chol_bwd(h.ptr, vl.ref, vb.ref, ref(vu), vo.ref))
+    return out
+
+
+def trsm_bwd(L, X, Xbar, U=None, want_lbar=True):
+    """Adjoint of X = B L^-T: (Bbar = Xbar L^-1, Lbar = -tril(Bbar^T X) or None)."""
+    L, X, Xbar = _prep(L), _prep(X), _prep(Xbar)
+    Bbar = torch.empty_like(X, memory_format=torch.contiguous_format)
+    Lbar = torch.empty_like(L, memory_format=torch.contiguous_format) if want_lbar else None
+    if X.numel() == 0:
+        return Bbar, (torch.zeros_like(L) if want_lbar else None)
+    h = handle_for(L)
+    vl, vx, vxb, vu, vb, vlb = view(L), view(X), view(Xbar), view(U), view(Bbar), view(Lbar)
+    h.check(h.lib.gps_trsm_bwd(h.ptr, vl.ref, vx.ref, vxb.ref, ref(vu), vb.ref, ref(vlb)))
+    return Bbar, Lbar
+
+
 # ------------------------------------------------------------------------- autograd Functions
 # EXPERIMENTAL switch (off until seen green on a GPU; the CPU tests run both settings): let the
 # adjoint of a triangular-aware product skip the zero tiles too.  With C = tri_a(A) tri_b(B)^T:
@@ -228,6 +271,8 @@ class _Cholesky(torch.autograd.Function):
     @staticmethod
     def backward(ctx, Lbar):
         (L,) = ctx.saved_tensors
+        if FUSED_ADJOINTS[0]:
+            return chol_bwd(L, Lbar, tri_inv_t(L))
         Lbar = torch.tril(_prep(Lbar))
         U = tri_inv_t(L)
         # P = Phi(L^T Lbar):  (L^T Lbar)[m,n] = sum_k Lt[m,k] Lbar_t[n,k]
@@ -260,6 +305,9 @@ class _TrsmRLT(torch.autograd.Function):
         X, L = ctx.saved_tensors
         Xbar = _prep(Xbar)
         U = tri_inv_t(L)
+        if FUSED_ADJOINTS[0]:
+            Bbar, dL = trsm_bwd(L, X, Xbar, U, want_lbar=ctx.needs_input_grad[1])
+            return (Bbar if ctx.needs_input_grad[0] else None), dL
         # Bbar = Xbar L^-1 = Xbar U^T
         Bbar = gemm_nt(Xbar, U, b_tri=TRI_UPPER)
         dL = None

@@ -176,6 +176,30 @@ int gps_gemm_nt(gps_handle* h, double alpha, const DLTensor* A, const DLTensor* 
                 DLTensor* C, int a_tri, int b_tri, int c_uplo);
 int gps_transpose(gps_handle* h, const DLTensor* A, DLTensor* At_out);
 
+/* ---- adjoints of the factorisation / the triangular solve, and K^-1 from the factor ------
+ * (the gps_potri / gps_chol_bwd / gps_trsm_bwd of the SURVEY.md 8(b) sketch; csrc/adjoint.cu.)
+ * The reference has no such code: TensorFlow's registered gradients of tf.cholesky and
+ * tf.matrix_triangular_solve run when optimizer.minimize differentiates the objective
+ * (examples/gpr.py:53-54, examples/svgp.py:160-161).  L must be lower triangular WITH zeros above
+ * the diagonal (gps_potrf with zero_upper = 1).  `U` is optional everywhere: pass the output of
+ * gps_tri_inv_t(L) to share one triangular inverse between several adjoints of the same factor,
+ * or NULL to have it computed into the handle's workspace.
+ * gps_potri:    Kinv_out (lower triangle only; the strict upper part is not written) = (L L^T)^-1.
+ * gps_chol_bwd: Abar_out = sym(L^-T Phi(L^T tril(Lbar)) L^-1), the adjoint of L = chol(A)
+ *               (tf.cholesky call sites: models/gpr.py:70,121, conditionals.py:84,
+ *               kullback_leiblers.py:53, models/sgpr.py:136,143,170,173).
+ * gps_trsm_bwd: for X = B L^-T (gps_trsm_rlt):  Bbar_out = Xbar L^-1  and, if Lbar_out is not
+ *               NULL,  Lbar_out = -tril(Bbar^T X)  (the tf.matrix_triangular_solve call sites
+ *               densities.py:82, conditionals.py:87, kullback_leiblers.py:54,93, ...).
+ * Status: written at the end of round 1 without GPU access; exercised through the CPU build of
+ * the library (tests/test_library_on_cpu.py); the Python layer calls them only when
+ * ops.FUSED_ADJOINTS is switched on. */
+int gps_potri(gps_handle* h, const DLTensor* L, DLTensor* Kinv_out);
+int gps_chol_bwd(gps_handle* h, const DLTensor* L, const DLTensor* Lbar, const DLTensor* U /* may be NULL */,
+                 DLTensor* Abar_out);
+int gps_trsm_bwd(gps_handle* h, const DLTensor* L, const DLTensor* X, const DLTensor* Xbar,
+                 const DLTensor* U /* may be NULL */, DLTensor* Bbar_out, DLTensor* Lbar_out /* may be NULL */);
+
 /* ---- building blocks of the block-row distributed GPR (one process per GPU) ---------------
  * The multi-GPU path (gpflowSlim/_backend/dist_gpr.py) distributes the rows of K over the
  * ranks in blocks; NCCL moves the panels, these entry points do the arithmetic.

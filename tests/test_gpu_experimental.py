@@ -163,3 +163,33 @@ def test_tri_aware_adjoints_match_reference_golden(golden, name, monkeypatch):
         e = relerr(res[key], gold[key])
         assert e < (1e-12 if key.startswith('param/') else 1e-8), '%s:%s %.3e' % (name, key, e)
 
+
+def test_library_side_adjoints_on_the_gpu(golden, monkeypatch):
+    """gps_potri / gps_chol_bwd / gps_trsm_bwd (csrc/adjoint.cu) against torch autograd, then two
+    golden cases with ops.FUSED_ADJOINTS on."""
+    import gpflowSlim as gpf
+    from gpflowSlim._backend import ops
+    from util import relerr
+    rng = np.random.default_rng(3)
+    n, m = 700, 300
+    A = rng.standard_normal((n, n + 3))
+    S = conv(A @ A.T / (n + 3) + 0.5 * np.eye(n)).requires_grad_(True)
+    B = conv(rng.standard_normal((m, n))).requires_grad_(True)
+    Lbar_in, Xbar_in = conv(rng.standard_normal((n, n))), conv(rng.standard_normal((m, n)))
+    L = torch.linalg.cholesky(S)
+    X = torch.linalg.solve_triangular(L, B.t(), upper=False).t()
+    (want_A,) = torch.autograd.grad((L * torch.tril(Lbar_in)).sum(), [S], retain_graph=True)
+    want_B, = torch.autograd.grad((X * Xbar_in).sum(), [B], retain_graph=True)
+    Ld = L.detach()
+    for U in (None, ops.tri_inv_t(Ld)):
+        assert_close(ops.chol_bwd(Ld, Lbar_in, U), 0.5 * (want_A + want_A.t()), 1e-10, 'chol_bwd')
+        assert_close(ops.trsm_bwd(Ld, X.detach(), Xbar_in, U)[0], want_B, 1e-10, 'trsm_bwd Bbar')
+    assert_close(ops.potri(Ld), torch.tril(torch.linalg.inv(S.detach())), 1e-9, 'potri')
+    monkeypatch.setattr(ops, 'FUSED_ADJOINTS', [True])
+    for name in ('svgp_white_full', 'sgpr'):
+        gold = golden(name)
+        res = cases.run_case(gpf, name, conv)
+        for key in sorted(gold):
+            e = relerr(res[key], gold[key])
+            assert e < (1e-12 if key.startswith('param/') else 1e-8), '%s:%s %.3e' % (name, key, e)
+

@@ -190,6 +190,36 @@ def test_autograd_adjoints_on_the_real_kernels(gpf):
         assert float((a - b).abs().max()) < 1e-10 * max(1.0, float(b.abs().max()))
 
 
+@pytest.mark.parametrize('n,m', [(70, 33), (200, 140), (1, 1)])
+def test_library_side_adjoints(gpf, n, m):
+    """gps_potri / gps_chol_bwd / gps_trsm_bwd (csrc/adjoint.cu), with U computed inside and with
+    a caller-supplied U, against torch autograd and a dense inverse."""
+    from gpflowSlim._backend import ops
+    rng = np.random.default_rng(n + m)
+    A = rng.standard_normal((n, n + 3))
+    S = conv(A @ A.T / (n + 3) + 0.5 * np.eye(n)).requires_grad_(True)
+    B = conv(rng.standard_normal((m, n))).requires_grad_(True)
+    Lbar_in, Xbar_in = conv(rng.standard_normal((n, n))), conv(rng.standard_normal((m, n)))
+    L = torch.linalg.cholesky(S)
+    X = torch.linalg.solve_triangular(L, B.t(), upper=False).t()
+    (want_A,) = torch.autograd.grad((L * torch.tril(Lbar_in)).sum(), [S], retain_graph=True)
+    want_A = 0.5 * (want_A + want_A.t())
+    Lleaf = L.detach().clone().requires_grad_(True)
+    Xl = torch.linalg.solve_triangular(Lleaf, B.detach().t(), upper=False).t()
+    want_L, = torch.autograd.grad((Xl * Xbar_in).sum(), [Lleaf])
+    want_B, = torch.autograd.grad((X * Xbar_in).sum(), [B], retain_graph=True)
+    Ld = L.detach()
+    close = lambda a, b: np.testing.assert_allclose(a.numpy(), b.detach().numpy(), rtol=0,
+                                                    atol=1e-10 * max(1.0, float(b.abs().max())))
+    for U in (None, ops.tri_inv_t(Ld)):
+        close(ops.chol_bwd(Ld, Lbar_in + torch.triu(torch.full((n, n), 9.0, dtype=torch.float64), 1), U), want_A)
+        Bbar, Lb = ops.trsm_bwd(Ld, X.detach(), Xbar_in, U)
+        close(Bbar, want_B)
+        close(Lb, torch.tril(want_L))
+        assert ops.trsm_bwd(Ld, X.detach(), Xbar_in, U, want_lbar=False)[1] is None
+    close(ops.potri(Ld), torch.tril(torch.linalg.inv(S.detach())))
+
+
 # case -> seconds on 8 host cores when this was written (all clean, worst relative error in brackets):
 #   kernels 1 [8e-16], kernels_extra 8 [1e-13], svgp_white_diag 8 [4e-14], nkn 15 [2e-15],
 #   svgp_nonwhite_diag 16 [3e-12], functions 19 [4e-13], gpr_features 19 [1e-10], mc_models 32 [1e-10],
@@ -263,6 +293,12 @@ def test_experimental_switches_through_the_real_dispatch_code(gpf, golden):
         check('svgp_nonwhite_diag')
     finally:
         ops.TRI_AWARE_ADJOINTS[0] = False
+    ops.FUSED_ADJOINTS[0] = True             # backward of cholesky / trsm_rlt in one library call each
+    try:
+        check('svgp_white_diag')
+        check('functions')
+    finally:
+        ops.FUSED_ADJOINTS[0] = False
 
 
 # ----------------------------------------------------------------------------- distributed path
