@@ -309,8 +309,11 @@ def _layout_maps(lay, P, dev):
     lo_table = torch.tensor([[l for l, _ in row] for row in below_all], dtype=torch.int64)
     if len(_MAPS) > 8:
         _MAPS.clear()
-    hit = _MAPS[key] = (own.to(dev), lrow.to(dev), below_all, lo_table.to(dev))
+    hit = _MAPS[key] = (own.to(dev), lrow.to(dev), below_all, lo_table.to(dev), {})
     return hit
+
+
+_FLOPS_CACHE = {}
 
 
 def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
@@ -350,7 +353,7 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
     # outside those triangles is never written and never read
     Lfull = be.empty(N, ld)
     Lt = be.empty(N, ld)
-    own_of_row, lrow_of_row, below_all, lo_table = _layout_maps(lay, P, dev)
+    own_of_row, lrow_of_row, below_all, lo_table, unpack_index = _layout_maps(lay, P, dev)
 
     Lkk_buf = be.empty(bs * bs)
     top_buf = be.empty(bs * bs)
@@ -359,6 +362,7 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
     recv_buf = be.empty(P * mmax_all * bs) if P > 1 else None
 
     import numpy as np
+    flops_cache = _FLOPS_CACHE.setdefault((lay.n, lay.block, P, rank, R), {})
 
     def update(k, c_lo, c_hi, Bsrc=None):
         """my rows below block row k, global columns [c_lo, c_hi):  A -= P_k L[c_lo:c_hi, k]^T,
@@ -368,11 +372,19 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
             return
         k0, k1 = lay.rows(k)
         lo, mrows = below_all[k][rank]
-        flops = 2.0 * (k1 - k0) * R * (c_hi - c_lo)            # algorithmic flops of this launch
-        for b in mine:
-            if b > k:
-                g = np.arange(*lay.rows(b))
-                flops += 2.0 * (k1 - k0) * float(np.clip(np.minimum(g, c_hi - 1) - c_lo + 1, 0, None).sum())
+        # algorithmic flops of this launch (what the profile option books): a pure function of
+        # the layout, so it is computed once per (layout, rank, R) and looked up afterwards --
+        # the chain stream's critical path is host-issue bound at 8 ranks, and this loop used to
+        # cost ~0.2 ms of host time per panel
+        fkey = (k, c_lo, c_hi)
+        flops = flops_cache.get(fkey)
+        if flops is None:
+            flops = 2.0 * (k1 - k0) * R * (c_hi - c_lo)
+            for b in mine:
+                if b > k:
+                    g = np.arange(*lay.rows(b))
+                    flops += 2.0 * (k1 - k0) * float(np.clip(np.minimum(g, c_hi - 1) - c_lo + 1, 0, None).sum())
+            flops_cache[fkey] = flops
         Bop = Lfull[c_lo:c_hi, k0:k1] if Bsrc is None else Bsrc
         be.gemm_rowmap_(Aloc[lo:, k0:k1], Bop, Aloc[lo:, c_lo:c_hi], grow[lo:], c_lo, flops)
 
@@ -412,8 +424,12 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
                 send[mrows:].zero_()                # padding rows are never unpacked; keep them finite
             recv = recv_buf[:P * mmax * nb]
             comm.all_gather(recv, send.reshape(-1))
-            oq = own_of_row[r1:]
-            src = oq * mmax + lrow_of_row[r1:] - lo_table[k][oq]
+            src = unpack_index.get(k)
+            if src is None:
+                # row of the gathered buffer that holds global row r (static per layout and
+                # panel: built once, it saves five small launches per panel on the gather stream)
+                oq = own_of_row[r1:]
+                src = unpack_index[k] = oq * mmax + lrow_of_row[r1:] - lo_table[k][oq]
             Lfull[r1:, r0:r1] = recv.view(P * mmax, nb).index_select(0, src)
         else:
             Lfull[r1:, r0:r1] = Pn[:mrows]
