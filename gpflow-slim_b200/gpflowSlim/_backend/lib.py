@@ -185,7 +185,8 @@ def handle_for(tensor_or_device):
 
 # DLTensor (48 bytes) followed by shape[2] and strides[2]: one 80-byte buffer per view, filled by a
 # single struct.pack_into -- a third of the host time of building the ctypes objects field by
-# field, which matters for the launch-bound SVGP step (~100 library calls per step).
+# field; it is paid on every library call (37 per SVGP step, ~25 per panel of the distributed
+# factorisation).
 _DL_PACK = struct.Struct('<QiiiBBHQQQ4q')
 assert _DL_PACK.size == 80 and ctypes.sizeof(DLTensor) == 48
 

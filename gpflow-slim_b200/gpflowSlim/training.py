@@ -70,9 +70,9 @@ class GraphedStep(object):
     """EXPERIMENTAL (written without GPU access at the end of round 1; validated by
     tests/test_gpu_experimental.py in round 2).  One training step -- objective, gradients of
     every trainable tensor, Adam update -- captured ONCE in a CUDA graph and replayed per
-    minibatch.  The SVGP step of BASELINE config C4 issues ~100 library calls and ~150 small
-    torch kernels for ~3 ms of GPU work: it is launch-bound, which is what a graph removes
-    ("CUDA-graph replay for SVGP").
+    minibatch ("CUDA-graph replay for SVGP").  The SVGP step of BASELINE
+    config C4 issues 37 library calls and ~100 torch ops: ~2 ms of host time per step (measured
+    against a null library), which replay removes from the critical path.
 
         step = gpf.training.GraphedStep(model, Xb0, Yb0, learning_rate=1e-3)
         for Xb, Yb in batches:                    # same shapes as Xb0 / Yb0
