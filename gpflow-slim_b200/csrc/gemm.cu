@@ -44,6 +44,12 @@ struct GemmArgs {
   const int64_t* rowlo;
   int64_t lo_off;
   int lo_mode;
+  // split-K (EXPERIMENTAL, option "gemm_splitk"; cp.async kernel only): blockIdx.y = slice s works on
+  // k in [s * k_chunk, (s + 1) * k_chunk) and writes its partial tile (alpha = 1, beta = 0) to
+  // part + s * part_stride; splitk_reduce_kernel then forms alpha * sum_s + beta * C.
+  int split_k, k_chunk;
+  double* part;
+  int64_t ldp, part_stride;
 };
 
 __device__ __forceinline__ void tile_coords(const GemmArgs& g, int bid, int& ti, int& tj) {
@@ -233,6 +239,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_dmma_kernel(const Gem
     int64_t lo = g.rowlo[m0] - g.lo_off;     // rows are sorted: the tile's first row starts first
     if (lo > klo) klo = (int)(lo < khi ? lo / BK * BK : khi);
   }
+  if (g.split_k > 1) {                      // this CTA's slice of K (k_chunk is a multiple of BK)
+    klo = max(klo, (int)blockIdx.y * g.k_chunk);
+    khi = min(khi, ((int)blockIdx.y + 1) * g.k_chunk);
+  }
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps, warp tile 64 x 32
@@ -279,7 +289,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_dmma_kernel(const Gem
   }
   cp_async_wait<0>();
 
+  if (g.split_k > 1) {                      // partial tile of slice blockIdx.y, plain store
+    GemmArgs gs = g;
+    gs.C = g.part + (int64_t)blockIdx.y * g.part_stride;
+    gs.ldc = g.ldp;
+    gs.alpha = 1.0;
+    gs.beta = 0.0;
+    gemm_epilogue(gs, acc, m0, n0, wm, wn, lr, lc);
+    return;
+  }
   gemm_epilogue(g, acc, m0, n0, wm, wn, lr, lc);
+}
+
+// C = alpha * sum_s part[s] + beta * C over the elements the product writes (all, or j <= i)
+__global__ void splitk_reduce_kernel(const double* __restrict__ part, int64_t ldp, int64_t stride, int nsplit,
+                                     double* __restrict__ C, int64_t ldc, int M, int N, double alpha, double beta,
+                                     int lower) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = blockIdx.y; i < M; i += gridDim.y) {
+    if (j >= N || (lower && j > i)) continue;
+    double s = 0.0;
+    for (int q = 0; q < nsplit; ++q) s += part[(int64_t)q * stride + (int64_t)i * ldp + j];
+    double* c = C + (int64_t)i * ldc + j;
+    *c = (beta != 0.0) ? fma(beta, *c, alpha * s) : alpha * s;
+  }
 }
 
 // ------------------------------------------------------------------ TMA + mbarrier variant
@@ -546,7 +579,25 @@ int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, M
   g.tiles_n = (g.N + BN - 1) / BN;
   g.rowlim = rowlim; g.coff = coff;
   g.rowlo = rowlo; g.lo_off = lo_off; g.lo_mode = rowlo ? lo_mode : 0;
+  g.split_k = 1; g.k_chunk = 0; g.part = nullptr; g.ldp = 0; g.part_stride = 0;
   if (c_uplo == C_ROWMAP && !rowlim) return gps_fail(h, -7, "gemm_nt: C_ROWMAP needs a row-limit array");
+  // split-K: a product with a long K and fewer output tiles than half the SMs (the 1024 x 1024 x 8192
+  // products of the SVGP backward leave 84 of 148 SMs idle) is cut into K slices
+  if (h->gemm_splitk && h->gemm_impl != 1 && (c_uplo == C_ALL || c_uplo == C_LOWER) && !rowlo &&
+      a_tri == TRI_NONE && b_tri == TRI_NONE && g.K >= 1024) {
+    const int tiles = (c_uplo == C_LOWER) ? g.tiles_m * (g.tiles_m + 1) / 2 : g.tiles_m * g.tiles_n;
+    int split = h->sm_count / (tiles > 0 ? tiles : 1);
+    if (split > g.K / 512) split = g.K / 512;
+    if (split > 8) split = 8;
+    if (split >= 2) {
+      const int64_t ldp = ((int64_t)g.N + 15) / 16 * 16;
+      double* part = (double*)gps_ws(h, WS_SPLITK, (size_t)split * g.M * ldp * sizeof(double));
+      if (!part) return -102;
+      g.split_k = split;
+      g.k_chunk = ((g.K + split - 1) / split + BK - 1) / BK * BK;
+      g.part = part; g.ldp = ldp; g.part_stride = (int64_t)g.M * ldp;
+    }
+  }
 
   GemmEvent* ev = nullptr;
   if (h->profile) {
@@ -580,8 +631,16 @@ int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, M
     unsigned grid = (unsigned)(g.tiles_m * g.tiles_n);
     // gemm_impl 0: TMA kernel whenever the operands qualify; 2: force the cp.async kernel
     CUtensorMap tmA, tmB;
-    bool tma = vec16 && h->gemm_impl == 0 && g.K > 0 && make_tensor_map(&tmA, A) && make_tensor_map(&tmB, B);
-    if (tma) {
+    bool tma = vec16 && h->gemm_impl == 0 && g.K > 0 && g.split_k == 1 && make_tensor_map(&tmA, A) &&
+               make_tensor_map(&tmB, B);
+    if (g.split_k > 1) {
+      const dim3 grid2(grid, (unsigned)g.split_k);
+      if (vec16) gemm_nt_dmma_kernel<true><<<grid2, GEMM_THREADS, GEMM_SMEM, h->stream>>>(g);
+      else gemm_nt_dmma_kernel<false><<<grid2, GEMM_THREADS, GEMM_SMEM, h->stream>>>(g);
+      h->launches++;
+      splitk_reduce_kernel<<<dim3((unsigned)((g.N + 127) / 128), (unsigned)(g.M < 4096 ? g.M : 4096)), 128, 0, h->stream>>>(
+          g.part, g.ldp, g.part_stride, g.split_k, g.C, g.ldc, g.M, g.N, g.alpha, g.beta, c_uplo == C_LOWER);
+    } else if (tma) {
       static bool tma_attr_set = false;
       if (!tma_attr_set) {
         cudaFuncSetAttribute(gemm_nt_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM);

@@ -156,6 +156,10 @@ int gps_set_option(gps_handle* h, const char* name, int64_t value) {
     h->leaf_impl = (int)value;
     return 0;
   }
+  if (!strcmp(name, "gemm_splitk")) {
+    h->gemm_splitk = (int)value;
+    return 0;
+  }
   if (!strcmp(name, "profile")) {
     h->profile = (int)value;
     return 0;

@@ -43,6 +43,7 @@ enum WsSlot {
   WS_ADJ_A,       // ... three n x ld scratch matrices
   WS_ADJ_B,
   WS_ADJ_C,
+  WS_SPLITK,      // split-K partial tiles (gemm.cu)
   WS_COUNT
 };
 
@@ -57,6 +58,7 @@ struct gps_handle {
   int gram_impl = 0;   // 0 = register-tiled fast path for single stationary kernels, 1 = interpreter only,
                        // 2 = experimental shared-memory-accumulator interpreter backward
   int profile = 0;
+  int gemm_splitk = 0; // 1 = EXPERIMENTAL split-K for long-K products with few output tiles
   void* ws_ptr[WS_COUNT] = {};
   size_t ws_bytes[WS_COUNT] = {};
   std::vector<GemmEvent> events;   // pool

@@ -116,6 +116,9 @@ int gps_version(void);
  *                          2 = EXPERIMENTAL interpreter backward with its accumulators in shared
  *                          memory (written blind at the end of round 1, not yet run on a GPU;
  *                          tests/test_gpu_experimental.py holds it to the default path);
+ *          "gemm_splitk" 1 = EXPERIMENTAL split-K: products with K >= 1024 and fewer output tiles
+ *                          than half the SMs are cut into up to 8 K slices (cp.async kernel + a
+ *                          reduction pass); 0 (default) = off.  Not yet run on a GPU;
  *          "leaf_impl" 0 = blocked DMMA 128x128 Cholesky leaf (default), 1 = scalar check kernel;
  *          "profile"   1 = bracket every GEMM-class launch with CUDA events. */
 int gps_set_option(gps_handle* h, const char* name, int64_t value);

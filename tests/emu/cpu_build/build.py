@@ -99,7 +99,7 @@ def build(outdir):
     res = subprocess.run(['g++', '-shared', '-pthread', '-o', so] + objs, capture_output=True, text=True)
     if res.returncode:
         raise RuntimeError(res.stderr[-5000:])
-    assert launches == 44, launches
+    assert launches == 47, launches
     return so
 
 

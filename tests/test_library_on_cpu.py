@@ -190,6 +190,34 @@ def test_autograd_adjoints_on_the_real_kernels(gpf):
         assert float((a - b).abs().max()) < 1e-10 * max(1.0, float(b.abs().max()))
 
 
+def test_split_k_gemm_through_the_launch_code(gpf):
+    """Option "gemm_splitk" (experimental): long-K products with few output tiles are cut into K
+    slices by the host code (slice count from the SM count -- 4 in the CPU build), partial tiles
+    go to the workspace, a reduction pass applies alpha / beta and the lower-output mask."""
+    from gpflowSlim._backend import lib, ops
+    rng = np.random.default_rng(17)
+    h = lib.handle_for(None)
+    close = lambda a, b: np.testing.assert_allclose(a.numpy(), b, rtol=0, atol=1e-12 * max(1.0, np.abs(b).max()))
+    A, B = rng.standard_normal((100, 2050)), rng.standard_normal((90, 2050))
+    C0 = rng.standard_normal((100, 90))
+    Asq = rng.standard_normal((100, 1100))
+    A3 = conv(rng.standard_normal((40, 1031)))[:, :1029]                 # odd leading dimension, ragged K
+    h.set_option('gemm_splitk', 1)
+    try:
+        before = h.profile_read(reset=False)[2]
+        close(ops.gemm_nt(conv(A), conv(B)), A @ B.T)
+        assert h.profile_read(reset=False)[2] - before == 2              # sliced product + reduction
+        close(ops.gemm_nt(conv(A), conv(B), alpha=-0.7, beta=0.4, out=conv(C0.copy())), 0.4 * C0 - 0.7 * A @ B.T)
+        low = ops.gemm_nt(conv(Asq), conv(Asq), alpha=-1.0, c_uplo=1)
+        close(low, -np.tril(Asq @ Asq.T))
+        close(ops.gemm_nt(A3, A3), A3.numpy() @ A3.numpy().T)
+        before = h.profile_read(reset=False)[2]
+        close(ops.gemm_nt(conv(A[:, :600]), conv(B[:, :600])), A[:, :600] @ B[:, :600].T)   # K < 1024: not sliced
+        assert h.profile_read(reset=False)[2] - before == 1
+    finally:
+        h.set_option('gemm_splitk', 0)
+
+
 @pytest.mark.parametrize('n,m', [(70, 33), (200, 140), (1, 1)])
 def test_library_side_adjoints(gpf, n, m):
     """gps_potri / gps_chol_bwd / gps_trsm_bwd (csrc/adjoint.cu), with U computed inside and with
