@@ -19,6 +19,16 @@ class InducingFeature(object):
     def Kuf(self, kern, Xnew):
         raise NotImplementedError
 
+    def Kfu(self, kern, Xnew):
+        """Kuf^T [N, M]: the orientation the row-major NT products want.  Features whose Kuf is
+        not a plain kernel evaluation (Multiscale) go through their own Kuf."""
+        return _ops.t(self.Kuf(kern, Xnew))
+
+    @property
+    def parameters(self):
+        """Parameters of the feature itself (the reference trains tf.trainable_variables())."""
+        return []
+
 
 class InducingPoints(InducingFeature):
     """Real-space inducing points; Z is a trainable Parameter (features.py:55-81)."""
@@ -40,6 +50,13 @@ class InducingPoints(InducingFeature):
     def Kuf(self, kern, Xnew):
         return kern.K(self.Z, Xnew)
 
+    def Kfu(self, kern, Xnew):
+        return kern.K(Xnew, self.Z)
+
+    @property
+    def parameters(self):
+        return [self._Z]
+
 
 class Multiscale(InducingPoints):
     """Multi-scale inducing features (Lazaro-Gredilla & Figueiras-Vidal 2009; features.py:89-150):
@@ -55,6 +72,13 @@ class Multiscale(InducingPoints):
             raise ValueError('Input locations `Z` and `scales` must have the same shape.')
 
     scales = param_value('scales')
+
+    @property
+    def parameters(self):
+        return [self._Z, self._scales]
+
+    def Kfu(self, kern, Xnew):
+        return _ops.t(self.Kuf(kern, Xnew))
 
     def _cust_square_dist(self, A, B, sc):
         """sum_d ((a_d - b_d) / sc_d)^2 with per-pair scales sc [N, M, D] (or broadcastable)."""

@@ -824,8 +824,12 @@ class Combination(Kernel):
             part = None
             if len(fus) == 1:
                 part = fus[0]
-            elif fus and not rest and not self.fusable:
-                part = self             # children fuse one by one, their combination does not fit
+            elif fus and not rest:
+                # children fuse one by one: their combination does not fit, or it does but the
+                # composed path was chosen because d/dX is wanted on inputs wider than the fused
+                # kernel's column table (_use_fused) -- building Combination(fus) again would
+                # reproduce this very expression and recurse without end
+                part = self
             elif fus:
                 part = self.__class__(fus)
                 if not part.fusable:    # the fusable children together are too large: one by one

@@ -28,8 +28,9 @@ class Model(object):
             if p.trainable and not any(p.unconstrained_tensor is q for q in out):
                 out.append(p.unconstrained_tensor)
         feat = getattr(self, 'feature', None)
-        if feat is not None and getattr(feat, '_Z', None) is not None and feat._Z.trainable:
-            out.append(feat._Z.unconstrained_tensor)
+        for p in (getattr(feat, 'parameters', None) or []):      # Z; Multiscale: Z and scales
+            if p.trainable and not any(p.unconstrained_tensor is q for q in out):
+                out.append(p.unconstrained_tensor)
         return out
 
     def compute_log_prior(self):

@@ -19,7 +19,7 @@ class SGPRUpperMixin(object):
         num_data = float(self.Y.shape[0])
         Kdiag = self.kern.Kdiag(self.X)
         Kuu = self.feature.Kuu(self.kern, jitter=settings.numerics.jitter_level)
-        Kfu = self.kern.K(self.X, self.feature.Z)                                  # Kuf^T  [N, M]
+        Kfu = self.feature.Kfu(self.kern, self.X)                                  # Kuf^T  [N, M]
         Kuf = _ops.t(Kfu)
         var = self.likelihood.variance
         L = _ops.cholesky(Kuu)                                                     # :62
@@ -51,7 +51,7 @@ class SGPR(GPModel, SGPRUpperMixin):
         orientation: At = Kuf^T L^-T / sigma  [N, M]."""
         M = len(self.feature)
         err = self.Y - self.mean_function(self.X)
-        Kfu = self.kern.K(self.X, self.feature.Z)                                  # Kuf^T
+        Kfu = self.feature.Kfu(self.kern, self.X)                                  # Kuf^T
         Kuu = self.feature.Kuu(self.kern, jitter=settings.numerics.jitter_level)
         L = _ops.cholesky(Kuu)
         var = self.likelihood.variance
@@ -83,7 +83,7 @@ class SGPR(GPModel, SGPRUpperMixin):
         """sgpr.py:158-189."""
         Xnew = to_tensor(Xnew)
         err, L, LB, AAT, c, var = self._common()
-        Ksu = self.kern.K(Xnew, self.feature.Z)                                    # Kus^T [N*, M]
+        Ksu = self.feature.Kfu(self.kern, Xnew)                                    # Kus^T [N*, M]
         tmp1t = _ops.trsm_rlt(Ksu, L)                                              # (L^-1 Kus)^T
         tmp2t = _ops.trsm_rlt(tmp1t, LB)                                           # (LB^-1 tmp1)^T
         mean = _ops.matmul_nt(tmp2t, _ops.t(c))                                    # tmp2^T c
@@ -115,7 +115,7 @@ class GPRFITC(GPModel, SGPRUpperMixin):
         M = len(self.feature)
         err = self.Y - self.mean_function(self.X)
         Kdiag = self.kern.Kdiag(self.X)
-        Kfu = self.kern.K(self.X, self.feature.Z)                                  # Kuf^T
+        Kfu = self.feature.Kfu(self.kern, self.X)                                  # Kuf^T
         Kuu = self.feature.Kuu(self.kern, jitter=settings.numerics.jitter_level)
         Luu = _ops.cholesky(Kuu)
         Vt = _ops.trsm_rlt(Kfu, Luu)                                               # (Luu^-1 Kuf)^T
@@ -141,7 +141,7 @@ class GPRFITC(GPModel, SGPRUpperMixin):
         """:293-317."""
         Xnew = to_tensor(Xnew)
         _, _, Luu, L, _, _, gamma = self._build_common_terms()
-        Ksu = self.kern.K(Xnew, self.feature.Z)                                    # Kus^T [N*, M]
+        Ksu = self.feature.Kfu(self.kern, Xnew)                                    # Kus^T [N*, M]
         wt = _ops.trsm_rlt(Ksu, Luu)                                               # (Luu^-1 Kus)^T
         tmp = _ops.solve_upper_t(L, gamma)                                         # L^-T gamma [M, R]
         mean = _ops.matmul_nt(wt, _ops.t(tmp)) + self.mean_function(Xnew)

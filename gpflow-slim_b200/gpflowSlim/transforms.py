@@ -145,29 +145,26 @@ class Logistic(Transform):
 
 
 class Rescale(Transform):
-    """y = factor * x, chained in front of another transform."""
+    """y = factor * x (transforms.py:215-251).  Chained like any other transform:
+    `Rescale(s)(positive)` = Chain(Rescale(s), positive): y = s * (softplus(x) + 1e-6)."""
 
-    def __init__(self, factor=1.0, chain_transform=None):
+    def __init__(self, factor=1.0):
         self.factor = float(factor)
-        self.chain_transform = chain_transform or Identity()
 
     def forward(self, x):
-        return self.chain_transform.forward(x * self.factor)
+        return x * self.factor
 
     def backward(self, y):
-        return self.chain_transform.backward(y) / self.factor
+        return y / self.factor
 
     def forward_tensor(self, x):
-        return self.chain_transform.forward_tensor(x * self.factor)
+        return x * self.factor
 
     def log_jacobian_tensor(self, x):
-        return x.numel() * np.log(self.factor) + self.chain_transform.log_jacobian_tensor(x * self.factor)
-
-    def __call__(self, other):
-        return Rescale(self.factor, other)
+        return x.numel() * torch.log(torch.as_tensor(self.factor, dtype=x.dtype, device=x.device))
 
     def __str__(self):
-        return '{}*{}'.format(self.factor, self.chain_transform)
+        return '{}*'.format(self.factor)
 
 
 class DiagMatrix(Transform):

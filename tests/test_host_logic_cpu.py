@@ -218,3 +218,29 @@ def test_white_and_bias_terms_keep_the_gpr_on_the_fused_path(monkeypatch):
         g.models.GPR(X, Y, kern=kern2).objective
         assert calls == {'fused': 0, 'chol': 1}
     g.settings.device = None
+
+
+def test_rescale_follows_reference_semantics():
+    """Rescale is plain y = factor * x (reference transforms.py:215-251) and
+    positiveRescale(s) = Chain(Rescale(s), positive): y = s * (softplus(x) + 1e-6), with
+    log|dy/dx| = N log s + sum log sigmoid(x) (transforms.py:110-112, 244-248, 380-392)."""
+    import gpflowSlim as gpf
+    T = gpf.transforms
+    s = 3.5
+    t = T.positiveRescale(s)
+    x = np.array([-2.0, 0.3, 4.0])
+    y = t.forward(x)
+    np.testing.assert_allclose(y, s * (np.log1p(np.exp(x)) + 1e-6), rtol=1e-15)
+    np.testing.assert_allclose(t.backward(y), x, rtol=1e-12)
+    xt = torch.tensor(x)
+    np.testing.assert_allclose(t.forward_tensor(xt).numpy(), y, rtol=1e-15)
+    lj = float(t.log_jacobian_tensor(xt))
+    want = 3 * np.log(s) + np.log(1.0 / (1.0 + np.exp(-x))).sum()
+    assert abs(lj - want) < 1e-12
+    r = T.Rescale(s)
+    np.testing.assert_allclose(r.forward(x), s * x)
+    np.testing.assert_allclose(r.backward(s * x), x)
+    assert str(r) == '%s*' % s and str(t).startswith('%s* ' % s)
+    # a Parameter on the chained transform round-trips its value
+    p = gpf.Param(2.0, transform=T.positiveRescale(s))
+    assert abs(float(p.value) - 2.0) < 1e-12

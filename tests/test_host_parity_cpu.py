@@ -111,3 +111,61 @@ def test_tri_aware_matmul_adjoint_against_torch(gpf_raw, monkeypatch):
                 assert relerr(gA, wA) < 1e-12, (tri_aware, a_tri, b_tri, 'dA')
                 assert relerr(gB, wB) < 1e-12, (tri_aware, a_tri, b_tri, 'dB')
 
+
+
+def test_sgpr_with_multiscale_feature_uses_feature_kuf(gpf):
+    """SGPR / GPRFITC / upper bound must build the cross-covariance through the feature
+    (reference models/sgpr.py:132 `self.feature.Kuf(self.kern, self.X)`), not through kern.K --
+    with a Multiscale feature (features.py:89-150) the two differ.  Checked against the reference
+    formula (sgpr.py:121-156) written out with torch."""
+    rng = np.random.default_rng(5)
+    N, M, D = 60, 7, 3
+    X, Y = conv(rng.standard_normal((N, D))), conv(rng.standard_normal((N, 1)))
+    Z = rng.standard_normal((M, D))
+    scales = 0.3 + rng.random((M, D))
+    kern = gpf.kernels.RBF(D, ARD=True, lengthscales=1.3)
+    feat = gpf.features.Multiscale(Z, scales)
+    m = gpf.models.SGPR(X, Y, kern, feat=feat, obs_var=0.2)
+    got = m.likelihood_tensor
+    with torch.no_grad():
+        Kuf = feat.Kuf(kern, X)
+        Kuu = feat.Kuu(kern, jitter=gpf.settings.numerics.jitter_level)
+        var = m.likelihood.variance
+        L = torch.linalg.cholesky(Kuu)
+        A = torch.linalg.solve_triangular(L, Kuf, upper=False) / torch.sqrt(var)
+        B = A @ A.t() + torch.eye(M, dtype=torch.float64)
+        LB = torch.linalg.cholesky(B)
+        c = torch.linalg.solve_triangular(LB, A @ Y, upper=False) / torch.sqrt(var)
+        want = (-0.5 * N * np.log(2 * np.pi) - torch.log(torch.diagonal(LB)).sum() - 0.5 * N * torch.log(var)
+                - 0.5 * (Y ** 2).sum() / var + 0.5 * (c ** 2).sum() - 0.5 * kern.Kdiag(X).sum() / var
+                + 0.5 * torch.diagonal(A @ A.t()).sum())
+    assert relerr(got.detach(), want) < 1e-10
+    # the feature's own parameters (Z and scales) are trained (reference: tf.trainable_variables())
+    tt = m.trainable_tensors
+    assert any(t is feat._scales.unconstrained_tensor for t in tt)
+    assert any(t is feat._Z.unconstrained_tensor for t in tt)
+    grads = torch.autograd.grad(m.objective, tt)
+    assert all(torch.isfinite(g).all() for g in grads)
+    # FITC and the upper bound run through the same feature path
+    f = gpf.models.GPRFITC(X, Y, kern, feat=feat, obs_var=0.2)
+    assert torch.isfinite(f.likelihood_tensor) and torch.isfinite(m.compute_upper_bound())
+
+
+@pytest.mark.parametrize('comb', ['sum', 'product'])
+def test_wide_input_combination_with_input_gradient_does_not_recurse(gpf, comb):
+    """a fusable Sum / Product pushed onto the composed path because d/dX is wanted on
+    inputs wider than GPS_MAX_DIMS used to rebuild itself for ever in Combination._split."""
+    rng = np.random.default_rng(6)
+    X0 = conv(rng.standard_normal((9, 40)))
+    k1 = gpf.kernels.RBF(20, active_dims=list(range(20)), lengthscales=2.0)
+    k2 = gpf.kernels.Linear(20, active_dims=list(range(20, 40)))
+    kern = (k1 + k2) if comb == 'sum' else (k1 * k2)
+    X = X0.clone().requires_grad_(True)
+    K = kern.K(X)
+    (g,) = torch.autograd.grad(K.sum(), [X])
+    with torch.no_grad():
+        want = kern.K(X0)               # no input gradient wanted: the fused path
+    assert relerr(K.detach(), want) < 1e-12
+    assert torch.isfinite(g).all()
+    Kd = kern.Kdiag(X)
+    assert relerr(Kd.detach(), torch.diagonal(want)) < 1e-12
