@@ -44,7 +44,7 @@ struct GemmArgs {
   const int64_t* rowlo;
   int64_t lo_off;
   int lo_mode;
-  // split-K (EXPERIMENTAL, option "gemm_splitk"; cp.async kernel only): blockIdx.y = slice s works on
+  // split-K (option "gemm_splitk", on by default; both tensor-core kernels): blockIdx.y = slice s works on
   // k in [s * k_chunk, (s + 1) * k_chunk) and writes its partial tile (alpha = 1, beta = 0) to
   // part + s * part_stride; splitk_reduce_kernel then forms alpha * sum_s + beta * C.
   int split_k, k_chunk;
@@ -386,6 +386,10 @@ gemm_nt_tma_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmA,
     int64_t lo = g.rowlo[m0] - g.lo_off;
     if (lo > klo) klo = (int)(lo < khi ? lo / TBK * TBK : khi);
   }
+  if (g.split_k > 1) {   // this CTA's slice of K; k_chunk is a multiple of TBK, so no box straddles a slice
+    klo = max(klo, (int)blockIdx.y * g.k_chunk);
+    khi = min(khi, ((int)blockIdx.y + 1) * g.k_chunk);
+  }
   const int nk = (khi > klo) ? (khi - klo + TBK - 1) / TBK : 0;
 
   const int tid = threadIdx.x;
@@ -402,7 +406,7 @@ gemm_nt_tma_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmA,
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
-  prefetch_c_tile(g, m0, n0, tid);
+  if (g.split_k == 1) prefetch_c_tile(g, m0, n0, tid);
 
   // ---------------- producer duty: lane 0 of warp 0 feeds the ring.  Load L goes to slot
   // L % TSTAGES; it is issued in the middle of iteration L - (TSTAGES - 1), i.e. one full
@@ -489,6 +493,15 @@ gemm_nt_tma_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmA,
     ph = ph2;
   }
 
+  if (g.split_k > 1) {                      // partial tile of slice blockIdx.y, plain store
+    GemmArgs gs = g;
+    gs.C = g.part + (int64_t)blockIdx.y * g.part_stride;
+    gs.ldc = g.ldp;
+    gs.alpha = 1.0;
+    gs.beta = 0.0;
+    gemm_epilogue(gs, acc, m0, n0, wm, wn, pr, lc);
+    return;
+  }
   gemm_epilogue(g, acc, m0, n0, wm, wn, pr, lc);
 }
 
@@ -581,20 +594,23 @@ int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, M
   g.rowlo = rowlo; g.lo_off = lo_off; g.lo_mode = rowlo ? lo_mode : 0;
   g.split_k = 1; g.k_chunk = 0; g.part = nullptr; g.ldp = 0; g.part_stride = 0;
   if (c_uplo == C_ROWMAP && !rowlim) return gps_fail(h, -7, "gemm_nt: C_ROWMAP needs a row-limit array");
-  // split-K: a product with a long K and fewer output tiles than half the SMs (the 1024 x 1024 x 8192
-  // products of the SVGP backward leave 84 of 148 SMs idle) is cut into K slices
+  // split-K: a product with a long K and too few output tiles to fill the SMs -- the 1024 x 1024 x 8192
+  // products of the SVGP backward are 64 (36 lower) tiles on 148 SMs, an M x R product with R <= 128 is
+  // M/128 tiles -- is cut into K slices (blockIdx.y); the partial tiles go to a per-stream scratch and
+  // one reduction pass applies alpha / beta and the lower-output mask.  One wave of CTAs at most.
   if (h->gemm_splitk && h->gemm_impl != 1 && (c_uplo == C_ALL || c_uplo == C_LOWER) && !rowlo &&
-      a_tri == TRI_NONE && b_tri == TRI_NONE && g.K >= 1024) {
-    const int tiles = (c_uplo == C_LOWER) ? g.tiles_m * (g.tiles_m + 1) / 2 : g.tiles_m * g.tiles_n;
+      a_tri == TRI_NONE && b_tri == TRI_NONE && g.K >= 512) {
+    const int tiles = (c_uplo == C_LOWER && g.M == g.N) ? g.tiles_m * (g.tiles_m + 1) / 2 : g.tiles_m * g.tiles_n;
     int split = h->sm_count / (tiles > 0 ? tiles : 1);
-    if (split > g.K / 512) split = g.K / 512;
-    if (split > 8) split = 8;
+    if (split > g.K / 256) split = g.K / 256;
+    if (split > 32) split = 32;
     if (split >= 2) {
       const int64_t ldp = ((int64_t)g.N + 15) / 16 * 16;
-      double* part = (double*)gps_ws(h, WS_SPLITK, (size_t)split * g.M * ldp * sizeof(double));
+      g.k_chunk = ((g.K + split - 1) / split + BK - 1) / BK * BK;
+      split = (g.K + g.k_chunk - 1) / g.k_chunk;      // no empty slices
+      double* part = (double*)gps_ws_splitk(h, (size_t)split * g.M * ldp * sizeof(double));
       if (!part) return -102;
       g.split_k = split;
-      g.k_chunk = ((g.K + split - 1) / split + BK - 1) / BK * BK;
       g.part = part; g.ldp = ldp; g.part_stride = (int64_t)g.M * ldp;
     }
   }
@@ -617,13 +633,12 @@ int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, M
     dim3 grid((g.N + 15) / 16, (g.M + 15) / 16);
     gemm_nt_naive_kernel<<<grid, dim3(16, 16), 0, h->stream>>>(g);
   } else {
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!h->attr_gemm) {
       cudaFuncSetAttribute(gemm_nt_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            GEMM_SMEM);
       cudaFuncSetAttribute(gemm_nt_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            GEMM_SMEM);
-      attr_set = true;
+      h->attr_gemm = true;
     }
     bool vec16 = ((A.ld & 1) == 0) && ((B.ld & 1) == 0) &&
                  ((reinterpret_cast<uintptr_t>(A.p) & 15) == 0) &&
@@ -631,26 +646,24 @@ int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, M
     unsigned grid = (unsigned)(g.tiles_m * g.tiles_n);
     // gemm_impl 0: TMA kernel whenever the operands qualify; 2: force the cp.async kernel
     CUtensorMap tmA, tmB;
-    bool tma = vec16 && h->gemm_impl == 0 && g.K > 0 && g.split_k == 1 && make_tensor_map(&tmA, A) &&
-               make_tensor_map(&tmB, B);
-    if (g.split_k > 1) {
-      const dim3 grid2(grid, (unsigned)g.split_k);
-      if (vec16) gemm_nt_dmma_kernel<true><<<grid2, GEMM_THREADS, GEMM_SMEM, h->stream>>>(g);
-      else gemm_nt_dmma_kernel<false><<<grid2, GEMM_THREADS, GEMM_SMEM, h->stream>>>(g);
-      h->launches++;
-      splitk_reduce_kernel<<<dim3((unsigned)((g.N + 127) / 128), (unsigned)(g.M < 4096 ? g.M : 4096)), 128, 0, h->stream>>>(
-          g.part, g.ldp, g.part_stride, g.split_k, g.C, g.ldc, g.M, g.N, g.alpha, g.beta, c_uplo == C_LOWER);
-    } else if (tma) {
-      static bool tma_attr_set = false;
-      if (!tma_attr_set) {
+    bool tma = vec16 && h->gemm_impl == 0 && g.K > 0 && make_tensor_map(&tmA, A) && make_tensor_map(&tmB, B);
+    const dim3 grid2(grid, (unsigned)g.split_k);
+    if (tma) {
+      if (!h->attr_tma) {
         cudaFuncSetAttribute(gemm_nt_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM);
-        tma_attr_set = true;
+        h->attr_tma = true;
       }
-      gemm_nt_tma_kernel<<<grid, TMA_THREADS, TMA_SMEM, h->stream>>>(g, tmA, tmB);
+      gemm_nt_tma_kernel<<<grid2, TMA_THREADS, TMA_SMEM, h->stream>>>(g, tmA, tmB);
     } else if (vec16) {
-      gemm_nt_dmma_kernel<true><<<grid, GEMM_THREADS, GEMM_SMEM, h->stream>>>(g);
+      gemm_nt_dmma_kernel<true><<<grid2, GEMM_THREADS, GEMM_SMEM, h->stream>>>(g);
     } else {
-      gemm_nt_dmma_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM, h->stream>>>(g);
+      gemm_nt_dmma_kernel<false><<<grid2, GEMM_THREADS, GEMM_SMEM, h->stream>>>(g);
+    }
+    if (g.split_k > 1) {
+      h->launches++;
+      splitk_reduce_kernel<<<dim3((unsigned)((g.N + 127) / 128), (unsigned)(g.M < 4096 ? g.M : 4096)), 128, 0,
+                             h->stream>>>(g.part, g.ldp, g.part_stride, g.split_k, g.C, g.ldc, g.M, g.N,
+                                          g.alpha, g.beta, c_uplo == C_LOWER);
     }
   }
   if (ev) cudaEventRecord(ev->b, h->stream);

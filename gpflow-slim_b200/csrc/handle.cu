@@ -40,6 +40,23 @@ void* gps_ws(gps_handle* h, int slot, size_t bytes) {
   return p;
 }
 
+void* gps_ws_splitk(gps_handle* h, size_t bytes) {
+  auto& slot = h->splitk_ws[h->stream];
+  if (slot.first && bytes <= slot.second) return slot.first;
+  cudaStreamSynchronize(h->stream);
+  if (slot.first) cudaFree(slot.first);
+  slot = {nullptr, 0};
+  size_t want = bytes + bytes / 4 + 256;
+  void* p = nullptr;
+  if (cudaMalloc(&p, want) != cudaSuccess) {
+    cudaGetLastError();
+    gps_fail(h, -102, "split-K workspace allocation of %zu bytes failed", bytes);
+    return nullptr;
+  }
+  slot = {p, want};
+  return p;
+}
+
 int gps_as_mat(gps_handle* h, const DLTensor* t, int argidx, const char* name, Mat* out,
                bool allow_vec) {
   if (!t || !t->data)
@@ -126,6 +143,8 @@ int gps_destroy(gps_handle* h) {
   cudaStreamSynchronize(h->stream);
   for (int i = 0; i < WS_COUNT; ++i)
     if (h->ws_ptr[i]) cudaFree(h->ws_ptr[i]);
+  for (auto& kv : h->splitk_ws)
+    if (kv.second.first) cudaFree(kv.second.first);
   for (auto& e : h->events) {
     cudaEventDestroy(e.a);
     cudaEventDestroy(e.b);

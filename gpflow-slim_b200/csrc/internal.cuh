@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -58,7 +59,11 @@ struct gps_handle {
   int gram_impl = 0;   // 0 = register-tiled fast path for single stationary kernels, 1 = interpreter only,
                        // 2 = experimental shared-memory-accumulator interpreter backward
   int profile = 0;
-  int gemm_splitk = 0; // 1 = EXPERIMENTAL split-K for long-K products with few output tiles
+  int gemm_splitk = 1; // split-K for long-K products with few output tiles (0 switches it off)
+  // function attributes (opt-in shared memory sizes) are per device: one flag set per handle
+  bool attr_gemm = false, attr_tma = false, attr_potrf = false;
+  // split-K partial tiles, one buffer per stream (a handle may be driven from several streams)
+  std::map<cudaStream_t, std::pair<void*, size_t>> splitk_ws;
   void* ws_ptr[WS_COUNT] = {};
   size_t ws_bytes[WS_COUNT] = {};
   std::vector<GemmEvent> events;   // pool
@@ -70,6 +75,7 @@ struct gps_handle {
 
 int gps_fail(gps_handle* h, int code, const char* fmt, ...);
 void* gps_ws(gps_handle* h, int slot, size_t bytes);  // nullptr on failure (err set)
+void* gps_ws_splitk(gps_handle* h, size_t bytes);      // per-stream (h->stream) scratch
 
 #define GPS_CUDA(h, expr)                                                          \
   do {                                                                             \

@@ -461,16 +461,15 @@ trsm_strip_kernel(double* __restrict__ B, int64_t ldb, int m, int n, const doubl
   }
 }
 
-bool g_attr_set = false;
-void set_attrs() {
-  if (g_attr_set) return;
+void set_attrs(gps_handle* h) {
+  if (h->attr_potrf) return;
   cudaFuncSetAttribute(potrf_base_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BASE_SMEM);
   cudaFuncSetAttribute(potrf_base_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BASE_SMEM);
   cudaFuncSetAttribute(trsm_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRIP_SMEM);
   cudaFuncSetAttribute(trsm_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRIP_SMEM);
   cudaFuncSetAttribute(potrf_leaf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM);
   cudaFuncSetAttribute(potrf_leaf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM);
-  g_attr_set = true;
+  h->attr_potrf = true;
 }
 
 int64_t split_point(int64_t n) {
@@ -480,7 +479,7 @@ int64_t split_point(int64_t n) {
 
 int strip_launch(gps_handle* h, Mat B, int64_t n, const double* T, bool notrans = false) {
   if (B.rows <= 0) return 0;
-  set_attrs();
+  set_attrs(h);
   unsigned grid = (unsigned)((B.rows + STRIP - 1) / STRIP);
   if (notrans)
     trsm_strip_kernel<true><<<grid, 256, STRIP_SMEM, h->stream>>>(B.p, B.ld, (int)B.rows, (int)n, T);
@@ -522,7 +521,7 @@ int gps_potrf_rec(gps_handle* h, Mat A, int64_t n, int64_t below, int64_t blk0, 
   int rc;
   if (n <= 0) return 0;
   if (n <= NB) {
-    set_attrs();
+    set_attrs(h);
     if (h->leaf_impl == 1)
       potrf_base_kernel<true><<<1, BASE_THREADS, BASE_SMEM, h->stream>>>(
           A.p, A.ld, (int)n, tinv + blk0 * NB * NB, logdet ? logdet + blk0 : nullptr, info_dev,
@@ -637,7 +636,7 @@ int make_segs(gps_handle* h, const int64_t* row_start, int64_t rows, int64_t nco
 
 int gps_block_inverses(gps_handle* h, Mat L, double* tinv) {
   if (L.rows <= 0) return 0;
-  set_attrs();
+  set_attrs(h);
   unsigned nblk = (unsigned)((L.rows + NB - 1) / NB);
   if (h->leaf_impl == 1)
     potrf_base_kernel<false><<<nblk, BASE_THREADS, BASE_SMEM, h->stream>>>(

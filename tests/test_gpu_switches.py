@@ -1,14 +1,12 @@
-"""Kernels written WITHOUT GPU access at the end of round 1 (gpurun budget exhausted) and
-therefore not the default path: they run only when GPSLIM_TEST_EXPERIMENTAL=1, so that the
-regular `pytest -m gpu` stays a statement about validated code.  First thing to run in round 2:
-
-    GPSLIM_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -q -s
+"""Switches of the library that have an alternative implementation behind gps_set_option / the ops
+module flags, each held to the default path (or to torch) on the GPU.  Written blind at the end of
+round 1, first run (all green) on a B200 at the start of round 2 (profiles/r02_experimental_switches_gpu.txt);
+since then part of the regular `pytest -m gpu` run.
 
 gram_impl = 2: interpreter Gram forward / backward with the slot values, slot adjoints and
 theta-gradient accumulators in shared memory ([index][thread] layout) instead of local memory
-(csrc/gram.cu: gram_fwd_smem_kernel, gram_bwd_smem_kernel).  Their source text already passes
-the CPU emulation test (tests/test_gram_kernel_emulation_cpu.py).  Must reproduce the default interpreter (gram_impl = 1) to rounding:
-same per-element arithmetic, different summation order."""
+(csrc/gram.cu: gram_fwd_smem_kernel, gram_bwd_smem_kernel).  Must reproduce the default interpreter
+(gram_impl = 1) to rounding: same per-element arithmetic, different summation order."""
 import os
 
 import numpy as np
@@ -18,9 +16,7 @@ import torch
 from oracle import cases
 from util import assert_close, conv
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('GPSLIM_TEST_EXPERIMENTAL') != '1',
-                                 reason='experimental kernels: set GPSLIM_TEST_EXPERIMENTAL=1')]
+pytestmark = [pytest.mark.gpu]
 
 
 def _grads(kern, X, X2, W, Ws, impl, want_dx):
@@ -195,13 +191,17 @@ def test_library_side_adjoints_on_the_gpu(golden, monkeypatch):
 
 
 def test_split_k_gemm_on_the_gpu():
-    """Option "gemm_splitk": the 1024 x 1024 x 8192 products of the SVGP backward (64 / 36 output
-    tiles on 148 SMs) sliced along K; correctness against torch and the two timings."""
+    """Split-K (on by default): products with a long K and few output tiles -- the 1024 x 1024 x 8192
+    products of the SVGP backward (64 / 36 output tiles on 148 SMs), the M x 1 products with K = 8192
+    -- sliced along K in BOTH tensor-core kernels (TMA: gemm_impl 0, cp.async: 2); correctness
+    against torch incl. alpha / beta, lower output and ragged shapes, and the timings."""
     from gpflowSlim._backend import ops
     from gpflowSlim._backend.lib import handle_for
     rng = np.random.default_rng(0)
     A, B = conv(rng.standard_normal((1024, 8192))), conv(rng.standard_normal((1024, 8192)))
     C0 = conv(rng.standard_normal((1024, 1024)))
+    v = conv(rng.standard_normal((1, 8192)))
+    Ar, Br = conv(rng.standard_normal((300, 5000))), conv(rng.standard_normal((170, 5000)))
     h = handle_for(A)
     want = A @ B.t()
 
@@ -215,17 +215,27 @@ def test_split_k_gemm_on_the_gpu():
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
-    t_plain = timed(lambda: ops.gemm_nt(A, B))
-    t_low = timed(lambda: ops.gemm_nt(A, A, c_uplo=1))
-    h.set_option('gemm_splitk', 1)
     try:
-        assert_close(ops.gemm_nt(A, B), want, 1e-12, 'split-K')
-        assert_close(ops.gemm_nt(A, B, alpha=-0.5, beta=2.0, out=C0.clone()), 2.0 * C0 - 0.5 * want, 1e-12, 'split-K rmw')
-        assert_close(ops.gemm_nt(A, A, c_uplo=1), torch.tril(A @ A.t()), 1e-12, 'split-K lower')
-        t_split = timed(lambda: ops.gemm_nt(A, B))
-        t_split_low = timed(lambda: ops.gemm_nt(A, A, c_uplo=1))
+        for impl in (0, 2):
+            h.set_option('gemm_impl', impl)
+            h.set_option('gemm_splitk', 0)
+            t_plain = timed(lambda: ops.gemm_nt(A, B))
+            t_low = timed(lambda: ops.gemm_nt(A, A, c_uplo=1))
+            t_vec = timed(lambda: ops.gemm_nt(A, v))
+            h.set_option('gemm_splitk', 1)
+            assert_close(ops.gemm_nt(A, B), want, 1e-12, 'split-K')
+            assert_close(ops.gemm_nt(A, B, alpha=-0.5, beta=2.0, out=C0.clone()), 2.0 * C0 - 0.5 * want, 1e-12,
+                         'split-K rmw')
+            assert_close(ops.gemm_nt(A, A, c_uplo=1), torch.tril(A @ A.t()), 1e-12, 'split-K lower')
+            assert_close(ops.gemm_nt(A, v), A @ v.t(), 1e-12, 'split-K M x 1')
+            assert_close(ops.gemm_nt(v, A), v @ A.t(), 1e-12, 'split-K 1 x M')
+            assert_close(ops.gemm_nt(Ar, Br), Ar @ Br.t(), 1e-12, 'split-K ragged')
+            assert_close(ops.gemm_nt(Ar, Ar, c_uplo=1), torch.tril(Ar @ Ar.t()), 1e-12, 'split-K ragged lower')
+            t_split = timed(lambda: ops.gemm_nt(A, B))
+            t_split_low = timed(lambda: ops.gemm_nt(A, A, c_uplo=1))
+            t_split_vec = timed(lambda: ops.gemm_nt(A, v))
+            print('gemm_impl %d  1024 x 1024 x 8192: %.3f ms -> split-K %.3f ms;  lower output: %.3f -> %.3f ms;  '
+                  '1024 x 1 x 8192: %.3f -> %.3f ms' % (impl, t_plain, t_split, t_low, t_split_low, t_vec, t_split_vec))
     finally:
-        h.set_option('gemm_splitk', 0)
-    print('1024 x 1024 x 8192: %.3f ms -> split-K %.3f ms;  lower output: %.3f ms -> %.3f ms'
-          % (t_plain, t_split, t_low, t_split_low))
-
+        h.set_option('gemm_impl', 0)
+        h.set_option('gemm_splitk', 1)

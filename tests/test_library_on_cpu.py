@@ -191,7 +191,7 @@ def test_autograd_adjoints_on_the_real_kernels(gpf):
 
 
 def test_split_k_gemm_through_the_launch_code(gpf):
-    """Option "gemm_splitk" (experimental): long-K products with few output tiles are cut into K
+    """Option "gemm_splitk" (on by default): long-K products with few output tiles are cut into K
     slices by the host code (slice count from the SM count -- 4 in the CPU build), partial tiles
     go to the workspace, a reduction pass applies alpha / beta and the lower-output mask."""
     from gpflowSlim._backend import lib, ops
@@ -212,10 +212,10 @@ def test_split_k_gemm_through_the_launch_code(gpf):
         close(low, -np.tril(Asq @ Asq.T))
         close(ops.gemm_nt(A3, A3), A3.numpy() @ A3.numpy().T)
         before = h.profile_read(reset=False)[2]
-        close(ops.gemm_nt(conv(A[:, :600]), conv(B[:, :600])), A[:, :600] @ B[:, :600].T)   # K < 1024: not sliced
+        close(ops.gemm_nt(conv(A[:, :400]), conv(B[:, :400])), A[:, :400] @ B[:, :400].T)   # K < 512: not sliced
         assert h.profile_read(reset=False)[2] - before == 1
     finally:
-        h.set_option('gemm_splitk', 0)
+        h.set_option('gemm_splitk', 1)     # the default
 
 
 @pytest.mark.parametrize('n,m', [(70, 33), (200, 140), (1, 1)])
