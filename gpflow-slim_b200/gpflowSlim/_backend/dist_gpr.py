@@ -523,10 +523,21 @@ def nlml_and_grad(prog, theta, noise, X, Yc, block=512, group=None, backend=None
     if not want_grad:
         return nlml, None, None, None
 
-    # ---- rows of K^-1, no communication: L is replicated
+    out, beta_t = inverse_rows_and_contract(prog, theta, X, lay, comm.rank, Lsq, Ltf[:, :N], alpha_t, be)
+    comm.all_reduce_sum(out)
+    _mark('contract+allreduce')
+    return nlml, out[:prog.n_theta], out[prog.n_theta], beta_t.t().contiguous()
+
+
+def inverse_rows_and_contract(prog, theta, X, lay, rank, Lsq, Lt, alpha_t, be):
+    """This rank's share of the gradient, no communication (L and L^T are replicated): its block
+    rows of U = L^-T and of K^-1 = U L^-1 (columns >= the row block), contracted with dK/dtheta.
+    Returns (partial [dtheta..., dnoise] to be summed over ranks, beta^T [R, N])."""
+    N = Lsq.shape[0]
+    R = alpha_t.shape[0]
     dev = X.device
     bs = lay.block
-    mine = lay.inverse_assignment()[comm.rank]
+    mine = lay.inverse_assignment()[rank]
     m = R + sum(lay.rows(b)[1] - lay.rows(b)[0] for b in mine)
     ld = _round_up(N, 16)
     B = be.zeros(m, ld)[:, :N]
@@ -544,7 +555,6 @@ def nlml_and_grad(prog, theta, noise, X, Yc, block=512, group=None, backend=None
     start_u = np.concatenate([np.full(nr, r0, dtype=np.int64) for (r0, _, nr) in starts]
                              or [np.zeros(0, dtype=np.int64)])
     start_all = np.concatenate([np.zeros(R, dtype=np.int64), start_u])
-    Lt = Ltf[:, :N]
     _mark('nlml+inv_setup')
     if m > R:
         be.trsm_rlt_prefix_(Lsq, B[R:], start_u)          # rows of U = L^-T
@@ -558,6 +568,4 @@ def nlml_and_grad(prog, theta, noise, X, Yc, block=512, group=None, backend=None
         be.weight_rows_(W, growB, beta_t, bs)
         out[prog.n_theta] = W[torch.arange(m - R, device=dev), growB].sum()     # tr W
         out[:prog.n_theta] = be.gram_bwd(prog, theta, X.index_select(0, growB), X, W)
-    comm.all_reduce_sum(out)
-    _mark('contract+allreduce')
-    return nlml, out[:prog.n_theta], out[prog.n_theta], beta_t.t().contiguous()
+    return out, beta_t

@@ -98,23 +98,40 @@ def trsm_rlt_(L, B):
 _U_CACHE = {}
 
 
-def tri_inv_t(L):
-    """U = L^-T (upper triangular).  Cached per factor: backward passes reuse it."""
+def tri_inv_t(L, share=None):
+    """U = L^-T (upper triangular).  Computed once per factor: `share` is the dict that travels
+    with a factor produced by `cholesky()` (attribute `_gps_share` of the tensor, also held by
+    the autograd nodes that saved the factor), so the forward pass and every adjoint that needs
+    U -- Cholesky, triangular solves, L^-T itself -- use one triangular inverse.  Factors that do
+    not come from `cholesky()` fall back to a cache keyed by the tensor object."""
     L = _prep(L)
     if L.numel() == 0:
         return L.clone()
+    if share is None:
+        share = getattr(L, '_gps_share', None)
+    if share is not None:
+        U = share.get('U')
+        if U is not None:
+            return U
     key = (L.data_ptr(), L._version, tuple(L.shape))
     hit = _U_CACHE.get(key)
-    if hit is not None and hit[0]() is L:
+    if share is None and hit is not None and hit[0]() is L:
         return hit[1]
     h = handle_for(L)
     U = torch.empty_like(L, memory_format=torch.contiguous_format)
     vl, vu = view(L), view(U)
     h.check(h.lib.gps_tri_inv_t(h.ptr, vl.ref, vu.ref))
-    if len(_U_CACHE) > 8:
-        _U_CACHE.clear()
-    _U_CACHE[key] = (weakref.ref(L), U)
+    if share is not None:
+        share['U'] = U
+    else:
+        if len(_U_CACHE) > 8:
+            _U_CACHE.clear()
+        _U_CACHE[key] = (weakref.ref(L), U)
     return U
+
+
+def _share_of(L):
+    return getattr(L, '_gps_share', None)
 
 
 def row_sumsq(A):
@@ -129,10 +146,10 @@ def row_sumsq(A):
 
 # ------------------------------------------------------------------------- library-side adjoints
 # gps_potri / gps_chol_bwd / gps_trsm_bwd (csrc/adjoint.cu) do in one call what the autograd
-# Functions below compose from gps_tri_inv_t + gps_gemm_nt + transposes.  EXPERIMENTAL switch, off
-# until seen green on a GPU (the CPU build of the library runs both settings): with it on, the
-# backward of `cholesky` and `trsm_rlt` is one ctypes round trip each.
-FUSED_ADJOINTS = [False]
+# Functions below otherwise compose from gps_tri_inv_t + gps_gemm_nt + transposes: the backward of
+# `cholesky` and `trsm_rlt` is one ctypes round trip each.  On by default since it ran green on a
+# B200 (profiles/r02_experimental_switches_gpu.txt); False selects the composed formulas.
+FUSED_ADJOINTS = [True]
 
 
 def potri(L):
@@ -171,14 +188,14 @@ def trsm_bwd(L, X, Xbar, U=None, want_lbar=True):
 
 
 # ------------------------------------------------------------------------- autograd Functions
-# EXPERIMENTAL switch (off until seen green on a GPU; the CPU tests run both settings): let the
+# Switch (on by default since it ran green on a B200; the CPU tests run both settings): let the
 # adjoint of a triangular-aware product skip the zero tiles too.  With C = tri_a(A) tri_b(B)^T:
 #   dA = G tri_b(B)      -> NT product with B^T, which is triangular the other way round;
 #   dB = tri_b(G^T tri_a(A)) -> only the wanted triangle is computed (lower-output GEMM; an upper
 #                           triangle is computed as the lower triangle of the transpose).
 # For the SVGP bound with a full q_sqrt (conditionals.py:109-111) this halves two of the four
 # N M^2 products of the backward pass.
-TRI_AWARE_ADJOINTS = [False]
+TRI_AWARE_ADJOINTS = [True]
 _FLIP = {TRI_NONE: TRI_NONE, TRI_LOWER: TRI_UPPER, TRI_UPPER: TRI_LOWER}
 
 
@@ -234,6 +251,26 @@ class _MatmulNT(torch.autograd.Function):
         return dA, dB, None, None
 
 
+class _RowSumSq(torch.autograd.Function):
+    """sum_k A[i, k]^2 per row (the reference's reduce_sum(square(A), 0) in the transposed
+    orientation, conditionals.py:94,118): one pass of gps_row_sumsq, no N x M temporary."""
+
+    @staticmethod
+    def forward(ctx, A):
+        A = _prep(A)
+        ctx.save_for_backward(A)
+        return row_sumsq(A)
+
+    @staticmethod
+    def backward(ctx, g):
+        (A,) = ctx.saved_tensors
+        return A * (2.0 * g).unsqueeze(1)
+
+
+def row_sumsq_ad(A):
+    return _RowSumSq.apply(A)
+
+
 def matmul_nt(A, B, a_tri=TRI_NONE, b_tri=TRI_NONE):
     """A @ B.T; a_tri / b_tri declare A / B triangular (zero tiles are skipped)."""
     return _MatmulNT.apply(A, B, a_tri, b_tri)
@@ -263,18 +300,19 @@ class _Cholesky(torch.autograd.Function):
     evaluated with U = L^-T and triangular-aware tensor-core GEMMs."""
 
     @staticmethod
-    def forward(ctx, K):
+    def forward(ctx, K, share):
         L = potrf(K)
         ctx.save_for_backward(L)
+        ctx.share = share
         return L
 
     @staticmethod
     def backward(ctx, Lbar):
         (L,) = ctx.saved_tensors
         if FUSED_ADJOINTS[0]:
-            return chol_bwd(L, Lbar, tri_inv_t(L))
+            return chol_bwd(L, Lbar, tri_inv_t(L, ctx.share)), None
         Lbar = torch.tril(_prep(Lbar))
-        U = tri_inv_t(L)
+        U = tri_inv_t(L, ctx.share)
         # P = Phi(L^T Lbar):  (L^T Lbar)[m,n] = sum_k Lt[m,k] Lbar_t[n,k]
         P = gemm_nt(transpose(L), transpose(Lbar), a_tri=TRI_UPPER, b_tri=TRI_UPPER)
         P = torch.tril(P)
@@ -282,11 +320,14 @@ class _Cholesky(torch.autograd.Function):
         # S = U P U^T:  Qt = U P^T ; S = U Qt^T ... with NT products: Qt[m,n] = sum_k U[m,k] P[n,k]
         Qt = gemm_nt(U, P, a_tri=TRI_UPPER, b_tri=TRI_LOWER)
         S = gemm_nt(U, Qt, a_tri=TRI_UPPER)
-        return 0.5 * (S + S.t())
+        return 0.5 * (S + S.t()), None
 
 
 def cholesky(K):
-    return _Cholesky.apply(K)
+    share = {}
+    L = _Cholesky.apply(K, share)
+    L._gps_share = share       # travels with the factor: one L^-T for the forward pass and all adjoints
+    return L
 
 
 class _TrsmRLT(torch.autograd.Function):
@@ -294,6 +335,7 @@ class _TrsmRLT(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, B, L):
+        ctx.share = _share_of(L)
         L = _prep(L)
         X = _prep(B).clone()
         trsm_rlt_(L, X)
@@ -304,7 +346,7 @@ class _TrsmRLT(torch.autograd.Function):
     def backward(ctx, Xbar):
         X, L = ctx.saved_tensors
         Xbar = _prep(Xbar)
-        U = tri_inv_t(L)
+        U = tri_inv_t(L, ctx.share)
         if FUSED_ADJOINTS[0]:
             Bbar, dL = trsm_bwd(L, X, Xbar, U, want_lbar=ctx.needs_input_grad[1])
             return (Bbar if ctx.needs_input_grad[0] else None), dL
@@ -337,8 +379,9 @@ class _TriInvT(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, L):
+        share = _share_of(L)
         L = _prep(L)
-        U = tri_inv_t(L)
+        U = tri_inv_t(L, share)
         ctx.save_for_backward(U)
         return U
 

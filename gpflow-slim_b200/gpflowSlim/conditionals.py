@@ -17,32 +17,39 @@ def conditional(Xnew, X, kern, f, *, full_cov=False, q_sqrt=None, white=False):
     """conditionals.py:25-66."""
     Xnew, X = to_tensor(Xnew), to_tensor(X)
     Kmm = kern.K_jittered(X, settings.numerics.jitter_level)
-    Kmn = kern.K(X, Xnew)
+    Knm = kern.K(Xnew, X)                 # Kmn^T, evaluated directly in the orientation used below
     Knn = kern.K(Xnew) if full_cov else kern.Kdiag(Xnew)
-    return base_conditional(Kmn, Kmm, Knn, f, full_cov=full_cov, q_sqrt=q_sqrt, white=white)
+    return _base_conditional_t(Knm, Kmm, Knn, f, full_cov=full_cov, q_sqrt=q_sqrt, white=white)
 
 
 def feature_conditional(Xnew, feat, kern, f, *, full_cov=False, q_sqrt=None, white=False):
     """conditionals.py:70-77."""
     Xnew = to_tensor(Xnew)
     Kmm = feat.Kuu(kern, jitter=settings.numerics.jitter_level)
-    Kmn = feat.Kuf(kern, Xnew)
+    Knm = feat.Kfu(kern, Xnew)            # Kuf^T [N, M]
     Knn = kern.K(Xnew) if full_cov else kern.Kdiag(Xnew)
-    return base_conditional(Kmn, Kmm, Knn, f, full_cov=full_cov, q_sqrt=q_sqrt, white=white)
+    return _base_conditional_t(Knm, Kmm, Knn, f, full_cov=full_cov, q_sqrt=q_sqrt, white=white)
 
 
 def base_conditional(Kmn, Kmm, Knn, f, *, full_cov=False, q_sqrt=None, white=False):
     """conditionals.py:81-121.  Kmn [M, N], Kmm [M, M], Knn [N] or [N, N], f [M, K],
     q_sqrt None | [M, K] | [M, M, K]  ->  fmean [N, K], fvar [N, K] or [N, N, K]."""
-    Kmn, Kmm, Knn, f = to_tensor(Kmn), to_tensor(Kmm), to_tensor(Knn), to_tensor(f)
+    return _base_conditional_t(_ops.t(to_tensor(Kmn)), Kmm, Knn, f, full_cov=full_cov, q_sqrt=q_sqrt,
+                               white=white)
+
+
+def _base_conditional_t(Knm, Kmm, Knn, f, *, full_cov=False, q_sqrt=None, white=False):
+    """base_conditional with the cross-covariance handed over as Knm = Kmn^T [N, M] (what
+    `conditional` / `feature_conditional` evaluate directly: no 8 N M byte transpose)."""
+    Knm, Kmm, Knn, f = to_tensor(Knm), to_tensor(Kmm), to_tensor(Knn), to_tensor(f)
     num_func = f.shape[1]
     Lm = _ops.cholesky(Kmm)                                   # :84
-    At = _ops.trsm_rlt(_ops.t(Kmn), Lm)                       # :87   At = A^T, [N, M]
+    At = _ops.trsm_rlt(Knm, Lm)                               # :87   At = A^T, [N, M]
     if full_cov:
         fvar = Knn - _ops.matmul_nt(At, At)                   # :90   A^T A
         fvar = fvar.unsqueeze(0).expand(num_func, -1, -1)
     else:
-        fvar = Knn - (At ** 2).sum(1)                         # :94
+        fvar = Knn - _ops.row_sumsq_ad(At)                    # :94
         fvar = fvar.unsqueeze(0).expand(num_func, -1)
     if not white:
         # A <- Lm^-T A  (:99-100);  At <- At Lm^-1 = At U^T with U = Lm^-T
@@ -62,7 +69,7 @@ def base_conditional(Kmn, Kmm, Knn, f, *, full_cov=False, q_sqrt=None, white=Fal
             for k in range(num_func):
                 Lkt = _ops.t(torch.tril(q_sqrt[:, :, k]))
                 LTAt = _ops.matmul_nt(At, Lkt, b_tri=TRI_UPPER)               # [N, M]
-                adds.append(_ops.matmul_nt(LTAt, LTAt) if full_cov else (LTAt ** 2).sum(1))
+                adds.append(_ops.matmul_nt(LTAt, LTAt) if full_cov else _ops.row_sumsq_ad(LTAt))
             add = torch.stack(adds)
         else:
             raise ValueError('Bad dimension for q_sqrt: %s' % str(q_sqrt.dim()))

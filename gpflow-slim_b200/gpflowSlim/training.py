@@ -67,8 +67,7 @@ class DeviceAdam(object):
 
 
 class GraphedStep(object):
-    """EXPERIMENTAL (written without GPU access at the end of round 1; validated by
-    tests/test_gpu_experimental.py in round 2).  One training step -- objective, gradients of
+    """One training step -- objective, gradients of
     every trainable tensor, Adam update -- captured ONCE in a CUDA graph and replayed per
     minibatch ("CUDA-graph replay for SVGP").  The SVGP step of BASELINE
     config C4 issues 37 library calls and ~100 torch ops: ~2 ms of host time per step (measured
@@ -106,7 +105,9 @@ class GraphedStep(object):
         self.graph = torch.cuda.CUDAGraph()
         _ops.set_graph_capture(True)
         try:
-            with torch.cuda.graph(self.graph):
+            # capture on the stream the warm-up ran on: per-stream library state (the split-K
+            # scratch of the GEMM) then exists already -- no allocation may happen while capturing
+            with torch.cuda.graph(self.graph, stream=side):
                 self.static_objective = self._step()
         finally:
             _ops.set_graph_capture(False)

@@ -121,12 +121,16 @@ def trsm_rlt_(L, B):
     return B
 
 
-def tri_inv_t(L):
+def tri_inv_t(L, share=None):
     n = L.shape[0]
     return torch.linalg.solve_triangular(torch.tril(L), torch.eye(n, dtype=F64), upper=False).t().contiguous()
 
 
 def row_sumsq(A):
+    return (A ** 2).sum(1)
+
+
+def row_sumsq_ad(A):
     return (A ** 2).sum(1)
 
 
@@ -196,7 +200,7 @@ def gpr_predict(prog, X, Yc, noise, Xnew, full_cov=False):
         return mean, kdiag(prog, Xnew) - (A ** 2).sum(0)
 
 
-NAMES = ['gemm_nt', 'transpose', 'potrf', 'trsm_rlt_', 'tri_inv_t', 'row_sumsq', 'matmul_nt',
+NAMES = ['gemm_nt', 'transpose', 'potrf', 'trsm_rlt_', 'tri_inv_t', 'row_sumsq', 'row_sumsq_ad', 'matmul_nt',
          'matmul', 't', 'cholesky', 'trsm_rlt', 'solve_lower', 'solve_upper_t', '_TriInvT', 'gram',
          'kdiag', 'gpr_loglik', 'gpr_predict']
 

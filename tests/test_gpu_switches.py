@@ -144,15 +144,17 @@ def test_graphed_svgp_step_equals_eager_steps():
                                                                        timed(lambda: step(Xb, Yb))))
 
 
+@pytest.mark.parametrize('fused,tri_aware', [(False, False), (False, True), (True, False)])
 @pytest.mark.parametrize('name', ['svgp_white_full', 'svgp_nonwhite_full', 'sgpr', 'functions'])
-def test_tri_aware_adjoints_match_reference_golden(golden, name, monkeypatch):
-    """ops.TRI_AWARE_ADJOINTS: the adjoint of a triangular-aware product skips the zero tiles as
-    well (new flag combinations of the DMMA GEMM: b_tri + lower-only output, flipped a_tri).  The
-    CPU double already holds it to these goldens; this is the same check on the real kernels."""
+def test_adjoint_switches_match_reference_golden(golden, name, fused, tri_aware, monkeypatch):
+    """ops.FUSED_ADJOINTS / ops.TRI_AWARE_ADJOINTS are both on by default (that combination is what
+    tests/test_gpu_parity.py runs); the other three combinations -- the composed adjoint formulas,
+    and products whose adjoints do not skip the zero tiles -- must give the same gradients."""
     import gpflowSlim as gpf
     from gpflowSlim._backend import ops
     from util import relerr
-    monkeypatch.setattr(ops, 'TRI_AWARE_ADJOINTS', [True])
+    monkeypatch.setattr(ops, 'TRI_AWARE_ADJOINTS', [tri_aware])
+    monkeypatch.setattr(ops, 'FUSED_ADJOINTS', [fused])
     gold = golden(name)
     res = cases.run_case(gpf, name, conv)
     for key in sorted(gold):

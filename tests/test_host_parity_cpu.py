@@ -54,7 +54,11 @@ def gpf_raw(monkeypatch):
     """The package with only the library-touching entry points replaced: its hand-written
     autograd adjoints (ops.py) are the code under test."""
     import gpflowSlim
+    from gpflowSlim._backend import ops
     cpu_ops_double.install(monkeypatch, level='raw')
+    # the composed adjoint formulas of ops.py are the code under test here; the one-call library
+    # adjoints (the default, FUSED_ADJOINTS) are covered by tests/test_library_on_cpu.py and on the GPU
+    monkeypatch.setattr(ops, 'FUSED_ADJOINTS', [False])
     old = gpflowSlim.settings.device
     gpflowSlim.settings.device = 'cpu'
     yield gpflowSlim

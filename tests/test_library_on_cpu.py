@@ -297,7 +297,7 @@ def test_fused_gpr_objective_gradient_and_prediction(gpf):
 
 @pytest.mark.skipif(not FULL, reason='GPSLIM_CPU_LIB_FULL=1')
 def test_experimental_switches_through_the_real_dispatch_code(gpf, golden):
-    """The switches that are still off by default (tests/test_gpu_experimental.py), through the
+    """The switches with an alternative implementation (tests/test_gpu_switches.py), through the
     shipped host code on the CPU build: gram_impl = 2 (shared-memory interpreter kernels: their
     launch configuration and shared-memory sizing are host code) on the NKN case, and the
     triangular-aware matmul adjoints on a non-whitened SVGP."""
@@ -316,17 +316,17 @@ def test_experimental_switches_through_the_real_dispatch_code(gpf, golden):
         check('nkn')
     finally:
         h.set_option('gram_impl', 0)
-    ops.TRI_AWARE_ADJOINTS[0] = True
+    ops.TRI_AWARE_ADJOINTS[0] = False        # the defaults are True / True: run the other settings
     try:
         check('svgp_nonwhite_diag')
     finally:
-        ops.TRI_AWARE_ADJOINTS[0] = False
-    ops.FUSED_ADJOINTS[0] = True             # backward of cholesky / trsm_rlt in one library call each
+        ops.TRI_AWARE_ADJOINTS[0] = True
+    ops.FUSED_ADJOINTS[0] = False            # composed adjoints instead of one library call each
     try:
         check('svgp_white_diag')
         check('functions')
     finally:
-        ops.FUSED_ADJOINTS[0] = False
+        ops.FUSED_ADJOINTS[0] = True
 
 
 # ----------------------------------------------------------------------------- distributed path

@@ -152,6 +152,20 @@ def main():
                               'ELBO + grad (Z, q_mu, q_sqrt, theta) + Adam step', 'n_gpus': world,
                   'metric': 'SVGP steps/s', 'value': 1e3 / ms, 'ms': ms, 'tflops_model': flop / ms / 1e9,
                   'objective_last': float(obj)}]
+        if world == 1:
+            # the same step captured once in a CUDA graph and replayed (SURVEY.md 8d timing method)
+            m2 = gpf.models.SVGP(Xd[:B], Yd[:B], gpf.kernels.RBF(d, ARD=True, lengthscales=4.0),
+                                 gpf.likelihoods.Gaussian(var=0.1), Z=Z, num_data=n)
+            gstep = gpf.training.GraphedStep(m2, Xd[:B], Yd[:B], learning_rate=1e-3)
+            st2 = {'i': 0}
+
+            def graphed():
+                i0 = (st2['i'] * B) % (n - B)
+                st2['i'] += 1
+                return gstep(Xd[i0:i0 + B], Yd[i0:i0 + B])
+            gms, gobj = timed(graphed, max(args.reps, 20), warm=5)
+            lines.append(dict(lines[0], metric='SVGP steps/s (CUDA-graph replay)', value=1e3 / gms, ms=gms,
+                              tflops_model=flop / gms / 1e9, objective_last=float(gobj)))
         if world > 1:
             dist.destroy_process_group()
     if rank == 0:
