@@ -50,6 +50,10 @@ struct GemmArgs {
   int split_k, k_chunk;
   double* part;
   int64_t ldp, part_stride;
+  // strided batch (cp.async kernel only): blockIdx.y / blockIdx.z select one of by x bz independent
+  // products whose operands sit at uniform strides (diagonal blocks of a matrix, stacked tiles)
+  int batch_y;                 // 0: blockIdx.y is the split-K slice; > 0: blockIdx.y is a batch index
+  int64_t sAy, sBy, sCy, sAz, sBz, sCz;
 };
 
 __device__ __forceinline__ void tile_coords(const GemmArgs& g, int bid, int& ti, int& tj) {
@@ -224,8 +228,15 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs& g, double (&acc)[8
 }
 
 template <bool VEC16>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_dmma_kernel(const GemmArgs g) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_dmma_kernel(const GemmArgs g_in) {
   extern __shared__ __align__(16) double smem[];
+  GemmArgs g = g_in;
+  if (g.batch_y > 0) {
+    const int64_t by = blockIdx.y, bz = blockIdx.z;
+    g.A += by * g.sAy + bz * g.sAz;
+    g.B += by * g.sBy + bz * g.sBz;
+    g.C += by * g.sCy + bz * g.sCz;
+  }
   int ti, tj;
   tile_coords(g, blockIdx.x, ti, tj);
   const int m0 = ti * BM, n0 = tj * BN;
@@ -304,10 +315,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_dmma_kernel(const Gem
 // C = alpha * sum_s part[s] + beta * C over the elements the product writes (all, or j <= i)
 __global__ void splitk_reduce_kernel(const double* __restrict__ part, int64_t ldp, int64_t stride, int nsplit,
                                      double* __restrict__ C, int64_t ldc, int M, int N, double alpha, double beta,
-                                     int lower) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+                                     int lower, const int64_t* __restrict__ rowlo, int64_t lo_off) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;      // blockDim.x == BN: one tile column per block
   for (int i = blockIdx.y; i < M; i += gridDim.y) {
     if (j >= N || (lower && j > i)) continue;
+    // lo_mode 2: tiles wholly left of the first wanted column of their first row were never computed
+    if (rowlo && (int64_t)blockIdx.x * BN + BN - 1 + lo_off < rowlo[i / BM * BM]) continue;
     double s = 0.0;
     for (int q = 0; q < nsplit; ++q) s += part[(int64_t)q * stride + (int64_t)i * ldp + j];
     double* c = C + (int64_t)i * ldc + j;
@@ -575,7 +588,7 @@ double gemm_flops(const GemmArgs& g) {
 
 int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, Mat C, int a_tri,
                        int b_tri, int c_uplo, const int64_t* rowlim, int64_t coff, double flops,
-                       const int64_t* rowlo, int64_t lo_off, int lo_mode) {
+                       const int64_t* rowlo, int64_t lo_off, int lo_mode, const GemmBatch* batch) {
   if (A.cols != B.cols) return gps_fail(h, -3, "gemm_nt: K mismatch (%lld vs %lld)",
                                         (long long)A.cols, (long long)B.cols);
   if (C.rows != A.rows || C.cols != B.rows) return gps_fail(h, -6, "gemm_nt: C shape mismatch");
@@ -593,12 +606,21 @@ int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, M
   g.rowlim = rowlim; g.coff = coff;
   g.rowlo = rowlo; g.lo_off = lo_off; g.lo_mode = rowlo ? lo_mode : 0;
   g.split_k = 1; g.k_chunk = 0; g.part = nullptr; g.ldp = 0; g.part_stride = 0;
+  g.batch_y = 0; g.sAy = g.sBy = g.sCy = g.sAz = g.sBz = g.sCz = 0;
+  int batch_z = 1;
+  if (batch && batch->ny * batch->nz > 1) {
+    if (batch->ny < 1 || batch->nz < 1 || batch->ny > 65535 || batch->nz > 65535)
+      return gps_fail(h, -3, "gemm_nt: bad batch counts");
+    g.batch_y = batch->ny; batch_z = batch->nz;
+    g.sAy = batch->sAy; g.sBy = batch->sBy; g.sCy = batch->sCy;
+    g.sAz = batch->sAz; g.sBz = batch->sBz; g.sCz = batch->sCz;
+  }
   if (c_uplo == C_ROWMAP && !rowlim) return gps_fail(h, -7, "gemm_nt: C_ROWMAP needs a row-limit array");
   // split-K: a product with a long K and too few output tiles to fill the SMs -- the 1024 x 1024 x 8192
   // products of the SVGP backward are 64 (36 lower) tiles on 148 SMs, an M x R product with R <= 128 is
   // M/128 tiles -- is cut into K slices (blockIdx.y); the partial tiles go to a per-stream scratch and
   // one reduction pass applies alpha / beta and the lower-output mask.  One wave of CTAs at most.
-  if (h->gemm_splitk && h->gemm_impl != 1 && (c_uplo == C_ALL || c_uplo == C_LOWER) && !rowlo &&
+  if (h->gemm_splitk && h->gemm_impl != 1 && (c_uplo == C_ALL || c_uplo == C_LOWER) && g.batch_y == 0 &&
       a_tri == TRI_NONE && b_tri == TRI_NONE && g.K >= 512) {
     const int tiles = (c_uplo == C_LOWER && g.M == g.N) ? g.tiles_m * (g.tiles_m + 1) / 2 : g.tiles_m * g.tiles_n;
     int split = h->sm_count / (tiles > 0 ? tiles : 1);
@@ -625,13 +647,20 @@ int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, M
       h->events.push_back(e);
     }
     ev = &h->events[h->events_used++];
-    ev->flops = flops >= 0.0 ? flops : gemm_flops(g);
+    ev->flops = flops >= 0.0 ? flops : gemm_flops(g) * (g.batch_y > 0 ? (double)g.batch_y * batch_z : 1.0);
     cudaEventRecord(ev->a, h->stream);
   }
 
   if (h->gemm_impl == 1) {
     dim3 grid((g.N + 15) / 16, (g.M + 15) / 16);
-    gemm_nt_naive_kernel<<<grid, dim3(16, 16), 0, h->stream>>>(g);
+    for (int bz = 0; bz < batch_z; ++bz)
+      for (int by = 0; by < (g.batch_y > 0 ? g.batch_y : 1); ++by) {
+        GemmArgs gb = g;
+        gb.A += by * g.sAy + bz * g.sAz;
+        gb.B += by * g.sBy + bz * g.sBz;
+        gb.C += by * g.sCy + bz * g.sCz;
+        gemm_nt_naive_kernel<<<grid, dim3(16, 16), 0, h->stream>>>(gb);
+      }
   } else {
     if (!h->attr_gemm) {
       cudaFuncSetAttribute(gemm_nt_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -643,11 +672,13 @@ int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, M
     bool vec16 = ((A.ld & 1) == 0) && ((B.ld & 1) == 0) &&
                  ((reinterpret_cast<uintptr_t>(A.p) & 15) == 0) &&
                  ((reinterpret_cast<uintptr_t>(B.p) & 15) == 0);
+    if (g.batch_y > 0 && ((g.sAy | g.sBy | g.sAz | g.sBz) & 1)) vec16 = false;
     unsigned grid = (unsigned)(g.tiles_m * g.tiles_n);
     // gemm_impl 0: TMA kernel whenever the operands qualify; 2: force the cp.async kernel
     CUtensorMap tmA, tmB;
-    bool tma = vec16 && h->gemm_impl == 0 && g.K > 0 && make_tensor_map(&tmA, A) && make_tensor_map(&tmB, B);
-    const dim3 grid2(grid, (unsigned)g.split_k);
+    bool tma = vec16 && h->gemm_impl == 0 && g.K > 0 && g.batch_y == 0 && make_tensor_map(&tmA, A) &&
+               make_tensor_map(&tmB, B);
+    const dim3 grid2(grid, (unsigned)(g.batch_y > 0 ? g.batch_y : g.split_k), (unsigned)batch_z);
     if (tma) {
       if (!h->attr_tma) {
         cudaFuncSetAttribute(gemm_nt_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM);
@@ -663,7 +694,8 @@ int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, M
       h->launches++;
       splitk_reduce_kernel<<<dim3((unsigned)((g.N + 127) / 128), (unsigned)(g.M < 4096 ? g.M : 4096)), 128, 0,
                              h->stream>>>(g.part, g.ldp, g.part_stride, g.split_k, g.C, g.ldc, g.M, g.N,
-                                          g.alpha, g.beta, c_uplo == C_LOWER);
+                                          g.alpha, g.beta, c_uplo == C_LOWER, g.lo_mode == 2 ? g.rowlo : nullptr,
+                                          g.lo_off);
     }
   }
   if (ev) cudaEventRecord(ev->b, h->stream);

@@ -175,6 +175,11 @@ int gps_set_option(gps_handle* h, const char* name, int64_t value) {
     h->leaf_impl = (int)value;
     return 0;
   }
+  if (!strcmp(name, "trsm_leaf")) {
+    if (value < GPS_NB || value > 4096 || (value & (value - 1))) return gps_fail(h, -3, "trsm_leaf must be a power of two in [128, 4096]");
+    h->trsm_leaf = (int)value;
+    return 0;
+  }
   if (!strcmp(name, "gemm_splitk")) {
     h->gemm_splitk = (int)value;
     return 0;

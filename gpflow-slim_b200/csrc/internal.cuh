@@ -44,7 +44,11 @@ enum WsSlot {
   WS_ADJ_A,       // ... three n x ld scratch matrices
   WS_ADJ_B,
   WS_ADJ_C,
-  WS_SPLITK,      // split-K partial tiles (gemm.cu)
+  WS_SPLITK,      // (unused: split-K scratch is per stream, gps_ws_splitk)
+  WS_LEAF_U,      // prefix solves: inverses of the aligned diagonal blocks of size trsm_leaf,
+  WS_LEAF_T,      //   U_b = L_bb^-T (upper) and T_b = L_bb^-1 (lower), stacked [nblk][leaf][leaf]
+  WS_LEAF_W,      //   per-level scratch of the batched inverse
+  WS_LEAF_X,      //   output of a leaf product before it is copied back over its input
   WS_COUNT
 };
 
@@ -59,6 +63,8 @@ struct gps_handle {
   int gram_impl = 0;   // 0 = register-tiled fast path for single stationary kernels, 1 = interpreter only,
                        // 2 = experimental shared-memory-accumulator interpreter backward
   int profile = 0;
+  int trsm_leaf = 512; // prefix solves: aligned diagonal blocks of this size (a power-of-two multiple of 128)
+                       // are solved by ONE product with their explicit inverse; 128 = strips only
   int gemm_splitk = 1; // split-K for long-K products with few output tiles (0 switches it off)
   // function attributes (opt-in shared memory sizes) are per device: one flag set per handle
   bool attr_gemm = false, attr_tma = false, attr_potrf = false;
@@ -105,13 +111,16 @@ int gps_as_i64(gps_handle* h, const DLTensor* t, int argidx, const char* name, i
 enum { TRI_NONE = 0, TRI_LOWER = 1, TRI_UPPER = 2 };
 enum { C_ALL = 0, C_LOWER = 1, C_ROWMAP = 2 };
 
+// strided batch of independent products: member (y, z) uses A + y*sAy + z*sAz etc.
+struct GemmBatch { int ny, nz; int64_t sAy, sBy, sCy, sAz, sBz, sCz; };
+
 // C = alpha * A * B^T + beta * C   (A: MxK, B: NxK, C: MxN, all row-major)
 // c_uplo == C_ROWMAP: element (r, c) is updated iff c + coff <= rowlim[r] (device array,
 // non-decreasing).  flops >= 0 overrides the profile's flop count for this launch.
 int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, Mat C, int a_tri,
                        int b_tri, int c_uplo, const int64_t* rowlim = nullptr, int64_t coff = 0,
                        double flops = -1.0, const int64_t* rowlo = nullptr, int64_t lo_off = 0,
-                       int lo_mode = 0);
+                       int lo_mode = 0, const GemmBatch* batch = nullptr);
 
 // ----------------------------------------------------------------------------- factorisation
 // Factor the n x n block at A (lower, in place) and solve the `below` rows under it:

@@ -561,20 +561,127 @@ int gps_trsm_rec(gps_handle* h, Mat L, Mat B, int64_t blk0, const double* tinv) 
   return gps_trsm_rec(h, L.sub(n1, n1, n2, n2), B2, blk0 + n1 / NB, tinv);
 }
 
+namespace {
+// ---- explicit inverses of the aligned diagonal blocks ("big leaves") --------------------
+// For every full diagonal block b of size bs (bs = 128 * 2^q) of the factor L:
+//   U_b = L_bb^-T (upper)  and  T_b = L_bb^-1 = U_b^T (lower),  stacked densely [b][bs][bs].
+// Built bottom-up from the 128 x 128 block inverses, ALL blocks of a level in one strided-batch
+// launch per product:   W = -U11 L21^T,   U12 = W U22 = W T22^T,   T21 = U12^T = T22 W^T
+// (three NT products per level; keeping T next to U removes every transpose).
+__global__ void leaf_diag_kernel(const double* __restrict__ tinv, double* __restrict__ Uo,
+                                 double* __restrict__ To, int bs, int per) {
+  __shared__ double tile[32][33];
+  const int blk = blockIdx.z;                      // global 128-block index
+  const int z = blk / per, j = blk % per;
+  const int64_t off = (int64_t)z * bs * bs + (int64_t)j * NB * (bs + 1);
+  const double* T = tinv + (int64_t)blk * NB * NB;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const double v = T[(r0 + i) * NB + c0 + threadIdx.x];
+    tile[i][threadIdx.x] = v;
+    To[off + (int64_t)(r0 + i) * bs + c0 + threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8)      // U[r][c] = T[c][r]
+    Uo[off + (int64_t)(c0 + i) * bs + r0 + threadIdx.x] = tile[threadIdx.x][i];
+}
+
+struct LeafInv {
+  int bs = 0;               // 0: no big leaves (strips only)
+  int64_t nfull = 0;        // number of full aligned blocks
+  const double* U = nullptr;
+  const double* T = nullptr;
+  double* X = nullptr;      // [maxrows][bs] scratch
+};
+
+int build_leaf_inverses(gps_handle* h, Mat L, const double* tinv, int64_t maxrows, LeafInv* out) {
+  int rc;
+  const int bs = h->trsm_leaf;
+  out->bs = 0;
+  if (bs <= NB || L.rows < bs) return 0;
+  const int64_t nfull = L.rows / bs;
+  const int per = bs / NB;
+  const size_t bytes = (size_t)nfull * bs * bs * sizeof(double);
+  double* U = (double*)gps_ws(h, WS_LEAF_U, bytes);
+  double* T = (double*)gps_ws(h, WS_LEAF_T, bytes);
+  double* W = (double*)gps_ws(h, WS_LEAF_W, bytes / 4);
+  double* X = (double*)gps_ws(h, WS_LEAF_X, (size_t)maxrows * bs * sizeof(double));
+  if (!U || !T || !W || !X) return -102;
+  GPS_CUDA(h, cudaMemsetAsync(U, 0, bytes, h->stream));
+  GPS_CUDA(h, cudaMemsetAsync(T, 0, bytes, h->stream));
+  leaf_diag_kernel<<<dim3(NB / 32, NB / 32, (unsigned)(nfull * per)), dim3(32, 8), 0, h->stream>>>(tinv, U, T, bs, per);
+  GPS_LAUNCH_CHECK(h);
+  for (int sz = NB; sz < bs; sz *= 2) {
+    const int m = bs / (2 * sz);                       // nodes per block at this level
+    GemmBatch b;
+    b.ny = m; b.nz = (int)nfull;
+    const int64_t uy = (int64_t)2 * sz * (bs + 1), uz = (int64_t)bs * bs;
+    const int64_t ly = (int64_t)2 * sz * (L.ld + 1), lz = (int64_t)bs * (L.ld + 1);
+    const int64_t wy = (int64_t)sz * sz, wz = (int64_t)m * sz * sz;
+    Mat U11(U, sz, sz, bs), L21(L.p + (int64_t)sz * L.ld, sz, sz, L.ld), Wm(W, sz, sz, sz);
+    Mat T22(T + (int64_t)sz * (bs + 1), sz, sz, bs), U12(U + sz, sz, sz, bs), T21(T + (int64_t)sz * bs, sz, sz, bs);
+    // W = -U11 L21^T
+    b.sAy = uy; b.sAz = uz; b.sBy = ly; b.sBz = lz; b.sCy = wy; b.sCz = wz;
+    if ((rc = gps_gemm_nt_launch(h, -1.0, U11, L21, 0.0, Wm, TRI_UPPER, TRI_NONE, C_ALL, nullptr, 0, -1.0, nullptr,
+                                 0, 0, &b)))
+      return rc;
+    // U12 = W T22^T
+    b.sAy = wy; b.sAz = wz; b.sBy = uy; b.sBz = uz; b.sCy = uy; b.sCz = uz;
+    if ((rc = gps_gemm_nt_launch(h, 1.0, Wm, T22, 0.0, U12, TRI_NONE, TRI_LOWER, C_ALL, nullptr, 0, -1.0, nullptr, 0,
+                                 0, &b)))
+      return rc;
+    // T21 = T22 W^T
+    b.sAy = uy; b.sAz = uz; b.sBy = wy; b.sBz = wz; b.sCy = uy; b.sCz = uz;
+    if ((rc = gps_gemm_nt_launch(h, 1.0, T22, Wm, 0.0, T21, TRI_LOWER, TRI_NONE, C_ALL, nullptr, 0, -1.0, nullptr, 0,
+                                 0, &b)))
+      return rc;
+  }
+  out->bs = bs; out->nfull = nfull; out->U = U; out->T = T; out->X = X;
+  return 0;
+}
+
+// a node of the prefix recursions is split at a multiple of the big-leaf size while it is larger
+// than one leaf (so that leaves stay aligned); below that, at 128-block granularity as before
+int64_t split_node(int64_t n, int leaf) {
+  if (leaf > NB && n > leaf) return ((n + leaf - 1) / leaf / 2) * (int64_t)leaf;
+  return split_point(n);
+}
+
+// rows x bs leaf:  B <- B * op(inverse)  by one product into scratch + copy back
+int leaf_apply(gps_handle* h, Mat B, int64_t rows, const LeafInv& lv, int64_t c0, bool notrans) {
+  int rc;
+  const int bs = lv.bs;
+  const int64_t b = c0 / bs;
+  Mat X(lv.X, rows, bs, bs);
+  Mat Bl = B.sub(0, 0, rows, bs);
+  if (!notrans) {   // B L^-T = B T^T-form: X[r][j] = sum_{k<=j} B[r][k] T[j][k]
+    Mat T(const_cast<double*>(lv.T) + b * bs * bs, bs, bs, bs);
+    if ((rc = gps_gemm_nt_launch(h, 1.0, Bl, T, 0.0, X, TRI_NONE, TRI_LOWER, C_ALL))) return rc;
+  } else {          // B L^-1 = B T: X[r][j] = sum_{k>=j} B[r][k] U[j][k]
+    Mat U(const_cast<double*>(lv.U) + b * bs * bs, bs, bs, bs);
+    if ((rc = gps_gemm_nt_launch(h, 1.0, Bl, U, 0.0, X, TRI_NONE, TRI_UPPER, C_ALL))) return rc;
+  }
+  GPS_CUDA(h, cudaMemcpy2DAsync(Bl.p, Bl.ld * sizeof(double), X.p, X.ld * sizeof(double), bs * sizeof(double),
+                                rows, cudaMemcpyDeviceToDevice, h->stream));
+  return 0;
+}
+
 // Forward solve B <- B L^-T where row r of B is zero left of column start[r]: at the node that
 // covers columns [c0, c0 + n) only the rows with start < c0 + n take part, and the update GEMM
 // skips the leading zero K-range of each row tile.  With B = rows of the identity this yields
 // rows of U = L^-T at N^3/3 flops overall.
-namespace {
-int trsm_rlt_segs(gps_handle* h, Mat L, Mat B, int64_t c0, const double* tinv, const RowSegs& rs) {
+int trsm_rlt_segs(gps_handle* h, Mat L, Mat B, int64_t c0, const double* tinv, const RowSegs& rs,
+                  const LeafInv& lv) {
   int rc;
   int64_t n = L.rows;
   if (n <= 0) return 0;
   const int64_t rows = rs.active(c0 + n);
   if (rows <= 0) return 0;
+  if (lv.bs > NB && n == lv.bs && c0 % lv.bs == 0 && c0 / lv.bs < lv.nfull)
+    return leaf_apply(h, B, rows, lv, c0, false);
   if (n <= NB) return strip_launch(h, B.sub(0, 0, rows, n), n, tinv + (c0 / NB) * NB * NB);
-  int64_t n1 = split_point(n), n2 = n - n1;
-  if ((rc = trsm_rlt_segs(h, L.sub(0, 0, n1, n1), B.sub(0, 0, rows, n1), c0, tinv, rs))) return rc;
+  int64_t n1 = split_node(n, lv.bs), n2 = n - n1;
+  if ((rc = trsm_rlt_segs(h, L.sub(0, 0, n1, n1), B.sub(0, 0, rows, n1), c0, tinv, rs, lv))) return rc;
   const int64_t rows1 = rs.active(c0 + n1);
   if (rows1 > 0) {
     double flops = 2.0 * (double)n2 * rs.span(rows1, c0, c0 + n1);
@@ -583,20 +690,23 @@ int trsm_rlt_segs(gps_handle* h, Mat L, Mat B, int64_t c0, const double* tinv, c
                                  rs.dev, c0, 1)))
       return rc;
   }
-  return trsm_rlt_segs(h, L.sub(n1, n1, n2, n2), B.sub(0, n1, rows, n2), c0 + n1, tinv, rs);
+  return trsm_rlt_segs(h, L.sub(n1, n1, n2, n2), B.sub(0, n1, rows, n2), c0 + n1, tinv, rs, lv);
 }
 
 // B <- B L^-1 (solve X L = B) given Lt = L^T (upper, row-major) so that every product is NT;
 // columns are resolved right to left; row r wants the columns >= start[r] only.
-int trsm_rln_segs(gps_handle* h, Mat Lt, Mat B, int64_t c0, const double* tinv, const RowSegs& rs) {
+int trsm_rln_segs(gps_handle* h, Mat Lt, Mat B, int64_t c0, const double* tinv, const RowSegs& rs,
+                  const LeafInv& lv) {
   int rc;
   int64_t n = Lt.rows;
   if (n <= 0) return 0;
   const int64_t rows = rs.active(c0 + n);
   if (rows <= 0) return 0;
+  if (lv.bs > NB && n == lv.bs && c0 % lv.bs == 0 && c0 / lv.bs < lv.nfull)
+    return leaf_apply(h, B, rows, lv, c0, true);
   if (n <= NB) return strip_launch(h, B.sub(0, 0, rows, n), n, tinv + (c0 / NB) * NB * NB, true);
-  int64_t n1 = split_point(n), n2 = n - n1;
-  if ((rc = trsm_rln_segs(h, Lt.sub(n1, n1, n2, n2), B.sub(0, n1, rows, n2), c0 + n1, tinv, rs)))
+  int64_t n1 = split_node(n, lv.bs), n2 = n - n1;
+  if ((rc = trsm_rln_segs(h, Lt.sub(n1, n1, n2, n2), B.sub(0, n1, rows, n2), c0 + n1, tinv, rs, lv)))
     return rc;
   const int64_t rows1 = rs.active(c0 + n1);
   if (rows1 <= 0) return 0;
@@ -606,7 +716,7 @@ int trsm_rln_segs(gps_handle* h, Mat Lt, Mat B, int64_t c0, const double* tinv, 
                                B.sub(0, 0, rows1, n1), TRI_NONE, TRI_NONE, C_ALL, nullptr, 0, flops,
                                rs.dev, c0, 2)))
     return rc;
-  return trsm_rln_segs(h, Lt.sub(0, 0, n1, n1), B.sub(0, 0, rows1, n1), c0, tinv, rs);
+  return trsm_rln_segs(h, Lt.sub(0, 0, n1, n1), B.sub(0, 0, rows1, n1), c0, tinv, rs, lv);
 }
 
 int make_segs(gps_handle* h, const int64_t* row_start, int64_t rows, int64_t ncols, RowSegs* out) {
@@ -781,7 +891,9 @@ int gps_trsm_rlt_prefix(gps_handle* h, const DLTensor* Lt, DLTensor* B_inout,
   double* tinv = (double*)gps_ws(h, WS_TINV, (size_t)nblk * NB * NB * sizeof(double));
   if (!tinv) return -102;
   if ((rc = gps_block_inverses(h, L, tinv))) return rc;
-  return trsm_rlt_segs(h, L, B, 0, tinv, rs);
+  LeafInv lv;
+  if ((rc = build_leaf_inverses(h, L, tinv, B.rows, &lv))) return rc;
+  return trsm_rlt_segs(h, L, B, 0, tinv, rs, lv);
 }
 
 int gps_trsm_rln_prefix(gps_handle* h, const DLTensor* Lt, const DLTensor* Ltt, DLTensor* B_inout,
@@ -804,7 +916,9 @@ int gps_trsm_rln_prefix(gps_handle* h, const DLTensor* Lt, const DLTensor* Ltt, 
   double* tinv = (double*)gps_ws(h, WS_TINV, (size_t)nblk * NB * NB * sizeof(double));
   if (!tinv) return -102;
   if ((rc = gps_block_inverses(h, L, tinv))) return rc;
-  return trsm_rln_segs(h, LT, B, 0, tinv, rs);
+  LeafInv lv;
+  if ((rc = build_leaf_inverses(h, L, tinv, B.rows, &lv))) return rc;
+  return trsm_rln_segs(h, LT, B, 0, tinv, rs, lv);
 }
 
 int gps_tri_inv_t(gps_handle* h, const DLTensor* Lt, DLTensor* U_out) {

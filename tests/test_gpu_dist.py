@@ -43,9 +43,22 @@ def test_gemm_rowmap_masks_by_global_row(m, n, k, coff):
     assert_close(Cd, ref, 1e-13, 'rowmap gemm')
 
 
+@pytest.mark.parametrize('leaf', [128, 256, 512, 1024])
 @pytest.mark.parametrize('n,bs', [(384, 128), (1000, 256), (1500, 384), (4000, 512)])
-def test_prefix_triangular_solves(n, bs):
-    """Rows of U = L^-T and of K^-1 for a subset of block rows, against dense inverses."""
+def test_prefix_triangular_solves(n, bs, leaf):
+    """Rows of U = L^-T and of K^-1 for a subset of block rows, against dense inverses; with the
+    aligned diagonal blocks of size `leaf` solved by one product with their explicit inverse
+    (option trsm_leaf; 128 = strips only, 512 = default)."""
+    from gpflowSlim._backend.lib import handle_for
+    h = handle_for(dev())
+    h.set_option('trsm_leaf', leaf)
+    try:
+        _prefix_case(n, bs)
+    finally:
+        h.set_option('trsm_leaf', 512)
+
+
+def _prefix_case(n, bs):
     S = _spd(n, seed=n)
     L = np.linalg.cholesky(S)
     U, Kinv = np.linalg.inv(L).T, np.linalg.inv(S)

@@ -218,6 +218,47 @@ def test_split_k_gemm_through_the_launch_code(gpf):
         h.set_option('gemm_splitk', 1)     # the default
 
 
+def test_prefix_solves_with_big_leaves(gpf):
+    """gps_trsm_rlt_prefix / gps_trsm_rln_prefix with option trsm_leaf = 256: the aligned 256-blocks
+    are solved by one product with their explicit inverses (built for all blocks at once by
+    strided-batch products), the ragged tail by 128-strips; rows of U = L^-T and of K^-1 against
+    dense inverses, for rows that start inside and outside a leaf."""
+    from gpflowSlim._backend import dist_gpr, lib
+    rng = np.random.default_rng(11)
+    n, bs = 600, 128
+    A = rng.standard_normal((n, n + 3))
+    S = A @ A.T / (n + 3) + 0.5 * np.eye(n)
+    L = np.linalg.cholesky(S)
+    U, Kinv = np.linalg.inv(L).T, np.linalg.inv(S)
+    rows = np.concatenate([np.arange(0, 40), np.arange(128, 200), np.arange(384, 420), np.arange(512, 560)])
+    act = rows // bs * bs
+    h = lib.handle_for(None)
+
+    class Be(dist_gpr.CudaBackend):
+        def __init__(self):
+            self._L, self.device = lib, torch.device('cpu')
+    be = Be()
+    Ld = conv(L) + torch.triu(torch.full((n, n), 7.0, dtype=torch.float64), 1)       # junk above the diagonal
+    Lt = conv(L.T.copy())
+    results = {}
+    for leaf in (128, 256):
+        h.set_option('trsm_leaf', leaf)
+        try:
+            B = np.zeros((len(rows), n))
+            B[np.arange(len(rows)), rows] = 1.0
+            Bd = conv(B)
+            be.trsm_rlt_prefix_(Ld, Bd, act)
+            np.testing.assert_allclose(Bd.numpy(), U[rows], rtol=0, atol=1e-12 * np.abs(U).max())
+            be.trsm_rln_prefix_(Ld, Lt, Bd, act)
+            got = Bd.numpy()
+            keep = np.arange(n)[None, :] >= act[:, None]
+            assert np.abs(got - Kinv[rows])[keep].max() < 1e-11 * np.abs(Kinv).max()
+            results[leaf] = got[keep]
+        finally:
+            h.set_option('trsm_leaf', 512)
+    assert np.abs(results[128] - results[256]).max() < 1e-11 * np.abs(Kinv).max()
+
+
 @pytest.mark.parametrize('n,m', [(70, 33), (200, 140), (1, 1)])
 def test_library_side_adjoints(gpf, n, m):
     """gps_potri / gps_chol_bwd / gps_trsm_bwd (csrc/adjoint.cu), with U computed inside and with
