@@ -911,7 +911,7 @@ template <int DP>
 __global__ void __launch_bounds__(GRAM_THREADS)
 gram_bwd_stat_kernel(int type, int ard, int nd, int FT, int n_theta, const double* __restrict__ theta,
                      const double* __restrict__ FL, const double* __restrict__ FR, int64_t N, int64_t M,
-                     const BwdArgs w, double* __restrict__ part_theta) {
+                     const BwdArgs w, double* __restrict__ part_theta, double* __restrict__ Gout, int64_t ldg) {
   __shared__ __align__(16) double sl[DP][SLD];
   __shared__ __align__(16) double sr[DP][SLD];
   __shared__ double ssl[TILE], ssr[TILE];
@@ -990,6 +990,11 @@ gram_bwd_stat_kernel(int type, int ard, int nd, int FT, int n_theta, const doubl
           G[a][2 * bp + q] = Gq;
           if (!ard) acc_l[0] = fma(Gq, d2, acc_l[0]);
         }
+        if (Gout) {      // dObj / d(d2), kept for the input gradient (one skinny product afterwards)
+          double* gp = Gout + gi * ldg + gj;
+          if (ok0) gp[0] = G[a][2 * bp];
+          if (ok1) gp[1] = G[a][2 * bp + 1];
+        }
       }
     }
     if (ard) {
@@ -1041,6 +1046,33 @@ gram_bwd_stat_kernel(int type, int ard, int nd, int FT, int n_theta, const doubl
     for (int wq = 0; wq < GRAM_THREADS / 32; ++wq) sacc += red[wq][src];
     part_theta[cta * nacc + t] = sacc;
   }
+}
+
+// Input gradient of the fast path from G = dObj / d(d2) (N x M) and P = G [F_R | 1]  (N x (nd + 1)):
+//   d d2_ij / d x_id = 2 (f_id - f_jd) / l_d   =>   dX[i][d] = scale * 2 / l_d * (f_id * sum_j G_ij - sum_j G_ij f_jd)
+__global__ void stat_dx_finish_kernel(const double* __restrict__ P, int64_t ldp, const double* __restrict__ FL,
+                                      int FT, int nd, int ard, const double* __restrict__ theta, PlanDims pd,
+                                      int64_t N, int xcols, double scale, double* __restrict__ dX, int64_t lddx) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * xcols) return;
+  const int64_t i = idx / xcols;
+  const int c = (int)(idx - i * xcols);
+  double v = 0.0;
+  for (int k = 0; k < nd; ++k)
+    if (pd.dims[0][k] == c) {
+      const double l = theta[1 + (ard ? k : 0)];
+      v += scale * 2.0 / l * (FL[i * FT + k] * P[i * ldp + nd] - P[i * ldp + k]);
+    }
+  dX[i * lddx + c] = v;
+}
+
+// B[k][j] = F[j][k] for k < nd, B[nd][j] = 1   ((nd + 1) x M, the K-contiguous operand of P = G B^T)
+__global__ void stat_dx_operand_kernel(const double* __restrict__ F, int FT, int nd, int64_t M,
+                                       double* __restrict__ B, int64_t ldb) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  for (int k = 0; k < nd; ++k) B[(int64_t)k * ldb + j] = F[j * FT + k];
+  B[(int64_t)nd * ldb + j] = 1.0;
 }
 
 // single stationary primitive with the identity program and <= 16 active dimensions?
@@ -1260,7 +1292,7 @@ int gps_gram_bwd_mat(gps_handle* h, const gps_kernel_desc* desc, const double* t
   double* part = (double*)gps_ws(h, WS_PARTIAL, (size_t)nctas * nacc * sizeof(double));
   if (!part) return -102;
   double* pdx = nullptr;
-  if (dX) {
+  if (dX && !(stat_fast(h, pl) && !use_smem_acc)) {
     pdx = (double*)gps_ws(h, WS_PARTIAL2, (size_t)njc * N * X.cols * sizeof(double));
     if (!pdx) return -102;
   }
@@ -1270,15 +1302,37 @@ int gps_gram_bwd_mat(gps_handle* h, const gps_kernel_desc* desc, const double* t
   if (use_smem_acc) {
     gram_bwd_smem_kernel<<<dim3((unsigned)njc, (unsigned)itiles), NT2, smem2, h->stream>>>(
         pl, pd, nslots, theta, FL, FR, N, M, a, part, pdx);
-  } else if (!dX && stat_fast(h, pl)) {
+  } else if (stat_fast(h, pl)) {
     const PrimC P = pl.prims[0];
     const dim3 g2((unsigned)njc, (unsigned)itiles);
+    double* G = nullptr;
+    const int64_t ldg = (M + 15) / 16 * 16;
+    if (dX) {
+      G = (double*)gps_ws(h, WS_GRAM_G, (size_t)N * ldg * sizeof(double));
+      if (!G) return -102;
+    }
     if (P.ndims <= 4)
-      gram_bwd_stat_kernel<4><<<g2, GRAM_THREADS, 0, h->stream>>>(P.type, P.ard, P.ndims, pl.FT, pl.n_theta, theta, FL, FR, N, M, a, part);
+      gram_bwd_stat_kernel<4><<<g2, GRAM_THREADS, 0, h->stream>>>(P.type, P.ard, P.ndims, pl.FT, pl.n_theta, theta, FL, FR, N, M, a, part, G, ldg);
     else if (P.ndims <= 8)
-      gram_bwd_stat_kernel<8><<<g2, GRAM_THREADS, 0, h->stream>>>(P.type, P.ard, P.ndims, pl.FT, pl.n_theta, theta, FL, FR, N, M, a, part);
+      gram_bwd_stat_kernel<8><<<g2, GRAM_THREADS, 0, h->stream>>>(P.type, P.ard, P.ndims, pl.FT, pl.n_theta, theta, FL, FR, N, M, a, part, G, ldg);
     else
-      gram_bwd_stat_kernel<16><<<g2, GRAM_THREADS, 0, h->stream>>>(P.type, P.ard, P.ndims, pl.FT, pl.n_theta, theta, FL, FR, N, M, a, part);
+      gram_bwd_stat_kernel<16><<<g2, GRAM_THREADS, 0, h->stream>>>(P.type, P.ard, P.ndims, pl.FT, pl.n_theta, theta, FL, FR, N, M, a, part, G, ldg);
+    if (dX) {
+      GPS_LAUNCH_CHECK(h);
+      const int nd = P.ndims;
+      const int64_t ldpm = (nd + 1 + 15) / 16 * 16;
+      double* B = (double*)gps_ws(h, WS_GRAM_B, (size_t)(nd + 1) * ldg * sizeof(double));
+      double* Pm = (double*)gps_ws(h, WS_GRAM_P, (size_t)N * ldpm * sizeof(double));
+      if (!B || !Pm) return -102;
+      stat_dx_operand_kernel<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(FR, pl.FT, nd, M, B, ldg);
+      GPS_LAUNCH_CHECK(h);
+      if ((rc = gps_gemm_nt_launch(h, 1.0, Mat(G, N, M, ldg), Mat(B, nd + 1, M, ldg), 0.0, Mat(Pm, N, nd + 1, ldpm),
+                                   TRI_NONE, TRI_NONE, C_ALL)))
+        return rc;
+      const int64_t tot = N * X.cols;
+      stat_dx_finish_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(
+          Pm, ldpm, FL, pl.FT, nd, P.ard, theta, pd, N, (int)X.cols, a.dx_scale, dX->p, dX->ld);
+    }
   } else {
     gram_bwd_kernel<<<dim3((unsigned)njc, (unsigned)itiles), GRAM_THREADS, smem, h->stream>>>(
         pl, pd, theta, FL, FR, N, M, a, part, pdx);
@@ -1291,7 +1345,7 @@ int gps_gram_bwd_mat(gps_handle* h, const gps_kernel_desc* desc, const double* t
   GPS_CUDA(h, cudaMemcpyAsync(dtheta_out, part, pl.n_theta * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   if (trace_out)
     GPS_CUDA(h, cudaMemcpyAsync(trace_out, part + pl.n_theta, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  if (dX) {
+  if (dX && !(stat_fast(h, pl) && !use_smem_acc)) {
     int64_t tot = N * X.cols;
     reduce_dx_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(pdx, (int)njc, N, (int)X.cols,
                                                                           a.dx_scale, dX->p, dX->ld);

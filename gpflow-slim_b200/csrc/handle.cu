@@ -15,7 +15,28 @@ int gps_fail(gps_handle* h, int code, const char* fmt, ...) {
   return code;
 }
 
+static bool per_stream_slot(int slot) {
+  return slot == WS_TINV || slot == WS_INFO || slot == WS_LOGDET || slot == WS_ROWLO;
+}
+
 void* gps_ws(gps_handle* h, int slot, size_t bytes) {
+  if (per_stream_slot(slot) && h->stream != 0) {
+    // the handle's first (default / legacy) stream keeps the plain slot; side streams get their own
+    auto& e = h->stream_ws[std::make_pair(slot, h->stream)];
+    if (e.first && bytes <= e.second) return e.first;
+    cudaStreamSynchronize(h->stream);
+    if (e.first) cudaFree(e.first);
+    e = {nullptr, 0};
+    size_t want = bytes + bytes / 8 + 256;
+    void* p = nullptr;
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+      cudaGetLastError();
+      gps_fail(h, -102, "workspace allocation of %zu bytes failed", bytes);
+      return nullptr;
+    }
+    e = {p, want};
+    return p;
+  }
   if (bytes <= h->ws_bytes[slot] && h->ws_ptr[slot]) return h->ws_ptr[slot];
   // in-flight work may still use the old buffer
   cudaStreamSynchronize(h->stream);
@@ -144,6 +165,8 @@ int gps_destroy(gps_handle* h) {
   for (int i = 0; i < WS_COUNT; ++i)
     if (h->ws_ptr[i]) cudaFree(h->ws_ptr[i]);
   for (auto& kv : h->splitk_ws)
+    if (kv.second.first) cudaFree(kv.second.first);
+  for (auto& kv : h->stream_ws)
     if (kv.second.first) cudaFree(kv.second.first);
   for (auto& e : h->events) {
     cudaEventDestroy(e.a);

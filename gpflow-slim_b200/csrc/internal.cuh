@@ -49,6 +49,9 @@ enum WsSlot {
   WS_LEAF_T,      //   U_b = L_bb^-T (upper) and T_b = L_bb^-1 (lower), stacked [nblk][leaf][leaf]
   WS_LEAF_W,      //   per-level scratch of the batched inverse
   WS_LEAF_X,      //   output of a leaf product before it is copied back over its input
+  WS_GRAM_G,      // Gram fast-path backward with input gradient: G = dObj/d(d2)  [N][ldM]
+  WS_GRAM_B,      //   [F_R | 1]^T
+  WS_GRAM_P,      //   P = G [F_R | 1]
   WS_COUNT
 };
 
@@ -70,6 +73,9 @@ struct gps_handle {
   bool attr_gemm = false, attr_tma = false, attr_potrf = false;
   // split-K partial tiles, one buffer per stream (a handle may be driven from several streams)
   std::map<cudaStream_t, std::pair<void*, size_t>> splitk_ws;
+  // small scratch slots that calls running concurrently on different streams of one handle must
+  // not share (block inverses, info flag, row tables): kept per (slot, stream)
+  std::map<std::pair<int, cudaStream_t>, std::pair<void*, size_t>> stream_ws;
   void* ws_ptr[WS_COUNT] = {};
   size_t ws_bytes[WS_COUNT] = {};
   std::vector<GemmEvent> events;   // pool

@@ -154,9 +154,11 @@ class CudaBackend(object):
 
     # ---- streams / events for the look-ahead (CUDA streams, no tracing compiler)
     def streams(self):
-        """(main, chain, gather): the caller's stream and two high-priority side streams."""
+        """(main, chain, tb, gather): the caller's stream and three high-priority side streams
+        (chain highest: it carries the serial dependency chain of the factorisation)."""
         if getattr(self, '_side', None) is None:
-            self._side = (torch.cuda.Stream(self.device, priority=-1),
+            self._side = (torch.cuda.Stream(self.device, priority=-3),
+                          torch.cuda.Stream(self.device, priority=-2),
                           torch.cuda.Stream(self.device, priority=-1))
         return (torch.cuda.current_stream(self.device),) + self._side
 
@@ -196,6 +198,24 @@ class CudaBackend(object):
         va, vb, vc, vr = L.view(A), L.view(B), L.view(C), L.view(rowlim)
         h.check(h.lib.gps_gemm_nt_rowmap(h.ptr, -1.0, va.ref, vb.ref, 1.0, vc.ref, vr.ref, int(coff),
                                          float(flops)))
+
+    # plain device copies of the schedule, behind the backend so that the schedule checker of the
+    # tests (tests/test_dist_schedule_cpu.py) sees every access
+    def copy_(self, dst, src):
+        dst.copy_(src)
+
+    def zero_(self, t):
+        t.zero_()
+
+    def unpack_rows_(self, dst, src, index):
+        """dst[i, :] = src[index[i], :]"""
+        torch.index_select(src, 0, index, out=dst) if dst.is_contiguous() else dst.copy_(src.index_select(0, index))
+
+    def syrk_lower_(self, X, D):
+        """D <- D - X X^T, lower triangle only."""
+        h, L = self._h(), self._L
+        vx, vd = L.view(X), L.view(D)
+        h.check(h.lib.gps_gemm_nt(h.ptr, -1.0, vx.ref, vx.ref, 1.0, vd.ref, 0, 0, 1))
 
     def transpose(self, A):
         h, L = self._h(), self._L
@@ -254,36 +274,45 @@ class CudaBackend(object):
 # --------------------------------------------------------------------------------- collectives
 class _Comm(object):
     """torch.distributed plumbing (NCCL on GPUs, gloo in the CPU tests); a world of one needs
-    no process group at all."""
+    no process group at all.  `group` may be a dict {'chain': g1, 'tb': g2, 'gather': g3} of
+    process groups over the same ranks: the factorisation issues its three kinds of collectives
+    (diagonal-block broadcast, top-block broadcast, panel all-gather) on three communicators so
+    that a 100 MB all-gather never sits in front of a 2 MB broadcast of the critical path."""
 
     def __init__(self, group=None):
         import torch.distributed as dist
         self.dist = dist
-        self.group = group
+        self.groups = group if isinstance(group, dict) else {}
+        self.group = self.groups.get('gather') if isinstance(group, dict) else group
         if dist.is_available() and dist.is_initialized():
-            self.world = dist.get_world_size(group)
-            self.rank = dist.get_rank(group)
+            self.world = dist.get_world_size(self.group)
+            self.rank = dist.get_rank(self.group)
         else:
             self.world, self.rank = 1, 0
 
-    def global_rank(self, r):
-        if self.group is None or self.world == 1:
-            return r
-        return self.dist.get_global_rank(self.group, r)
+    def _g(self, which):
+        return self.groups.get(which, self.group)
 
-    def broadcast(self, t, src):
+    def global_rank(self, r, g=None):
+        g = self.group if g is None else g
+        if g is None or self.world == 1:
+            return r
+        return self.dist.get_global_rank(g, r)
+
+    def broadcast(self, t, src, which='chain'):
         if self.world > 1:
-            self.dist.broadcast(t, src=self.global_rank(src), group=self.group)
+            g = self._g(which)
+            self.dist.broadcast(t, src=self.global_rank(src, g), group=g)
 
     def all_gather(self, out, inp):
         if self.world > 1:
-            self.dist.all_gather_into_tensor(out, inp, group=self.group)
+            self.dist.all_gather_into_tensor(out, inp, group=self._g('gather'))
         else:
             out.copy_(inp.reshape(out.shape))
 
     def all_reduce_sum(self, t):
         if self.world > 1:
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self._g('gather'))
 
 
 # --------------------------------------------------------------------------------- the path
@@ -320,14 +349,20 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
     """Distributed Gram + Cholesky.  Returns (Lfull [N, ld] with the lower block triangle of
     L -- identical on every rank --, Lt [N, ld] = its transpose, alpha_t [R, N] = (L^-1 Yc)^T).
 
-    With `lookahead` the work of panel k is spread over three CUDA streams:
-      chain  (high priority): factor diagonal block k -> broadcast -> solve my panel rows ->
-              broadcast the solved block row k+1 ("top block") -> apply panel k to block
-              column k+1.  This is the only serial dependency chain of the factorisation and
-              it never waits for an all-gather or for a bulk update of the same panel.
-      gather (high priority): all-gather of the solved panel k -> column k of L on every rank.
-      main:   panel k applied to block column k+2 first (its completion releases the chain two
-              panels ahead), then to everything right of it (one masked DMMA GEMM each).
+    With `lookahead` the work of panel k is a software pipeline over four CUDA streams; only the
+    first carries the serial dependency chain of the factorisation, and it touches nothing but
+    512-row objects:
+      chain  (highest priority): owner(k) applies the previous panel to its diagonal block (SYRK),
+              factors it, broadcasts it; owner(k+1) solves ITS block row k+1 of the panel (the
+              "top block") at once.
+      tb     top block -> everyone (broadcast), then panel k applied to block column k+1 (the
+              block row k+2 of owner(k+2) first: the next top block).
+      gather the rest of the panel solve, all-gather of the solved panel -> column k of L (and row
+              k of L^T) on every rank, then panel k applied to block column k+2.
+      main   panel k applied to block columns >= k+3: the bulk, one masked DMMA GEMM per panel.
+    Writers of one block column are ordered main(<= c-3) -> gather(c-2) -> tb(c-1) -> solve(c) by
+    events; the chain never waits for an all-gather or a bulk update of the same or the previous
+    panel (look-ahead depth 2 with respect to the bulk).
     """
     N, R = Yc.shape
     P, rank = comm.world, comm.rank
@@ -419,9 +454,9 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
             mmax = max(m for _, m in below_all[k])
             send = send_buf[:mmax * nb].view(mmax, nb)
             if mrows:
-                send[:mrows].copy_(Pn[:mrows])
+                be.copy_(send[:mrows], Pn[:mrows])
             if mrows < mmax:
-                send[mrows:].zero_()                # padding rows are never unpacked; keep them finite
+                be.zero_(send[mrows:])              # padding rows are never unpacked; keep them finite
             recv = recv_buf[:P * mmax * nb]
             comm.all_gather(recv, send.reshape(-1))
             src = unpack_index.get(k)
@@ -430,22 +465,11 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
                 # panel: built once, it saves five small launches per panel on the gather stream)
                 oq = own_of_row[r1:]
                 src = unpack_index[k] = oq * mmax + lrow_of_row[r1:] - lo_table[k][oq]
-            Lfull[r1:, r0:r1] = recv.view(P * mmax, nb).index_select(0, src)
+            be.unpack_rows_(Lfull[r1:, r0:r1], recv.view(P * mmax, nb), src)
         else:
-            Lfull[r1:, r0:r1] = Pn[:mrows]
+            be.copy_(Lfull[r1:, r0:r1], Pn[:mrows])
         be.transpose_into(Lfull[r0:, r0:r1], Lt[r0:r1, r0:N])
         _mark('gather+unpack', fine=True)
-
-    def top_block(k):
-        """the solved block row k+1 of panel k, broadcast by its owner."""
-        r0, r1 = lay.rows(k)
-        t0, t1 = lay.rows(k + 1)
-        nxt = lay.owner(k + 1)
-        T = top_buf[:(t1 - t0) * (r1 - r0)].view(t1 - t0, r1 - r0)
-        if rank == nxt:
-            T.copy_(Aloc[offs[k + 1]:offs[k + 1] + t1 - t0, r0:r1])
-        comm.broadcast(T, nxt)
-        return T
 
     _mark('setup')
     streams = be.streams() if lookahead else None
@@ -460,39 +484,114 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
     else:
         global _FINE
         _FINE = False
-        main, chain, gath = streams
+        main, chain, tb, gath = streams
         nblk = lay.nblk
-        ev_narrow = [None] * nblk
+        ring = [be.empty(bs * bs) for _ in range(3)]      # diagonal blocks in flight (chain -> gather)
+        ev_L, ev_top, ev_colT, ev_col = {}, {}, {}, {}
+        ev_solve, ev_g, ev_narrow, ev_rest = {}, {}, {}, {}
+        nend = nloc + R
         start = be.record(main)
-        be.wait(chain, start)
-        be.wait(gath, start)
-        ev_c = ev_g = None
+        for st in (chain, tb, gath):
+            be.wait(st, start)
+
+        grow_host = np.full(nend, NEVER, dtype=np.int64)
+        for b_ in mine:
+            g0, g1 = lay.rows(b_)
+            grow_host[offs[b_]:offs[b_] + g1 - g0] = np.arange(g0, g1)
+
+        def update_rows(k, a, b, c_lo, c_hi, Bsrc=None):
+            """local rows [a, b) of panel k applied to global columns [c_lo, c_hi) (lower part by the
+            global index of each row; the ride-along rows unmasked)."""
+            if b <= a or c_hi <= c_lo:
+                return
+            k0, k1 = lay.rows(k)
+            fkey = (k, a, b, c_lo, c_hi)
+            flops = flops_cache.get(fkey)       # algorithmic flops, a pure function of the layout
+            if flops is None:
+                g = np.minimum(grow_host[a:b], c_hi - 1)
+                flops = flops_cache[fkey] = 2.0 * (k1 - k0) * float(np.clip(g - c_lo + 1, 0, None).sum())
+            Bop = Lfull[c_lo:c_hi, k0:k1] if Bsrc is None else Bsrc
+            be.gemm_rowmap_(Aloc[a:b, k0:k1], Bop, Aloc[a:b, c_lo:c_hi], grow[a:b], c_lo, flops)
+
         for k in range(nblk):
-            with be.on(chain):
-                # block column k has seen panels <= k-2 (main, before ev_narrow[k-2]) and panel
-                # k-1 (chain, previous iteration)
-                Pn, mrows = factor_diag_and_solve(k)
-                ev_trsm = be.record(chain)
-                if k + 1 < nblk:
-                    T = top_block(k)
-                    if k >= 1:
-                        be.wait(chain, ev_narrow[k - 1])      # column k+1 has seen panels <= k-1
-                    update(k, *lay.rows(k + 1), Bsrc=T)
-                ev_c = be.record(chain)
-            with be.on(gath):
-                be.wait(gath, ev_trsm)
-                gather_panel(k, Pn, mrows)
-                ev_g = be.record(gath)
+            r0, r1 = lay.rows(k)
+            nb = r1 - r0
+            own = lay.owner(k)
+            nxt = lay.owner(k + 1) if k + 1 < nblk else -1
+            lo_k, m_k = below_all[k][rank]
+            Lkk = ring[k % 3][:nb * nb].view(nb, nb)
             if k + 1 < nblk:
+                t0, t1 = lay.rows(k + 1)
+                nb1 = t1 - t0
+                lo1, _ = below_all[k + 1][rank]
+            # ------------------------------------------------ chain: the serial dependency chain
+            with be.on(chain):
+                be.wait(chain, ev_narrow.get(k - 2))      # column k has seen panels <= k-2 ...
+                be.wait(chain, ev_rest.get(k - 3))
+                if rank == own:
+                    D = Aloc[offs[k]:offs[k] + nb, r0:r1]
+                    if k >= 1:                            # ... and panel k-1 on the diagonal block, here
+                        p0, p1 = lay.rows(k - 1)
+                        be.syrk_lower_(Aloc[offs[k]:offs[k] + nb, p0:p1], D)
+                    be.potrf_(D)
+                    be.copy_(Lkk, D)
+                comm.broadcast(Lkk, own, 'chain')
+                ev_L[k] = be.record(chain)
+                if rank == nxt:
+                    be.wait(chain, ev_colT.get(k - 1))    # my block row k+1 has seen panel k-1 in column k
+                    be.trsm_rlt_(Lkk, Aloc[offs[k + 1]:offs[k + 1] + nb1, r0:r1])
+                    ev_top[k] = be.record(chain)
+            # ------------------------------------------------ tb (1): top block -> everyone
+            if k + 1 < nblk:
+                T = top_buf[:nb1 * nb].view(nb1, nb)
+                with be.on(tb):
+                    if rank == nxt:
+                        be.wait(tb, ev_top[k])
+                        be.copy_(T, Aloc[offs[k + 1]:offs[k + 1] + nb1, r0:r1])
+                    comm.broadcast(T, nxt, 'tb')
+            # ------------------------------------------------ gather (1): the rest of the panel solve
+            with be.on(gath):
+                be.wait(gath, ev_L[k])
+                be.copy_(Lfull[r0:r1, r0:r1], Lkk)
+                be.wait(gath, ev_col.get(k - 1))          # column k of my rows has seen panel k-1
+                s0 = lo_k + nb1 if rank == nxt else lo_k  # the top block is solved on the chain
+                if nend > s0:
+                    be.trsm_rlt_(Lkk, Aloc[s0:, r0:r1])
+                if rank == nxt:
+                    be.wait(gath, ev_top[k])
+                ev_solve[k] = be.record(gath)
+            # ------------------------------------------------ tb (2): panel k -> block column k+1
+            if k + 1 < nblk:
+                with be.on(tb):
+                    be.wait(tb, ev_solve[k])
+                    be.wait(tb, ev_narrow.get(k - 1))     # writers of column k+1: main -> gather -> tb
+                    be.wait(tb, ev_rest.get(k - 2))
+                    if k + 2 < nblk and rank == lay.owner(k + 2):
+                        # block row k+2 first: it is the next top block
+                        nb2 = lay.rows(k + 2)[1] - lay.rows(k + 2)[0]
+                        update_rows(k, lo1, lo1 + nb2, t0, t1, Bsrc=T)
+                        ev_colT[k] = be.record(tb)
+                        update_rows(k, lo1 + nb2, nend, t0, t1, Bsrc=T)
+                    else:
+                        update_rows(k, lo1, nend, t0, t1, Bsrc=T)
+                    ev_col[k] = be.record(tb)
+            # ------------------------------------------------ gather (2): all-gather, panel k -> column k+2
+            with be.on(gath):
+                gather_panel(k, Aloc[lo_k:, r0:r1], m_k)
+                ev_g[k] = be.record(gath)
+                if k + 2 < nblk:
+                    be.wait(gath, ev_rest.get(k - 1))     # main writes columns >= k+2 with panel k-1
+                    update_rows(k, lo1, nend, *lay.rows(k + 2))
+                    ev_narrow[k] = be.record(gath)
+            # ------------------------------------------------ main: the bulk
+            if k + 3 < nblk:
                 with be.on(main):
-                    be.wait(main, ev_g)
-                    if k + 2 < nblk:
-                        update(k, *lay.rows(k + 2))
-                    ev_narrow[k] = be.record(main)
-                    if k + 3 < nblk:
-                        update(k, lay.rows(k + 3)[0], N)
-        be.wait(main, ev_c)
-        be.wait(main, ev_g)
+                    be.wait(main, ev_g[k])
+                    lo3, _ = below_all[k + 2][rank]
+                    update_rows(k, lo3, nend, lay.rows(k + 3)[0], N)
+                    ev_rest[k] = be.record(main)
+        for st in (chain, tb, gath):
+            be.wait(main, be.record(st))
         _FINE = True
         _mark('factor(lookahead)')
     alpha_t = Aloc[nloc:, :N]

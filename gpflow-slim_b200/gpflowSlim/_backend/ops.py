@@ -447,6 +447,15 @@ class _Gram(torch.autograd.Function):
                     torch.zeros_like(X) if need_dx else None,
                     torch.zeros_like(X2) if need_dx2 else None, None, None)
         dtheta = torch.empty(prog.n_theta, dtype=F64, device=X.device)
+        if need_dx2 and not need_dx:
+            # only the second argument wants a gradient (K(Xb, Z) of the sparse models): ONE pass
+            # with the roles swapped, K(X, X2)^T = K(X2, X), yields d theta and d X2 together
+            dX2 = torch.empty_like(X2)
+            Wt = transpose(W)
+            vt, vx, vx2, vw, vd, vdx = view(theta), view(X2), view(X), view(Wt), view(dtheta), view(dX2)
+            h.check(h.lib.gps_gram_bwd(h.ptr, ctypes.byref(prog.desc), vt.ref, vx.ref, vx2.ref, vw.ref,
+                                       vd.ref, vdx.ref))
+            return dtheta, None, dX2, None, None
         dX = torch.empty_like(X) if need_dx else None
         if not ctx.has_x2:
             # the library treats W as symmetric in the one-argument case

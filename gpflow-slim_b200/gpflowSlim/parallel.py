@@ -27,16 +27,25 @@ def init(group=None, block=512, backend='nccl', device=None, lookahead=True):
         dist.init_process_group(backend, device_id=device if backend == 'nccl' else None)
     if group is None and dist.is_initialized() and dist.get_world_size() > 1 \
             and dist.get_backend() == 'nccl' and _STATE.get('own_group') is None:
-        # a dedicated communicator whose NCCL stream has HIGH priority: the panel broadcasts and
-        # all-gathers of the distributed Cholesky sit on its critical path and must not queue
-        # behind the CTAs of a bulk trailing-update GEMM already in flight
+        # three dedicated communicators whose NCCL streams have HIGH priority, one per kind of
+        # collective of the distributed Cholesky (diagonal-block broadcast / top-block broadcast /
+        # panel all-gather): a process group runs its collectives in issue order on ONE stream, so
+        # with a single communicator a 100 MB panel all-gather would sit in front of the 2 MB
+        # broadcast the serial chain is waiting for
         opts = dist.ProcessGroupNCCL.Options()
         opts.is_high_priority_stream = True
-        _STATE['own_group'] = dist.new_group(ranks=list(range(dist.get_world_size())), backend='nccl',
-                                             pg_options=opts)
+        ranks = list(range(dist.get_world_size()))
+        _STATE['own_group'] = {name: dist.new_group(ranks=ranks, backend='nccl', pg_options=opts)
+                               for name in ('chain', 'tb', 'gather')}
     if group is None:
         group = _STATE.get('own_group')
     _STATE.update(active=True, group=group, block=int(block), lookahead=bool(lookahead))
+
+
+def _pg():
+    """the plain process group (all-reduces, world size, rank)."""
+    g = _STATE['group']
+    return g.get('gather') if isinstance(g, dict) else g
 
 
 def shutdown():
@@ -61,12 +70,12 @@ def lookahead():
 
 def world_size():
     import torch.distributed as dist
-    return dist.get_world_size(_STATE['group']) if dist.is_available() and dist.is_initialized() else 1
+    return dist.get_world_size(_pg()) if dist.is_available() and dist.is_initialized() else 1
 
 
 def rank():
     import torch.distributed as dist
-    return dist.get_rank(_STATE['group']) if dist.is_available() and dist.is_initialized() else 0
+    return dist.get_rank(_pg()) if dist.is_available() and dist.is_initialized() else 0
 
 
 def svgp_objective_and_grads(model, Xb, Yb, params=None):
@@ -83,7 +92,7 @@ def svgp_objective_and_grads(model, Xb, Yb, params=None):
     world = world_size()
     nloc = torch.tensor([float(Xb.shape[0])], dtype=torch.float64, device=Xb.device)
     if world > 1:
-        dist.all_reduce(nloc, group=_STATE['group'])
+        dist.all_reduce(nloc, group=_pg())
     btot = float(nloc)
     fmean, fvar = model._build_predict(Xb, full_cov=False)
     var_exp = model.likelihood.variational_expectations(fmean, fvar, Yb)
@@ -94,7 +103,7 @@ def svgp_objective_and_grads(model, Xb, Yb, params=None):
     flat = torch.cat([local.detach().reshape(1)] +
                      [(g if g is not None else torch.zeros_like(p)).reshape(-1) for g, p in zip(grads, params)])
     if world > 1:
-        dist.all_reduce(flat, group=_STATE['group'])
+        dist.all_reduce(flat, group=_pg())
     out, o = [], 1
     for p in params:
         out.append(flat[o:o + p.numel()].view_as(p))

@@ -16,7 +16,7 @@ class CpuBackend(object):
     # look-ahead "streams": sequential execution in issue order is one valid schedule of the
     # dependency graph, so the look-ahead ORDER of operations is what gets tested here
     def streams(self):
-        return 'main', 'chain', 'gather'
+        return 'main', 'chain', 'tb', 'gather'
 
     def on(self, stream):
         import contextlib
@@ -43,6 +43,18 @@ class CpuBackend(object):
 
     def trsm_rlt_(self, Lm, B):
         B.copy_(torch.linalg.solve_triangular(torch.tril(Lm), B.T, upper=False).T)
+
+    def copy_(self, dst, src):
+        dst.copy_(src)
+
+    def zero_(self, t):
+        t.zero_()
+
+    def unpack_rows_(self, dst, src, index):
+        dst.copy_(src.index_select(0, index))
+
+    def syrk_lower_(self, X, D):
+        D.sub_(torch.tril(X @ X.T))
 
     def gemm_rowmap_(self, A, B, C, rowlim, coff, flops=-1.0):
         cols = torch.arange(C.shape[1]) + coff

@@ -91,4 +91,6 @@ def test_sharded_svgp_step_equals_single_process(world, whiten, q_diag, multicla
         p.join(timeout=60)
         assert p.exitcode == 0
     for rank, errs in res:
-        assert max(errs) < 1e-9, (rank, errs)    # the multi-class kernel-variance gradient is ~1e-6 of the others
+        # the multi-class kernel-variance gradient is ~1e-6 of the others (cancellation): held to
+        # the north-star tolerance
+        assert max(errs) < 1e-8, (rank, errs)

@@ -286,7 +286,15 @@ def test_gram_fast_path_equals_interpreter(cls, d, ard):
             mdl = gpf.models.GPR(conv(Xn), conv(Yn), kern=kern)
             obj = mdl.objective
             go = torch.autograd.grad(obj, [p.unconstrained_tensor for p in mdl.parameters])
-            out[impl] = [K.detach(), K2.detach(), val.detach(), obj.detach()] + [t.detach() for t in g + go]
+            # input gradients: both arguments, only the second one (the sparse models' K(Xb, Z)),
+            # and the one-argument (symmetric) form -- with active dims that skip a column
+            Xg, X2g = conv(Xn).requires_grad_(True), conv(X2n).requires_grad_(True)
+            v2 = (kern.K(Xg, X2g) * conv(Wn)).sum() + (kern.K(Xg) * conv(Wsn)).sum()
+            gx = torch.autograd.grad(v2, [Xg, X2g] + params)
+            X2h = conv(X2n).requires_grad_(True)
+            gz = torch.autograd.grad((kern.K(conv(Xn), X2h) * conv(Wn)).sum(), [X2h] + params)
+            out[impl] = [K.detach(), K2.detach(), val.detach(), obj.detach()] + \
+                [t.detach() for t in g + go + gx + gz]
         finally:
             h.set_option('gram_impl', 0)
     for i, (a, b) in enumerate(zip(out[0], out[1])):

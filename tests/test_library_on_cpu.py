@@ -218,6 +218,37 @@ def test_split_k_gemm_through_the_launch_code(gpf):
         h.set_option('gemm_splitk', 1)     # the default
 
 
+def test_fast_path_gram_input_gradient(gpf):
+    """gps_gram_bwd of a single stationary kernel with d/dX: the register-tiled kernel writes
+    G = dObj/d(d2) and one skinny tensor-core product G [F | 1] gives the input gradient; against
+    torch autograd through the oracle kernel, for K(X, X2) (both gradients, and X2 only: one
+    swapped pass) and the symmetric K(X), with active dims that skip a column."""
+    import gpflowSlim
+    from oracle import ref_torch as R
+    rng = np.random.default_rng(4)
+    n, m, d = 150, 70, 5
+    Xn, X2n = rng.standard_normal((n, d)), rng.standard_normal((m, d))
+    W, Ws = conv(rng.standard_normal((n, m))), conv(rng.standard_normal((n, n)))
+    dims = [0, 2, 3, 4]
+    for cls, typ in (('RBF', 'rbf'), ('Matern52', 'matern52')):
+        kern = getattr(gpflowSlim.kernels, cls)(4, variance=1.3, lengthscales=[0.7, 0.9, 1.1, 1.3], ARD=True,
+                                                active_dims=dims)
+        spec = dict(type=typ, variance=torch.tensor(1.3, dtype=torch.float64),
+                    lengthscales=torch.tensor([0.7, 0.9, 1.1, 1.3], dtype=torch.float64), active_dims=dims)
+        for mode in ('both', 'x2', 'sym'):
+            X, X2 = conv(Xn).requires_grad_(mode != 'x2'), conv(X2n).requires_grad_(mode != 'sym')
+            Xo, X2o = conv(Xn).requires_grad_(mode != 'x2'), conv(X2n).requires_grad_(mode != 'sym')
+            if mode == 'sym':
+                val, valo = (kern.K(X) * Ws).sum(), (R.K(spec, Xo) * Ws).sum()
+                wrt, wrto = [X], [Xo]
+            else:
+                val, valo = (kern.K(X, X2) * W).sum(), (R.K(spec, Xo, X2o) * W).sum()
+                wrt, wrto = ([X, X2], [Xo, X2o]) if mode == 'both' else ([X2], [X2o])
+            g, go = torch.autograd.grad(val, wrt), torch.autograd.grad(valo, wrto)
+            for a, b in zip(g, go):
+                assert float((a - b).abs().max()) < 1e-11 * float(b.abs().max()), (cls, mode)
+
+
 def test_prefix_solves_with_big_leaves(gpf):
     """gps_trsm_rlt_prefix / gps_trsm_rln_prefix with option trsm_leaf = 256: the aligned 256-blocks
     are solved by one product with their explicit inverses (built for all blocks at once by
@@ -408,7 +439,7 @@ def _dist_worker(rank, world, port, so_path, n, r, block, out_q):
             self._L, self.device = lib, torch.device('cpu')
 
         def streams(self):
-            return 'main', 'chain', 'gather'
+            return 'main', 'chain', 'tb', 'gather'
 
         def on(self, stream):
             return contextlib.nullcontext()
