@@ -1075,6 +1075,12 @@ __global__ void stat_dx_operand_kernel(const double* __restrict__ F, int FT, int
   B[(int64_t)nd * ldb + j] = 1.0;
 }
 
+// The product form of the input gradient, f_id sum_j G_ij - sum_j G_ij f_jd, cancels the j == i (or
+// coincident-point) term only to rounding.  That is harmless where dk/d(d2) is bounded at zero
+// distance (RBF, Matern 3/2, 5/2) and not for Matern 1/2 / Exponential, whose derivative is
+// ~ 1 / sqrt(1e-12) there: those keep the interpreter, which multiplies by the exact difference.
+bool stat_dx_ok(int type) { return type == GPS_RBF || type == GPS_MATERN32 || type == GPS_MATERN52; }
+
 // single stationary primitive with the identity program and <= 16 active dimensions?
 bool stat_fast(const gps_handle* h, const Plan& pl) {
   return h->gram_impl == 0 && pl.n_prims == 1 && pl.n_ops == 0 && pl.out_slot == 0 &&
@@ -1291,8 +1297,10 @@ int gps_gram_bwd_mat(gps_handle* h, const gps_kernel_desc* desc, const double* t
   const int64_t nctas = itiles * njc;
   double* part = (double*)gps_ws(h, WS_PARTIAL, (size_t)nctas * nacc * sizeof(double));
   if (!part) return -102;
+  // register-tiled fast path (with the input gradient where its product form is safe)
+  const bool fast = !use_smem_acc && stat_fast(h, pl) && (!dX || stat_dx_ok(pl.prims[0].type));
   double* pdx = nullptr;
-  if (dX && !(stat_fast(h, pl) && !use_smem_acc)) {
+  if (dX && !fast) {
     pdx = (double*)gps_ws(h, WS_PARTIAL2, (size_t)njc * N * X.cols * sizeof(double));
     if (!pdx) return -102;
   }
@@ -1302,7 +1310,7 @@ int gps_gram_bwd_mat(gps_handle* h, const gps_kernel_desc* desc, const double* t
   if (use_smem_acc) {
     gram_bwd_smem_kernel<<<dim3((unsigned)njc, (unsigned)itiles), NT2, smem2, h->stream>>>(
         pl, pd, nslots, theta, FL, FR, N, M, a, part, pdx);
-  } else if (stat_fast(h, pl)) {
+  } else if (fast) {
     const PrimC P = pl.prims[0];
     const dim3 g2((unsigned)njc, (unsigned)itiles);
     double* G = nullptr;
@@ -1345,7 +1353,7 @@ int gps_gram_bwd_mat(gps_handle* h, const gps_kernel_desc* desc, const double* t
   GPS_CUDA(h, cudaMemcpyAsync(dtheta_out, part, pl.n_theta * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   if (trace_out)
     GPS_CUDA(h, cudaMemcpyAsync(trace_out, part + pl.n_theta, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  if (dX && !(stat_fast(h, pl) && !use_smem_acc)) {
+  if (dX && !fast) {
     int64_t tot = N * X.cols;
     reduce_dx_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(pdx, (int)njc, N, (int)X.cols,
                                                                           a.dx_scale, dX->p, dX->ld);

@@ -263,6 +263,14 @@ class CudaBackend(object):
                                    vd.ref, None))
         return dtheta
 
+    def matmul_nt(self, A, B):
+        from . import ops
+        return ops.gemm_nt(A, B)
+
+    def row_sumsq(self, A):
+        from . import ops
+        return ops.row_sumsq(A)
+
     def sum_log_diag(self, Lm):
         h, L = self._h(), self._L
         out = torch.empty(1, dtype=F64, device=Lm.device)
@@ -668,3 +676,35 @@ def inverse_rows_and_contract(prog, theta, X, lay, rank, Lsq, Lt, alpha_t, be):
         out[prog.n_theta] = W[torch.arange(m - R, device=dev), growB].sum()     # tr W
         out[:prog.n_theta] = be.gram_bwd(prog, theta, X.index_select(0, growB), X, W)
     return out, beta_t
+
+
+def predict(prog, theta, noise, X, Yc, Xnew, kdiag_new, block=512, group=None, backend=None, lookahead=True):
+    """Distributed GPR prediction (reference models/gpr.py:118-131): the ranks factor K + noise I
+    together (every rank ends up with all of L), then the COLUMNS of K(X, Xnew) -- the test points --
+    are dealt out: rank r computes A_r^T = K(Xnew_r, X) L^-T, mean_r = A_r^T V with V = L^-1 (Y - m)
+    and var_r = Kdiag(Xnew_r) - sum A_r^2, and one all-gather joins the slices.  Returns
+    (mean [N*, R] without the mean function, var [N*]) on every rank."""
+    comm = _Comm(group)
+    be = backend if backend is not None else CudaBackend(X.device)
+    N, R = Yc.shape
+    lay = BlockRowLayout(N, block, comm.world)
+    Lfull, _, alpha_t = factor(prog, theta, float(noise), X, Yc, lay, comm, be, lookahead=lookahead)
+    Lsq = Lfull[:, :N]
+    ns = Xnew.shape[0]
+    P, rank = comm.world, comm.rank
+    per = (ns + P - 1) // P                       # equal slices (the last ones may be short / empty)
+    lo, hi = min(ns, rank * per), min(ns, (rank + 1) * per)
+    out = be.zeros(per, R + 1)
+    if hi > lo:
+        At = be.empty(hi - lo, _round_up(N, 16))[:, :N]
+        be.gram_rows(prog, theta, Xnew[lo:hi], X, At)          # K(Xnew_r, X) = K(X, Xnew_r)^T
+        be.trsm_rlt_(Lsq, At)                                  # (L^-1 Kx)^T
+        out[:hi - lo, :R] = be.matmul_nt(At, alpha_t)          # A^T V
+        out[:hi - lo, R] = kdiag_new[lo:hi] - be.row_sumsq(At)
+    if P > 1:
+        full = be.empty(P * per, R + 1)
+        comm.all_gather(full.view(-1), out.reshape(-1))
+    else:
+        full = out
+    return full[:ns, :R].contiguous(), full[:ns, R].contiguous()
+

@@ -76,6 +76,20 @@ class GPR(GPModel):
         features = self._feature_map()
         if features is not None:
             return self._build_predict_features(features, Xnew, full_cov)
+        from .. import parallel
+        if parallel.active() and not full_cov and self._fusable(self.X, Xnew) and not torch.is_grad_enabled():
+            # all ranks of the group factor K + noise I together and share out the test points
+            from .._backend import dist_gpr
+            core, white = self._core_and_white()
+            noise = self.likelihood.variance if white is None else self.likelihood.variance.reshape(()) + white
+            prog = core.program()
+            mean, var = dist_gpr.predict(prog, prog.theta(self.X.device).detach(), float(noise), self.X,
+                                         (self.Y - self.mean_function(self.X)).detach(), Xnew,
+                                         core.Kdiag(Xnew).detach(), block=parallel.block(), group=parallel.group(),
+                                         lookahead=parallel.lookahead())
+            if white is not None:
+                var = var + white
+            return mean + self.mean_function(Xnew), var.reshape(-1, 1).expand(-1, r)
         if self._fusable(self.X, Xnew) and not torch.is_grad_enabled():
             core, white = self._core_and_white()
             noise = self.likelihood.variance if white is None else self.likelihood.variance.reshape(()) + white

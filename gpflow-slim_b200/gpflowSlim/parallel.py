@@ -9,6 +9,11 @@ section 2.2); this module is what shards its hot path where it shards naturally:
   * SVGP (models/svgp.py:108-125): `parallel.svgp_objective_and_grads(model, Xb, Yb)` shards the
     minibatch rows across ranks, evaluates the ELBO terms locally and all-reduces one flat
     gradient buffer.
+  * SGPR (models/sgpr.py:121-156): `parallel.sgpr_objective_and_grads(model)` shards the DATA rows
+    (the columns of Kuf): A A^T and A err are summed over ranks by one all-reduce of
+    M^2 + M R + 3 doubles, the two small Cholesky factorisations are replicated.
+  * GPR prediction (models/gpr.py:118-131): under `parallel.init()` `GPR.predict_f` factors
+    distributed and shares out the test points (`_backend/dist_gpr.predict`).
 """
 import torch
 
@@ -109,3 +114,64 @@ def svgp_objective_and_grads(model, Xb, Yb, params=None):
         out.append(flat[o:o + p.numel()].view_as(p))
         o += p.numel()
     return flat[0], out
+
+
+def sgpr_objective_and_grads(model, params=None):
+    """Data-parallel SGPR objective (last row; reference models/sgpr.py:121-156).
+    `model` is an SGPR whose X, Y are THIS RANK's rows of the data set (the global data set is their
+    concatenation over ranks; Z, kernel and noise are replicated).  With A = L^-1 Kuf / sigma the
+    bound needs A A^T (M x M), A err (M x R), sum err^2, sum Kdiag and N: all sums over data rows,
+    i.e. over ranks -- one all-reduce of M^2 + M R + 3 doubles.  What follows (B = A A^T + I,
+    chol(B), c, the bound) is replicated.
+
+    Gradient: bound = h(S(theta), theta) with S = sum_r s_r(theta).  Every rank differentiates h
+    w.r.t. the reduced S (a leaf) and w.r.t. theta directly (replicated, identical on all ranks),
+    pulls dh/dS back through ITS s_r, and one all-reduce sums those pull-backs:
+        d/d theta = dh/d theta|_S + sum_r (d s_r / d theta)^T dh/dS.
+    Returns (objective, grads) identical on every rank and equal to the single-process values."""
+    import math
+    import torch.distributed as dist
+    from ._backend import ops as _ops
+    from ._settings import SETTINGS as settings
+    params = list(params) if params is not None else model.trainable_tensors
+    world = world_size()
+    X, Y = model.X, model.Y
+    M, R = len(model.feature), Y.shape[1]
+    err = Y - model.mean_function(X)
+    Kfu = model.feature.Kfu(model.kern, X)                                      # Kuf^T, this rank's rows
+    L = _ops.cholesky(model.feature.Kuu(model.kern, jitter=settings.numerics.jitter_level))
+    var = model.likelihood.variance
+    sigma = torch.sqrt(var)
+    At = _ops.trsm_rlt(Kfu, L) / sigma
+    Att = _ops.t(At)
+    pieces = [_ops.matmul_nt(Att, Att).reshape(-1),                             # A A^T   (sgpr.py:140-141)
+              _ops.matmul_nt(Att, _ops.t(err)).reshape(-1),                     # A err   (:144)
+              (err ** 2).sum().reshape(1), model.kern.Kdiag(X).sum().reshape(1),
+              torch.full((1,), float(X.shape[0]), dtype=At.dtype, device=At.device)]
+    local = torch.cat(pieces)
+    S = local.detach().clone()
+    if world > 1:
+        dist.all_reduce(S, group=_pg())
+    S.requires_grad_(True)
+    AAT, Aerr = S[:M * M].view(M, M), S[M * M:M * M + M * R].view(M, R)
+    e2, kd, ntot = S[M * M + M * R], S[M * M + M * R + 1], float(S[M * M + M * R + 2])
+    B = AAT + torch.eye(M, dtype=AAT.dtype, device=AAT.device)
+    LB = _ops.cholesky(B)
+    c = _ops.solve_lower(LB, Aerr) / sigma
+    bound = (-0.5 * ntot * R * math.log(2 * math.pi) - R * torch.log(torch.diagonal(LB)).sum()
+             - 0.5 * ntot * R * torch.log(var) - 0.5 * e2 / var + 0.5 * (c ** 2).sum()
+             - 0.5 * R * kd / var + 0.5 * R * torch.diagonal(AAT).sum())            # sgpr.py:147-154
+    obj = -(bound + model.prior_tensor)
+    g = torch.autograd.grad(obj, [S] + params, allow_unused=True, retain_graph=True)   # sigma / var are shared with `local`
+    gS, gdir = g[0], g[1:]
+    gloc = torch.autograd.grad(local, params, grad_outputs=gS, allow_unused=True)
+    flat = torch.cat([(t if t is not None else torch.zeros_like(p)).reshape(-1) for t, p in zip(gloc, params)])
+    if world > 1:
+        dist.all_reduce(flat, group=_pg())
+    out, o = [], 0
+    for p, gd in zip(params, gdir):
+        t = flat[o:o + p.numel()].view_as(p)
+        out.append(t if gd is None else t + gd)
+        o += p.numel()
+    return obj.detach(), out
+

@@ -101,5 +101,11 @@ class CpuBackend(object):
         (g,) = torch.autograd.grad((K * W).sum(), th)
         return g
 
+    def matmul_nt(self, A, B):
+        return A @ B.T
+
+    def row_sumsq(self, A):
+        return (A ** 2).sum(1)
+
     def sum_log_diag(self, Lm):
         return torch.log(torch.diagonal(Lm)).sum()

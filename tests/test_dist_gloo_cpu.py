@@ -83,6 +83,52 @@ def test_distributed_gpr_host_logic_matches_oracle(world, n, r, block, lookahead
         assert max(errs) < 1e-9, (rank, errs)
 
 
+def _predict_worker(rank, world, port, n, ns, r, block, out_q):
+    sys.path.insert(0, HERE)
+    import torch.distributed as dist
+    from dist_cpu_backend import CpuBackend
+    from gpflowSlim._backend import dist_gpr
+    torch.set_num_threads(2)
+    if world > 1:
+        dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
+    d = 3
+    X, Y, th, _, _ = _oracle(n, d, r, 0.1, 1.7)
+    Xs = np.random.default_rng(9).standard_normal((ns, d))
+    spec = _spec(th, d)
+    mo, vo = R.gpr_predict(spec, torch.tensor(X), torch.tensor(Y), torch.tensor(0.1, dtype=torch.float64),
+                           torch.tensor(Xs))
+
+    class Prog(object):
+        n_theta = 1 + d
+    be = CpuBackend(lambda t: _spec(t, d))
+    mean, var = dist_gpr.predict(Prog(), th, 0.1, torch.tensor(X), torch.tensor(Y), torch.tensor(Xs),
+                                 R.Kdiag(spec, torch.tensor(Xs)), block=block, backend=be)
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    out_q.put((rank, [rel(mean, mo), rel(var, vo.reshape(ns, -1)[:, 0])]))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,n,ns,r,block', [(1, 500, 37, 1, 128), (2, 700, 53, 2, 128), (3, 640, 5, 1, 256),
+                                                (4, 600, 2, 1, 128)])
+def test_distributed_predict_matches_oracle(world, n, ns, r, block):
+    """dist_gpr.predict: the ranks factor together, the test points are dealt out (ragged, also
+    fewer test points than ranks), one all-gather joins mean / variance."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_predict_worker, args=(i, world, port, n, ns, r, block, q)) for i in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, errs in res:
+        assert max(errs) < 1e-9, (rank, errs)
+
+
 def test_layout_is_a_partition_and_balanced():
     from gpflowSlim._backend.dist_gpr import BlockRowLayout
     lay = BlockRowLayout(32768, 512, 8)
