@@ -620,11 +620,14 @@ int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, M
   // products of the SVGP backward are 64 (36 lower) tiles on 148 SMs, an M x R product with R <= 128 is
   // M/128 tiles -- is cut into K slices (blockIdx.y); the partial tiles go to a per-stream scratch and
   // one reduction pass applies alpha / beta and the lower-output mask.  One wave of CTAs at most.
-  if (h->gemm_splitk && h->gemm_impl != 1 && (c_uplo == C_ALL || c_uplo == C_LOWER) && g.batch_y == 0 &&
-      a_tri == TRI_NONE && b_tri == TRI_NONE && g.K >= 512) {
+  if (h->gemm_splitk && h->gemm_impl != 1 && (c_uplo == C_ALL || c_uplo == C_LOWER) && g.batch_y == 0 && g.K >= 256) {
     const int tiles = (c_uplo == C_LOWER && g.M == g.N) ? g.tiles_m * (g.tiles_m + 1) / 2 : g.tiles_m * g.tiles_n;
+    // slices at least 128 deep for the small latency-bound products (one 128 x 128 tile of depth 512
+    // keeps a single SM busy for 70 us), 256 deep otherwise; triangular operands are sliced too (a
+    // slice outside a tile's K range just stores zeros)
+    const int min_chunk = (tiles <= 32) ? 128 : 256;
     int split = h->sm_count / (tiles > 0 ? tiles : 1);
-    if (split > g.K / 256) split = g.K / 256;
+    if (split > g.K / min_chunk) split = g.K / min_chunk;
     if (split > 32) split = 32;
     if (split >= 2) {
       const int64_t ldp = ((int64_t)g.N + 15) / 16 * 16;

@@ -568,22 +568,61 @@ namespace {
 // Built bottom-up from the 128 x 128 block inverses, ALL blocks of a level in one strided-batch
 // launch per product:   W = -U11 L21^T,   U12 = W U22 = W T22^T,   T21 = U12^T = T22 W^T
 // (three NT products per level; keeping T next to U removes every transpose).
-__global__ void leaf_diag_kernel(const double* __restrict__ tinv, double* __restrict__ Uo,
-                                 double* __restrict__ To, int bs, int per) {
+__global__ void leaf_diag_kernel(const double* __restrict__ tinv, double* __restrict__ Uo, int64_t ldu,
+                                 int64_t zu, double* __restrict__ To, int64_t ldt, int64_t zt, int per) {
   __shared__ double tile[32][33];
   const int blk = blockIdx.z;                      // global 128-block index
   const int z = blk / per, j = blk % per;
-  const int64_t off = (int64_t)z * bs * bs + (int64_t)j * NB * (bs + 1);
+  const int64_t offu = (int64_t)z * zu + (int64_t)j * NB * (ldu + 1);
+  const int64_t offt = (int64_t)z * zt + (int64_t)j * NB * (ldt + 1);
   const double* T = tinv + (int64_t)blk * NB * NB;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += 8) {
     const double v = T[(r0 + i) * NB + c0 + threadIdx.x];
     tile[i][threadIdx.x] = v;
-    To[off + (int64_t)(r0 + i) * bs + c0 + threadIdx.x] = v;
+    To[offt + (int64_t)(r0 + i) * ldt + c0 + threadIdx.x] = v;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += 8)      // U[r][c] = T[c][r]
-    Uo[off + (int64_t)(c0 + i) * bs + r0 + threadIdx.x] = tile[threadIdx.x][i];
+    Uo[offu + (int64_t)(c0 + i) * ldu + r0 + threadIdx.x] = tile[threadIdx.x][i];
+}
+
+// U / T: `nfull` blocks of size bs, block z at U + z * zu with leading dimension ldu (same for T);
+// W: scratch of nfull * bs * bs / 4 doubles.  The diagonal 128-tiles are written in full (zeros
+// on the other side of the diagonal); off-diagonal tiles on the zero side are NOT touched.
+int block_inverses_batched(gps_handle* h, Mat L, const double* tinv, int bs, int64_t nfull, double* U,
+                           int64_t ldu, int64_t zu, double* T, int64_t ldt, int64_t zt, double* W) {
+  int rc;
+  const int per = bs / NB;
+  leaf_diag_kernel<<<dim3(NB / 32, NB / 32, (unsigned)(nfull * per)), dim3(32, 8), 0, h->stream>>>(tinv, U, ldu, zu, T,
+                                                                                                ldt, zt, per);
+  GPS_LAUNCH_CHECK(h);
+  for (int sz = NB; sz < bs; sz *= 2) {
+    const int m = bs / (2 * sz);                       // nodes per block at this level
+    GemmBatch b;
+    b.ny = m; b.nz = (int)nfull;
+    const int64_t uy = (int64_t)2 * sz * (ldu + 1), ty = (int64_t)2 * sz * (ldt + 1);
+    const int64_t ly = (int64_t)2 * sz * (L.ld + 1), lz = (int64_t)bs * (L.ld + 1);
+    const int64_t wy = (int64_t)sz * sz, wz = (int64_t)m * sz * sz;
+    Mat U11(U, sz, sz, ldu), L21(L.p + (int64_t)sz * L.ld, sz, sz, L.ld), Wm(W, sz, sz, sz);
+    Mat T22(T + (int64_t)sz * (ldt + 1), sz, sz, ldt), U12(U + sz, sz, sz, ldu), T21(T + (int64_t)sz * ldt, sz, sz, ldt);
+    // W = -U11 L21^T
+    b.sAy = uy; b.sAz = zu; b.sBy = ly; b.sBz = lz; b.sCy = wy; b.sCz = wz;
+    if ((rc = gps_gemm_nt_launch(h, -1.0, U11, L21, 0.0, Wm, TRI_UPPER, TRI_NONE, C_ALL, nullptr, 0, -1.0, nullptr,
+                                 0, 0, &b)))
+      return rc;
+    // U12 = W T22^T
+    b.sAy = wy; b.sAz = wz; b.sBy = ty; b.sBz = zt; b.sCy = uy; b.sCz = zu;
+    if ((rc = gps_gemm_nt_launch(h, 1.0, Wm, T22, 0.0, U12, TRI_NONE, TRI_LOWER, C_ALL, nullptr, 0, -1.0, nullptr, 0,
+                                 0, &b)))
+      return rc;
+    // T21 = T22 W^T
+    b.sAy = ty; b.sAz = zt; b.sBy = wy; b.sBz = wz; b.sCy = ty; b.sCz = zt;
+    if ((rc = gps_gemm_nt_launch(h, 1.0, T22, Wm, 0.0, T21, TRI_LOWER, TRI_NONE, C_ALL, nullptr, 0, -1.0, nullptr, 0,
+                                 0, &b)))
+      return rc;
+  }
+  return 0;
 }
 
 struct LeafInv {
@@ -600,7 +639,6 @@ int build_leaf_inverses(gps_handle* h, Mat L, const double* tinv, int64_t maxrow
   out->bs = 0;
   if (bs <= NB || L.rows < bs) return 0;
   const int64_t nfull = L.rows / bs;
-  const int per = bs / NB;
   const size_t bytes = (size_t)nfull * bs * bs * sizeof(double);
   double* U = (double*)gps_ws(h, WS_LEAF_U, bytes);
   double* T = (double*)gps_ws(h, WS_LEAF_T, bytes);
@@ -609,33 +647,8 @@ int build_leaf_inverses(gps_handle* h, Mat L, const double* tinv, int64_t maxrow
   if (!U || !T || !W || !X) return -102;
   GPS_CUDA(h, cudaMemsetAsync(U, 0, bytes, h->stream));
   GPS_CUDA(h, cudaMemsetAsync(T, 0, bytes, h->stream));
-  leaf_diag_kernel<<<dim3(NB / 32, NB / 32, (unsigned)(nfull * per)), dim3(32, 8), 0, h->stream>>>(tinv, U, T, bs, per);
-  GPS_LAUNCH_CHECK(h);
-  for (int sz = NB; sz < bs; sz *= 2) {
-    const int m = bs / (2 * sz);                       // nodes per block at this level
-    GemmBatch b;
-    b.ny = m; b.nz = (int)nfull;
-    const int64_t uy = (int64_t)2 * sz * (bs + 1), uz = (int64_t)bs * bs;
-    const int64_t ly = (int64_t)2 * sz * (L.ld + 1), lz = (int64_t)bs * (L.ld + 1);
-    const int64_t wy = (int64_t)sz * sz, wz = (int64_t)m * sz * sz;
-    Mat U11(U, sz, sz, bs), L21(L.p + (int64_t)sz * L.ld, sz, sz, L.ld), Wm(W, sz, sz, sz);
-    Mat T22(T + (int64_t)sz * (bs + 1), sz, sz, bs), U12(U + sz, sz, sz, bs), T21(T + (int64_t)sz * bs, sz, sz, bs);
-    // W = -U11 L21^T
-    b.sAy = uy; b.sAz = uz; b.sBy = ly; b.sBz = lz; b.sCy = wy; b.sCz = wz;
-    if ((rc = gps_gemm_nt_launch(h, -1.0, U11, L21, 0.0, Wm, TRI_UPPER, TRI_NONE, C_ALL, nullptr, 0, -1.0, nullptr,
-                                 0, 0, &b)))
-      return rc;
-    // U12 = W T22^T
-    b.sAy = wy; b.sAz = wz; b.sBy = uy; b.sBz = uz; b.sCy = uy; b.sCz = uz;
-    if ((rc = gps_gemm_nt_launch(h, 1.0, Wm, T22, 0.0, U12, TRI_NONE, TRI_LOWER, C_ALL, nullptr, 0, -1.0, nullptr, 0,
-                                 0, &b)))
-      return rc;
-    // T21 = T22 W^T
-    b.sAy = uy; b.sAz = uz; b.sBy = wy; b.sBz = wz; b.sCy = uy; b.sCz = uz;
-    if ((rc = gps_gemm_nt_launch(h, 1.0, T22, Wm, 0.0, T21, TRI_LOWER, TRI_NONE, C_ALL, nullptr, 0, -1.0, nullptr, 0,
-                                 0, &b)))
-      return rc;
-  }
+  if ((rc = block_inverses_batched(h, L, tinv, bs, nfull, U, bs, (int64_t)bs * bs, T, bs, (int64_t)bs * bs, W)))
+    return rc;
   out->bs = bs; out->nfull = nfull; out->U = U; out->T = T; out->X = X;
   return 0;
 }
@@ -938,6 +951,15 @@ int gps_tri_inv_t(gps_handle* h, const DLTensor* Lt, DLTensor* U_out) {
   GPS_CUDA(h, cudaMemset2DAsync(U.p, U.ld * sizeof(double), 0, U.cols * sizeof(double), U.rows,
                                 h->stream));
   if ((rc = gps_block_inverses(h, L, tinv))) return rc;
+  const int64_t n = L.rows;
+  if (n > NB && n <= 4096 && n % NB == 0 && ((n / NB) & (n / NB - 1)) == 0) {
+    // a power-of-two number of 128-blocks: all nodes of a level in ONE strided-batch launch
+    // (3 launches per level instead of 3 per node: 9 instead of 21 at n = 1024)
+    double* T = (double*)gps_ws(h, WS_LEAF_T, (size_t)n * n * sizeof(double));
+    double* W = (double*)gps_ws(h, WS_LEAF_W, (size_t)n * n / 4 * sizeof(double));
+    if (!T || !W) return -102;
+    return block_inverses_batched(h, L, tinv, (int)n, 1, U.p, U.ld, 0, T, n, 0, W);
+  }
   return gps_inv_upper_full(h, L, U, tinv);
 }
 

@@ -77,7 +77,7 @@ def test_abi_of_the_cpu_build_matches_the_header(cpu_lib):
     assert cdll.gps_version() == 100
 
 
-@pytest.mark.parametrize('n', [1, 31, 129, 200])
+@pytest.mark.parametrize('n', [1, 31, 129, 200, 256])    # 256: the level-batched triangular inverse
 def test_cholesky_solve_inverse_through_the_host_recursion(gpf, n):
     """gps_potrf (recursive blocked, leaves + strip TRSMs + lower-masked GEMM updates),
     gps_trsm_rlt, gps_tri_inv_t, gps_sum_log_diag, gps_row_sumsq, gps_transpose."""
@@ -212,7 +212,7 @@ def test_split_k_gemm_through_the_launch_code(gpf):
         close(low, -np.tril(Asq @ Asq.T))
         close(ops.gemm_nt(A3, A3), A3.numpy() @ A3.numpy().T)
         before = h.profile_read(reset=False)[2]
-        close(ops.gemm_nt(conv(A[:, :400]), conv(B[:, :400])), A[:, :400] @ B[:, :400].T)   # K < 512: not sliced
+        close(ops.gemm_nt(conv(A[:, :200]), conv(B[:, :200])), A[:, :200] @ B[:, :200].T)   # K < 256: not sliced
         assert h.profile_read(reset=False)[2] - before == 1
     finally:
         h.set_option('gemm_splitk', 1)     # the default
