@@ -193,9 +193,18 @@ class CudaBackend(object):
         vl, vb = L.view(Lm), L.view(B)
         h.check(h.lib.gps_trsm_rlt(h.ptr, vl.ref, vb.ref))
 
-    def gemm_rowmap_(self, A, B, C, rowlim, coff, flops=-1.0):
+    def gemm_rowmap_(self, A, B, C, rowlim, coff, flops=-1.0, prefix=None, n_tiles=0):
+        """C -= A B^T where column c + coff <= rowlim[row]; with `prefix` (device int64, per 128-row tile
+        row the number of wanted tiles before it) only the wanted tiles get a thread block."""
         h, L = self._h(), self._L
         va, vb, vc, vr = L.view(A), L.view(B), L.view(C), L.view(rowlim)
+        if prefix is not None:
+            if n_tiles == 0:
+                return
+            vp = L.view(prefix)
+            h.check(h.lib.gps_gemm_nt_rowmap_compact(h.ptr, -1.0, va.ref, vb.ref, 1.0, vc.ref, vr.ref, int(coff),
+                                                     float(flops), vp.ref, int(n_tiles)))
+            return
         h.check(h.lib.gps_gemm_nt_rowmap(h.ptr, -1.0, va.ref, vb.ref, 1.0, vc.ref, vr.ref, int(coff),
                                          float(flops)))
 
@@ -321,6 +330,10 @@ class _Comm(object):
     def all_reduce_sum(self, t):
         if self.world > 1:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self._g('gather'))
+
+
+def _to_device(a, dev):
+    return torch.as_tensor(a, device=dev)
 
 
 # --------------------------------------------------------------------------------- the path
@@ -514,12 +527,20 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
                 return
             k0, k1 = lay.rows(k)
             fkey = (k, a, b, c_lo, c_hi)
-            flops = flops_cache.get(fkey)       # algorithmic flops, a pure function of the layout
-            if flops is None:
+            hit = flops_cache.get(fkey)         # pure functions of the layout: computed once
+            if hit is None:
                 g = np.minimum(grow_host[a:b], c_hi - 1)
-                flops = flops_cache[fkey] = 2.0 * (k1 - k0) * float(np.clip(g - c_lo + 1, 0, None).sum())
+                flops = 2.0 * (k1 - k0) * float(np.clip(g - c_lo + 1, 0, None).sum())
+                # wanted 128 x 128 tiles per tile row (rows are sorted by global index, so the last row
+                # of a tile row reaches furthest right)
+                last = grow_host[a:b][np.minimum(np.arange(127, b - a + 127, 128), b - a - 1)]
+                tiles_n = (c_hi - c_lo + 127) // 128
+                cnt = np.clip((np.minimum(last, c_hi - 1) - c_lo) // 128 + 1, 0, tiles_n)
+                pre = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+                hit = flops_cache[fkey] = (flops, _to_device(pre, dev), int(pre[-1]))
+            flops, prefix, n_tiles = hit
             Bop = Lfull[c_lo:c_hi, k0:k1] if Bsrc is None else Bsrc
-            be.gemm_rowmap_(Aloc[a:b, k0:k1], Bop, Aloc[a:b, c_lo:c_hi], grow[a:b], c_lo, flops)
+            be.gemm_rowmap_(Aloc[a:b, k0:k1], Bop, Aloc[a:b, c_lo:c_hi], grow[a:b], c_lo, flops, prefix, n_tiles)
 
         for k in range(nblk):
             r0, r1 = lay.rows(k)
