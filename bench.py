@@ -370,6 +370,8 @@ def main():
                     help='auto: 1 GPU -> fused single-GPU path; N GPUs -> ONE problem distributed over '
                          'the ranks (strong scaling); independent: one problem per GPU (weak)')
     ap.add_argument('--block', type=int, default=512)
+    ap.add_argument('--schedule', default='v2', choices=['v1', 'v2'],
+                    help='look-ahead schedule of the distributed factorisation (v1: the round-1 three-stream one)')
     ap.add_argument('--cpu-n', type=int, default=8192, dest='cpu_n')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-secondary', action='store_true', help='skip the C2 / C3 / C4 lines')
@@ -402,7 +404,7 @@ def main():
     # together; independent: every rank owns its own problem (seed = rank).  DESIGN.md (e)
     Xh, Yh = synth_gpr(n, d, seed=rank if mode == 'independent' else 0)
     if mode == 'dist':
-        gpf.parallel.init(block=args.block)
+        gpf.parallel.init(block=args.block, lookahead='v1' if args.schedule == 'v1' else True)
     Xp = torch.from_numpy(Xh).pin_memory()
     Yp = torch.from_numpy(Yh).pin_memory()
     kern = gpf.kernels.RBF(d, ARD=True, lengthscales=math.sqrt(d))
@@ -519,9 +521,9 @@ def main():
         nparam = d + 2
         nprob = world if mode == 'independent' else 1     # problems evaluated per step, whole job
         par = {'fused': 'single GPU, fused path', 'independent': 'independent problem per GPU',
-               'dist': 'one problem over %d GPU(s): block-row (block %d) distributed Cholesky + inverse; '
-                       'four-stream look-ahead pipeline, NCCL broadcasts (diagonal / top block) + all-gather '
-                       'per panel on three communicators' % (world, args.block)}[mode]
+               'dist': ('one problem over %d GPU(s): block-row (block %d) distributed Cholesky + inverse; schedule %s '
+                        '(v2: four-stream look-ahead pipeline; v1: three streams); NCCL broadcasts (diagonal / top '
+                        'block) + all-gather per panel on three communicators' % (world, args.block, args.schedule))}[mode]
         step_tf = nprob * float(n) ** 3 / (ms * 1e-3) / 1e12
         line = {
             'metric': 'GPR NLML+grad evals/s', 'value': nprob * 1e3 / ms, 'unit': 'evals/s',

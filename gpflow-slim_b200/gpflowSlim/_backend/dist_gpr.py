@@ -70,6 +70,11 @@ class PhaseTimer(object):
 
 TIMER = None
 _FINE = True     # fine-grained marks only make sense when everything runs on one stream
+# TRACE = {} switches on a per-panel timeline of the look-ahead schedule: every event the schedule
+# records becomes a timing event, and after the factorisation TRACE holds, per event family, the
+# milliseconds since the fork of the streams, plus the host time at which each panel was issued
+# (tools/dist_trace.py prints it).  Diagnostic only: timing events cost a little on every record.
+TRACE = None
 
 
 def _mark(name, fine=False):
@@ -154,11 +159,12 @@ class CudaBackend(object):
 
     # ---- streams / events for the look-ahead (CUDA streams, no tracing compiler)
     def streams(self):
-        """(main, chain, tb, gather): the caller's stream and three high-priority side streams
+        """(main, chain, tb, gather, narrow): the caller's stream and four high-priority side streams
         (chain highest: it carries the serial dependency chain of the factorisation)."""
         if getattr(self, '_side', None) is None:
             self._side = (torch.cuda.Stream(self.device, priority=-3),
                           torch.cuda.Stream(self.device, priority=-2),
+                          torch.cuda.Stream(self.device, priority=-1),
                           torch.cuda.Stream(self.device, priority=-1))
         return (torch.cuda.current_stream(self.device),) + self._side
 
@@ -166,7 +172,7 @@ class CudaBackend(object):
         return torch.cuda.stream(stream)
 
     def record(self, stream):
-        e = torch.cuda.Event()
+        e = torch.cuda.Event(enable_timing=TRACE is not None)
         e.record(stream)
         return e
 
@@ -502,17 +508,66 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
             if k < lay.nblk - 1:
                 update(k, lay.rows(k)[1], N)
                 _mark('trailing_gemm', fine=True)
-    else:
+    elif lookahead == 'v1':
+        # the round-1 schedule, kept for A/B measurements: chain = factor + broadcast + solve of ALL my
+        # panel rows + top-block broadcast + column k+1; gather = all-gather; main = column k+2, rest
         global _FINE
         _FINE = False
-        main, chain, tb, gath = streams
+        main, chain, _, gath = streams[:4]
+        nblk = lay.nblk
+        ev_narrow = [None] * nblk
+        start = be.record(main)
+        be.wait(chain, start)
+        be.wait(gath, start)
+        ev_c = ev_g = None
+        for k in range(nblk):
+            with be.on(chain):
+                Pn, mrows = factor_diag_and_solve(k)
+                ev_trsm = be.record(chain)
+                if k + 1 < nblk:
+                    r0, r1 = lay.rows(k)
+                    t0, t1 = lay.rows(k + 1)
+                    nxt = lay.owner(k + 1)
+                    T = top_buf[:(t1 - t0) * (r1 - r0)].view(t1 - t0, r1 - r0)
+                    if rank == nxt:
+                        be.copy_(T, Aloc[offs[k + 1]:offs[k + 1] + t1 - t0, r0:r1])
+                    comm.broadcast(T, nxt, 'chain')
+                    if k >= 1:
+                        be.wait(chain, ev_narrow[k - 1])      # column k+1 has seen panels <= k-1
+                    update(k, *lay.rows(k + 1), Bsrc=T)
+                ev_c = be.record(chain)
+            with be.on(gath):
+                be.wait(gath, ev_trsm)
+                gather_panel(k, Pn, mrows)
+                ev_g = be.record(gath)
+            if k + 1 < nblk:
+                with be.on(main):
+                    be.wait(main, ev_g)
+                    if k + 2 < nblk:
+                        update(k, *lay.rows(k + 2))
+                    ev_narrow[k] = be.record(main)
+                    if k + 3 < nblk:
+                        update(k, lay.rows(k + 3)[0], N)
+        be.wait(main, ev_c)
+        be.wait(main, ev_g)
+        _FINE = True
+        _mark('factor(lookahead)')
+    else:
+        _FINE = False
+        main, chain, tb, gath = streams[:4]
+        # the column-(k+2) update gets its own stream: on the gather stream it would hold up the next
+        # panel's solve and all-gather while it waits for the bulk update of the previous panel
+        import os as _os
+        nar = streams[4] if len(streams) > 4 and _os.environ.get('GPSLIM_DIST_NARROW_STREAM', '1') != '0' else gath
         nblk = lay.nblk
         ring = [be.empty(bs * bs) for _ in range(3)]      # diagonal blocks in flight (chain -> gather)
         ev_L, ev_top, ev_colT, ev_col = {}, {}, {}, {}
         ev_solve, ev_g, ev_narrow, ev_rest = {}, {}, {}, {}
         nend = nloc + R
+        if TRACE is not None and hasattr(torch.cuda, 'synchronize') and X.is_cuda:
+            torch.cuda.synchronize()            # align the host clock with the fork event
         start = be.record(main)
-        for st in (chain, tb, gath):
+        for st in (chain, tb, gath, nar):
             be.wait(st, start)
 
         grow_host = np.full(nend, NEVER, dtype=np.int64)
@@ -542,7 +597,11 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
             Bop = Lfull[c_lo:c_hi, k0:k1] if Bsrc is None else Bsrc
             be.gemm_rowmap_(Aloc[a:b, k0:k1], Bop, Aloc[a:b, c_lo:c_hi], grow[a:b], c_lo, flops, prefix, n_tiles)
 
+        import time as _time
+        host_issue, host_t0 = {}, _time.perf_counter()
         for k in range(nblk):
+            if TRACE is not None:
+                host_issue[k] = _time.perf_counter()
             r0, r1 = lay.rows(k)
             nb = r1 - r0
             own = lay.owner(k)
@@ -608,10 +667,12 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
             with be.on(gath):
                 gather_panel(k, Aloc[lo_k:, r0:r1], m_k)
                 ev_g[k] = be.record(gath)
-                if k + 2 < nblk:
-                    be.wait(gath, ev_rest.get(k - 1))     # main writes columns >= k+2 with panel k-1
+            if k + 2 < nblk:
+                with be.on(nar):
+                    be.wait(nar, ev_g[k])
+                    be.wait(nar, ev_rest.get(k - 1))      # main writes columns >= k+2 with panel k-1
                     update_rows(k, lo1, nend, *lay.rows(k + 2))
-                    ev_narrow[k] = be.record(gath)
+                    ev_narrow[k] = be.record(nar)
             # ------------------------------------------------ main: the bulk
             if k + 3 < nblk:
                 with be.on(main):
@@ -619,8 +680,17 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
                     lo3, _ = below_all[k + 2][rank]
                     update_rows(k, lo3, nend, lay.rows(k + 3)[0], N)
                     ev_rest[k] = be.record(main)
-        for st in (chain, tb, gath):
+        for st in (chain, tb, gath, nar):
             be.wait(main, be.record(st))
+        if TRACE is not None and hasattr(start, 'elapsed_time'):
+            end = be.record(main)
+            end.synchronize()
+            fam = dict(L=ev_L, top=ev_top, colT=ev_colT, col=ev_col, solve=ev_solve, gathered=ev_g,
+                       narrow=ev_narrow, rest=ev_rest)
+            TRACE.clear()
+            TRACE.update({name: {k: start.elapsed_time(e) for k, e in d.items()} for name, d in fam.items()})
+            TRACE['host_issue_ms'] = {k: (t - host_t0) * 1e3 for k, t in host_issue.items()}
+            TRACE['total_ms'] = start.elapsed_time(end)
         _FINE = True
         _mark('factor(lookahead)')
     alpha_t = Aloc[nloc:, :N]

@@ -44,7 +44,8 @@ def init(group=None, block=512, backend='nccl', device=None, lookahead=True):
                                for name in ('chain', 'tb', 'gather')}
     if group is None:
         group = _STATE.get('own_group')
-    _STATE.update(active=True, group=group, block=int(block), lookahead=bool(lookahead))
+    _STATE.update(active=True, group=group, block=int(block),
+                  lookahead=lookahead if lookahead == 'v1' else bool(lookahead))
 
 
 def _pg():

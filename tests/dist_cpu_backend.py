@@ -16,7 +16,7 @@ class CpuBackend(object):
     # look-ahead "streams": sequential execution in issue order is one valid schedule of the
     # dependency graph, so the look-ahead ORDER of operations is what gets tested here
     def streams(self):
-        return 'main', 'chain', 'tb', 'gather'
+        return 'main', 'chain', 'tb', 'gather', 'narrow'
 
     def on(self, stream):
         import contextlib

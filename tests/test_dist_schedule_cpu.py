@@ -44,7 +44,7 @@ class Tracer(object):
 
     # ---- streams / events
     def streams(self):
-        return 'main', 'chain', 'tb', 'gather'
+        return 'main', 'chain', 'tb', 'gather', 'narrow'
 
     @contextlib.contextmanager
     def on(self, stream):
@@ -156,7 +156,7 @@ def test_lookahead_schedule_has_no_unordered_conflicts(world, nblk):
         assert not bad, 'rank %d: %d unordered conflicting pairs, first: %s' % (rank, len(bad), bad[:5])
         # the schedule really is concurrent: most cross-stream pairs are NOT ordered
         streams_used = {o[1] for o in ops}
-        assert streams_used == {'main', 'chain', 'tb', 'gather'} or nblk < 4
+        assert streams_used == {'main', 'chain', 'tb', 'gather', 'narrow'} or nblk < 4
 
 
 def test_the_checker_sees_a_missing_wait(monkeypatch):

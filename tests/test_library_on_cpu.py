@@ -439,7 +439,7 @@ def _dist_worker(rank, world, port, so_path, n, r, block, out_q):
             self._L, self.device = lib, torch.device('cpu')
 
         def streams(self):
-            return 'main', 'chain', 'tb', 'gather'
+            return 'main', 'chain', 'tb', 'gather', 'narrow'
 
         def on(self, stream):
             return contextlib.nullcontext()
