@@ -191,38 +191,67 @@ __device__ __forceinline__ void inv8(const double* S, double* Tdp, int c0, int l
   }
 }
 
-// Cholesky + inverse of the 8x8 diagonal block (executed by one full warp)
+// 1 / sqrt(a) to FP64 rounding accuracy from the single-precision MUFU seed and two Newton steps
+// (relative error 2^-22 -> 1e-13 -> 1e-26): the library rsqrt(double) costs ~3x more in the
+// serial chain of the 8x8 factorisation.  Out-of-range arguments take the library routine.
+__device__ __forceinline__ double fast_rsqrt(double a) {
+  if (!(a > 1e-30 && a < 1e30)) return rsqrt(a);
+  double y = (double)rsqrtf((float)a);
+  const double h = 0.5 * a;
+  y = y * fma(-h * y, y, 1.5);
+  y = y * fma(-h * y, y, 1.5);
+  return y;
+}
+
+// Cholesky + inverse of the 8x8 diagonal block (executed by one full warp).  EVERY lane holds the
+// whole lower triangle in registers and factors it redundantly: no shuffle sits on the serial
+// chain (sqrt -> scale -> rank-1 update, 8 times), which is the critical path of the whole leaf --
+// the row-per-lane variant spent ~4500 cycles here per 8 columns, mostly in shuffles and the
+// library rsqrt.  Lane c < 8 then inverts column c of the factor from the same registers.
 __device__ __forceinline__ void factor8(double* S, double* Tdp, int c0, int lane, int* s_bad) {
-  const int l = lane & 7;
-  double a[8];
+  double a[8][8], rinv[8];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) a[c] = (c <= l) ? S[(c0 + l) * LLD + c0 + c] : 0.0;
-  double myrinv = 0.0;
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) a[i][j] = S[(c0 + i) * LLD + c0 + j];      // broadcast loads
+  __syncwarp();      // every lane has read the block before lanes 0..7 overwrite it below
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    double akk = __shfl_sync(0xffffffffu, a[k], k);
+    const double akk = a[k][k];
     if (!(akk > 0.0) && lane == 0 && *s_bad == 0) *s_bad = c0 + k + 1;
-    double rinv = rsqrt(akk);
-    double rk = akk * rinv;
-    if (l == k) {
-      a[k] = rk;
-      myrinv = rinv;
-    } else {
-      a[k] *= rinv;
-    }
+    const double r = fast_rsqrt(akk);
+    rinv[k] = r;
+    a[k][k] = akk * r;
 #pragma unroll
-    for (int c = k + 1; c < 8; ++c) {
-      double lck = __shfl_sync(0xffffffffu, a[k], c);
-      a[c] = fma(-a[k], lck, a[c]);
+    for (int i = k + 1; i < 8; ++i) a[i][k] *= r;
+#pragma unroll
+    for (int j = k + 1; j < 8; ++j)
+#pragma unroll
+      for (int i = j; i < 8; ++i) a[i][j] = fma(-a[i][k], a[j][k], a[i][j]);
+  }
+  const int l = lane & 7;
+  if (lane < 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {           // lane l stores row l (static register indices only)
+      if (i == l) {
+#pragma unroll
+        for (int c = 0; c <= i; ++c) S[(c0 + i) * LLD + c0 + c] = a[i][c];
+      }
     }
+  }
+  // T = L^-1, column c = l by forward substitution: t[i] = -rinv[i] * sum_{c <= k < i} a[i][k] t[k]
+  double t[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    double sacc = 0.0;
+#pragma unroll
+    for (int k = 0; k < i; ++k) sacc = fma(a[i][k], t[k], sacc);           // t[k] == 0 for k < c
+    t[i] = (i == l) ? rinv[i] : ((i > l) ? -sacc * rinv[i] : 0.0);
   }
   if (lane < 8) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      if (c <= l) S[(c0 + l) * LLD + c0 + c] = a[c];
+    for (int i = 0; i < 8; ++i) Tdp[i * 8 + l] = t[i];
   }
-  __syncwarp();
-  inv8(S, Tdp, c0, lane, myrinv);
 }
 
 template <bool DO_CHOL>
@@ -249,6 +278,16 @@ potrf_leaf_kernel(double* __restrict__ Abase, int64_t lda, int n_total, double* 
     S[i * LLD + j] = v;
   }
   if (tid == 0) s_bad = 0;
+  // (row, column) of the t-th tile of a lower triangle enumerated by rows: decoded once instead of
+  // with a square root per tile in the trailing-update loop
+  __shared__ unsigned char tile_r[120], tile_c[120];
+  if (tid < 120) {
+    int r = (int)((sqrtf(8.0f * (float)tid + 1.0f) - 1.0f) * 0.5f);
+    while (r * (r + 1) / 2 > tid) --r;
+    while ((r + 1) * (r + 2) / 2 <= tid) ++r;
+    tile_r[tid] = (unsigned char)r;
+    tile_c[tid] = (unsigned char)(tid - r * (r + 1) / 2);
+  }
   __syncthreads();
 
   if (DO_CHOL) {
@@ -274,10 +313,7 @@ potrf_leaf_kernel(double* __restrict__ Abase, int64_t lda, int n_total, double* 
       const int tstart = (warp == 0) ? 0 : warp;
       const int tstep = (warp == 0) ? ntiles : 7;     // warp 0 takes tile 0 only
       for (int t = tstart; t < ntiles; t += tstep) {
-        int r = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-        while (r * (r + 1) / 2 > t) --r;
-        while ((r + 1) * (r + 2) / 2 <= t) ++r;
-        const int c = t - r * (r + 1) / 2;
+        const int r = tile_r[t], c = tile_c[t];
         const int bi = p + 1 + r, bj = p + 1 + c;
         const double* ap = S + (8 * bi + lr) * LLD + c0 + lc;
         const double* bp = S + (8 * bj + lr) * LLD + c0 + lc;

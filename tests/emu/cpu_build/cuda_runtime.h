@@ -131,6 +131,7 @@ inline void dmma884(double& c0, double& c1, double a, double b) {
   c1 = s1;
 }
 inline double rsqrt(double x) { return 1.0 / sqrt(x); }
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 inline int atomicCAS(int* addr, int cmp, int val) {
   std::lock_guard<std::mutex> g(emu_atomic_mutex);
   int old = *addr;

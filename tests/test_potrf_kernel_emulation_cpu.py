@@ -29,7 +29,7 @@ NB = 128
 def emu(tmp_path_factory):
     src = open(POTRF_CU).read()
     start = src.index('#include "internal.cuh"') + len('#include "internal.cuh"')
-    end = src.index('bool g_attr_set = false;')
+    end = src.index('void set_attrs(gps_handle* h) {')
     region = src[start:end]
     region = region.replace('constexpr int NB = GPS_NB;', 'constexpr int NB = 128;')
     region, n1 = re.subn(r'extern __shared__ __align__\(16\) double sm\[\];', 'double* sm = emu_smem;', region)

@@ -10,8 +10,9 @@ import math
 import os
 import sys
 
-import torch
-import torch.distributed as dist
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', os.environ.get('GPSLIM_MAXCONN', '32'))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, 'gpflow-slim_b200'))
