@@ -347,7 +347,10 @@ gram_bwd_kernel(const Plan pl, const PlanDims pd, const double* __restrict__ the
   extern __shared__ double sm[];
   const int nacc = pl.n_theta + 1;
   double* th = sm;                                 // [n_theta]
-  double* sl = th + pl.n_theta;                    // [TILE][S]
+  double* tinv = th + pl.n_theta;                  // [n_theta]  1 / theta: the per-element gradient terms
+                                                   // multiply by these instead of dividing (an FP64 division
+                                                   // is ~25 instructions; the NKN config had ~40 per element)
+  double* sl = tinv + pl.n_theta;                  // [TILE][S]
   double* sr = sl + TILE * pl.S;                   // [TILE][S]
   double* bi = sr + TILE * pl.S;                   // [MAX_R][TILE]   beta rows (i side)
   double* bj = bi + (w.mode == W_GPR ? w.R * TILE : 0);
@@ -360,7 +363,10 @@ gram_bwd_kernel(const Plan pl, const PlanDims pd, const double* __restrict__ the
 
   double acc[MAX_ACC];
   for (int t = 0; t < nacc; ++t) acc[t] = 0.0;
-  for (int t = tid; t < pl.n_theta; t += GRAM_THREADS) th[t] = theta[t];
+  for (int t = tid; t < pl.n_theta; t += GRAM_THREADS) {
+    th[t] = theta[t];
+    tinv[t] = 1.0 / theta[t];
+  }
   for (int idx = tid; idx < TILE * pl.FT; idx += GRAM_THREADS) {
     int r = idx / pl.FT, c = idx - r * pl.FT;
     sl[r * pl.S + c] = (i0 + r < N) ? FL[(i0 + r) * pl.FT + c] : 0.0;
@@ -432,22 +438,23 @@ gram_bwd_kernel(const Plan pl, const PlanDims pd, const double* __restrict__ the
           const PrimC P = pl.prims[p];
           const double g = vb[p];
           const double* t = th + P.theta_off;
+          const double* ti = tinv + P.theta_off;
           const double* fip = fi + P.feat_off;
           const double* fjp = fj + P.feat_off;
           if (is_stationary(P.type)) {
-            acc[P.theta_off] += g * ev[p].k / t[0];
+            acc[P.theta_off] += g * ev[p].k * ti[0];
             const double G = g * ev[p].dk;               // dObj / d(d2)
             if (P.ard) {
               for (int k = 0; k < P.ndims; ++k) {
                 double df = fip[k] - fjp[k];
-                acc[P.theta_off + 1 + k] += G * (-2.0) * df * df / t[1 + k];
-                if (w.want_dx) dxr[pd.dims[p][k]] += 2.0 * G * df / t[1 + k];
+                acc[P.theta_off + 1 + k] += G * (-2.0) * df * df * ti[1 + k];
+                if (w.want_dx) dxr[pd.dims[p][k]] += 2.0 * G * df * ti[1 + k];
               }
             } else {
-              acc[P.theta_off + 1] += G * (-2.0) * ev[p].d2 / t[1];
+              acc[P.theta_off + 1] += G * (-2.0) * ev[p].d2 * ti[1];
               if (w.want_dx)
                 for (int k = 0; k < P.ndims; ++k)
-                  dxr[pd.dims[p][k]] += 2.0 * G * (fip[k] - fjp[k]) / t[1];
+                  dxr[pd.dims[p][k]] += 2.0 * G * (fip[k] - fjp[k]) * ti[1];
             }
           } else if (P.type == GPS_LINEAR) {
             for (int k = 0; k < P.ndims; ++k) {
@@ -456,16 +463,17 @@ gram_bwd_kernel(const Plan pl, const PlanDims pd, const double* __restrict__ the
             }
           } else {
             const int nd = P.ndims;
-            const double kk = ev[p].k, r = ev[p].dk, ls = t[1], per = t[2];
-            acc[P.theta_off] += g * kk / t[0];
-            acc[P.theta_off + 1] += g * kk * r / ls;
-            double dcs = 0.0;   // d(sum cos)/dp
+            const double kk = ev[p].k, r = ev[p].dk, ils = ti[1], iper = ti[2];
+            acc[P.theta_off] += g * kk * ti[0];
+            acc[P.theta_off + 1] += g * kk * r * ils;
+            double dcs = 0.0;   // per * d(sum cos)/dp
+            const double gx = -g * kk * (0.5 * M_PI) * iper * ils * ils;
             for (int k = 0; k < nd; ++k) {
               double sind = fip[nd + k] * fjp[k] - fip[k] * fjp[nd + k];   // sin(a_i - a_j)
-              dcs += sind * (fip[2 * nd + k] - fjp[2 * nd + k]) / per;
-              if (w.want_dx) dxr[pd.dims[p][k]] += -g * kk * sind * M_PI / (2.0 * per * ls * ls);
+              dcs += sind * (fip[2 * nd + k] - fjp[2 * nd + k]);
+              if (w.want_dx) dxr[pd.dims[p][k]] += gx * sind;
             }
-            acc[P.theta_off + 2] += g * kk * dcs / (4.0 * ls * ls);
+            acc[P.theta_off + 2] += g * kk * dcs * iper * (0.25 * ils * ils);
           }
         }
       }
@@ -1304,7 +1312,7 @@ int gps_gram_bwd_mat(gps_handle* h, const gps_kernel_desc* desc, const double* t
     pdx = (double*)gps_ws(h, WS_PARTIAL2, (size_t)njc * N * X.cols * sizeof(double));
     if (!pdx) return -102;
   }
-  size_t smem = (size_t)(pl.n_theta + 2 * TILE * pl.S + (w.mode == W_GPR ? 2 * w.R * TILE : 0) +
+  size_t smem = (size_t)(2 * pl.n_theta + 2 * TILE * pl.S + (w.mode == W_GPR ? 2 * w.R * TILE : 0) +
                          8 * nacc + (dX ? TILE * X.cols : 0)) * sizeof(double);
   if (!use_smem_acc && smem > 220 * 1024) return gps_fail(h, -2, "gram_bwd: kernel too large for shared memory");
   if (use_smem_acc) {

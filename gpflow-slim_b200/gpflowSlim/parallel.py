@@ -37,11 +37,22 @@ def init(group=None, block=512, backend='nccl', device=None, lookahead=True):
         # panel all-gather): a process group runs its collectives in issue order on ONE stream, so
         # with a single communicator a 100 MB panel all-gather would sit in front of the 2 MB
         # broadcast the serial chain is waiting for
-        opts = dist.ProcessGroupNCCL.Options()
-        opts.is_high_priority_stream = True
+        # ... and each with a SMALL CTA budget (ncclConfig max_ctas): a collective whose peers are not
+        # ready yet spins on its CTAs, and NCCL's default on an NVSwitch box is dozens of them per
+        # collective -- with three communicators that pinned up to ~100 of the 148 SMs while the
+        # owner of the next diagonal block was still computing (measured: the 8-GPU factor phase got
+        # SLOWER when the collectives moved to separate communicators with default budgets).  A 2 MB
+        # broadcast is latency-bound: 2 CTAs; the panel all-gather: 8.
+        ctas = [int(c) for c in os.environ.get('GPSLIM_NCCL_CTAS', '2,2,8').split(',')]
         ranks = list(range(dist.get_world_size()))
-        _STATE['own_group'] = {name: dist.new_group(ranks=ranks, backend='nccl', pg_options=opts)
-                               for name in ('chain', 'tb', 'gather')}
+        own = {}
+        for name, c in zip(('chain', 'tb', 'gather'), ctas):
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.is_high_priority_stream = True
+            if c > 0:
+                opts.config.max_ctas = c
+            own[name] = dist.new_group(ranks=ranks, backend='nccl', pg_options=opts)
+        _STATE['own_group'] = own
     if group is None:
         group = _STATE.get('own_group')
     _STATE.update(active=True, group=group, block=int(block),
