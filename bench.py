@@ -371,8 +371,9 @@ def main():
                     help='auto: 1 GPU -> fused single-GPU path; N GPUs -> ONE problem distributed over '
                          'the ranks (strong scaling); independent: one problem per GPU (weak)')
     ap.add_argument('--block', type=int, default=512)
-    ap.add_argument('--schedule', default='v2', choices=['v1', 'v2'],
-                    help='look-ahead schedule of the distributed factorisation (v1: the round-1 three-stream one)')
+    ap.add_argument('--schedule', default='v1', choices=['v1', 'v2'],
+                    help='look-ahead schedule of the distributed factorisation (v1: three streams, the faster one '
+                         'on 8 x B200; v2: the five-stream pipeline)')
     ap.add_argument('--cpu-n', type=int, default=8192, dest='cpu_n')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-secondary', action='store_true', help='skip the C2 / C3 / C4 lines')
@@ -405,7 +406,7 @@ def main():
     # together; independent: every rank owns its own problem (seed = rank).  DESIGN.md (e)
     Xh, Yh = synth_gpr(n, d, seed=rank if mode == 'independent' else 0)
     if mode == 'dist':
-        gpf.parallel.init(block=args.block, lookahead='v1' if args.schedule == 'v1' else True)
+        gpf.parallel.init(block=args.block, lookahead=args.schedule)
     Xp = torch.from_numpy(Xh).pin_memory()
     Yp = torch.from_numpy(Yh).pin_memory()
     kern = gpf.kernels.RBF(d, ARD=True, lengthscales=math.sqrt(d))

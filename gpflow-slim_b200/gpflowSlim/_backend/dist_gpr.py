@@ -508,6 +508,16 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
 
     _mark('setup')
     streams = be.streams() if lookahead else None
+    # The chain of the factorisation runs next to bulk updates that occupy every SM: each extra
+    # launch on it waits for an SM to come free, so the split-K slicing of its small products (a
+    # gain when the GPU is idle) is switched off for the duration of the factorisation, and the
+    # bulk update is launched on the plain grouped grid unless GPSLIM_DIST_COMPACT=1 -- the two
+    # differences to the round-1 factor phase (77 ms on 8 GPUs) that the round-2 A/B runs
+    # (profiles/r02_dist_8gpu_ab.txt: 87-94 ms) could not separate before the GPU budget ran out.
+    compact = _os_environ().get('GPSLIM_DIST_COMPACT', '0') == '1'
+    splitk_off = _os_environ().get('GPSLIM_DIST_SPLITK', '0') != '1' and hasattr(be, 'set_option')
+    if splitk_off:
+        be.set_option('gemm_splitk', 0)
     if streams is None:
         # plain right-looking order
         for k in range(lay.nblk):
@@ -516,7 +526,7 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
             if k < lay.nblk - 1:
                 update(k, lay.rows(k)[1], N)
                 _mark('trailing_gemm', fine=True)
-    elif lookahead == 'v1':
+    elif lookahead != 'v2':
         # the round-1 schedule, kept for A/B measurements: chain = factor + broadcast + solve of ALL my
         # panel rows + top-block broadcast + column k+1; gather = all-gather; main = column k+2, rest
         global _FINE
@@ -607,6 +617,8 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
                 pre = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
                 hit = flops_cache[fkey] = (flops, _to_device(pre, dev), int(pre[-1]))
             flops, prefix, n_tiles = hit
+            if not compact:
+                prefix, n_tiles = None, 0
             Bop = Lfull[c_lo:c_hi, k0:k1] if Bsrc is None else Bsrc
             be.gemm_rowmap_(Aloc[a:b, k0:k1], Bop, Aloc[a:b, c_lo:c_hi], grow[a:b], c_lo, flops, prefix, n_tiles)
 
@@ -708,6 +720,8 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
             TRACE['total_ms'] = start.elapsed_time(end)
         _FINE = True
         _mark('factor(lookahead)')
+    if splitk_off:
+        be.set_option('gemm_splitk', 1)
     alpha_t = Aloc[nloc:, :N]
     return Lfull, Lt, alpha_t
 

@@ -21,6 +21,8 @@ _STATE = {'active': False, 'group': None, 'block': 512, 'lookahead': True, 'own_
 
 
 def init(group=None, block=512, backend='nccl', device=None, lookahead=True):
+    # lookahead: True / 'v1' = the three-stream schedule (default: the faster one on 8 x B200, see
+    # profiles/r02_dist_8gpu_ab.txt), 'v2' = the five-stream pipeline, False = plain right-looking order
     """Activate the distributed paths.  If torch.distributed is not initialised yet and the
     torchrun environment variables are present, initialise it (backend NCCL)."""
     import os
@@ -37,26 +39,27 @@ def init(group=None, block=512, backend='nccl', device=None, lookahead=True):
         # panel all-gather): a process group runs its collectives in issue order on ONE stream, so
         # with a single communicator a 100 MB panel all-gather would sit in front of the 2 MB
         # broadcast the serial chain is waiting for
-        # ... and each with a SMALL CTA budget (ncclConfig max_ctas): a collective whose peers are not
-        # ready yet spins on its CTAs, and NCCL's default on an NVSwitch box is dozens of them per
-        # collective -- with three communicators that pinned up to ~100 of the 148 SMs while the
-        # owner of the next diagonal block was still computing (measured: the 8-GPU factor phase got
-        # SLOWER when the collectives moved to separate communicators with default budgets).  A 2 MB
-        # broadcast is latency-bound: 2 CTAs; the panel all-gather: 8.
-        ctas = [int(c) for c in os.environ.get('GPSLIM_NCCL_CTAS', '2,2,8').split(',')]
+        # GPSLIM_NCCL_COMMS=1 puts all three kinds on ONE high-priority communicator (the round-1
+        # arrangement); GPSLIM_NCCL_CTAS caps the CTAs NCCL may use per communicator (0 = NCCL's own
+        # choice).  Both are measurement knobs: profiles/r02_dist_8gpu_ab.txt holds the A/B runs.
+        ctas = [int(c) for c in os.environ.get('GPSLIM_NCCL_CTAS', '4,4,16').split(',')]
+        ncomm = int(os.environ.get('GPSLIM_NCCL_COMMS', '3'))
         ranks = list(range(dist.get_world_size()))
         own = {}
         for name, c in zip(('chain', 'tb', 'gather'), ctas):
+            if ncomm == 1 and own:
+                own[name] = own['chain']
+                continue
             opts = dist.ProcessGroupNCCL.Options()
             opts.is_high_priority_stream = True
-            if c > 0:
+            if c > 0 and ncomm != 1:
                 opts.config.max_ctas = c
             own[name] = dist.new_group(ranks=ranks, backend='nccl', pg_options=opts)
         _STATE['own_group'] = own
     if group is None:
         group = _STATE.get('own_group')
     _STATE.update(active=True, group=group, block=int(block),
-                  lookahead=lookahead if lookahead == 'v1' else bool(lookahead))
+                  lookahead=lookahead if lookahead in ('v1', 'v2') else bool(lookahead))
 
 
 def _pg():

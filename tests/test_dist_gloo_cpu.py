@@ -67,7 +67,8 @@ def _worker(rank, world, port, n, d, r, block, lookahead, out_q):
 
 @pytest.mark.parametrize('world,n,r,block,lookahead', [(1, 700, 1, 256, True), (2, 900, 2, 128, True),
                                                        (3, 1100, 1, 256, True), (2, 600, 1, 128, False),
-                                                       (4, 1300, 1, 128, True), (2, 515, 3, 256, True)])
+                                                       (4, 1300, 1, 128, True), (2, 515, 3, 256, True),
+                                                       (2, 900, 2, 128, 'v2'), (3, 1100, 1, 256, 'v2'), (4, 1300, 1, 128, 'v2')])
 def test_distributed_gpr_host_logic_matches_oracle(world, n, r, block, lookahead):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()

@@ -1,4 +1,4 @@
-"""Race check of the four-stream look-ahead schedule of the distributed factorisation
+"""Race check of the look-ahead schedules (v1: three streams, the default; v2: five streams) of the distributed factorisation
 (gpflowSlim/_backend/dist_gpr.py:factor) WITHOUT a GPU: a tracing backend records, for every
 operation the schedule issues, its stream and the memory regions it reads and writes, plus every
 event record / wait; vector clocks over the streams then say which pairs of operations are
@@ -126,8 +126,9 @@ def _happens_before(a, b):
     return a[2][sa] <= b[2].get(sa, 0)
 
 
+@pytest.mark.parametrize('schedule', ['v1', 'v2'])
 @pytest.mark.parametrize('world,nblk', [(1, 7), (2, 9), (3, 10), (4, 13), (8, 20)])
-def test_lookahead_schedule_has_no_unordered_conflicts(world, nblk):
+def test_lookahead_schedule_has_no_unordered_conflicts(world, nblk, schedule):
     bs, R = 128, 2
     N = nblk * bs - 37                    # ragged last block
     ld = dist_gpr._round_up(N, 16)
@@ -139,7 +140,8 @@ def test_lookahead_schedule_has_no_unordered_conflicts(world, nblk):
         tr = Tracer(ld, world, rank)
         X = torch.zeros(N, 2, dtype=F64)
         Yc = torch.zeros(N, R, dtype=F64)
-        Lfull, Lt, alpha_t = dist_gpr.factor(Prog(), torch.zeros(3, dtype=F64), 0.1, X, Yc, lay, tr, tr, lookahead=True)
+        Lfull, Lt, alpha_t = dist_gpr.factor(Prog(), torch.zeros(3, dtype=F64), 0.1, X, Yc, lay, tr, tr,
+                                             lookahead=schedule)
         # the consumer on the main stream reads everything
         tr._op('consume', [Lfull[:, :N], Lt[:, :N], alpha_t], [])
         ops = tr.ops
@@ -156,7 +158,8 @@ def test_lookahead_schedule_has_no_unordered_conflicts(world, nblk):
         assert not bad, 'rank %d: %d unordered conflicting pairs, first: %s' % (rank, len(bad), bad[:5])
         # the schedule really is concurrent: most cross-stream pairs are NOT ordered
         streams_used = {o[1] for o in ops}
-        assert streams_used == {'main', 'chain', 'tb', 'gather', 'narrow'} or nblk < 4
+        want = {'main', 'chain', 'tb', 'gather', 'narrow'} if schedule == 'v2' else {'main', 'chain', 'gather'}
+        assert streams_used == want or nblk < 4
 
 
 def test_the_checker_sees_a_missing_wait(monkeypatch):
@@ -176,7 +179,7 @@ def test_the_checker_sees_a_missing_wait(monkeypatch):
             Tracer.wait(self, stream, event)
     tr = Sloppy(ld, world, 0)
     dist_gpr.factor(Prog(), torch.zeros(3, dtype=F64), 0.1, torch.zeros(N, 2, dtype=F64), torch.zeros(N, R, dtype=F64),
-                    lay, tr, tr, lookahead=True)
+                    lay, tr, tr, lookahead='v2')
     ops = tr.ops
     n_bad = 0
     for j, b in enumerate(ops):

@@ -402,7 +402,7 @@ def test_experimental_switches_through_the_real_dispatch_code(gpf, golden):
 
 
 # ----------------------------------------------------------------------------- distributed path
-def _dist_worker(rank, world, port, so_path, n, r, block, out_q):
+def _dist_worker(rank, world, port, so_path, n, r, block, out_q, schedule=True):
     """One rank of the REAL distributed GPR algorithm (_backend/dist_gpr.py: block-row layout,
     look-ahead schedule, panel broadcasts / all-gathers, inverse rows, gradient contraction) on
     the REAL kernels (gps_gemm_nt_rowmap, gps_trsm_rl{t,n}_prefix, gps_gpr_weight_rows, ...) of the
@@ -459,7 +459,7 @@ def _dist_worker(rank, world, port, so_path, n, r, block, out_q):
     prog = kern.program()
     theta = prog.theta('cpu').detach()
     nlml, dth, dnz, dY = dist_gpr.nlml_and_grad(prog, theta, 0.1, torch.tensor(X), torch.tensor(Y), block=block,
-                                                backend=CpuLibBackend(), lookahead=True)
+                                                backend=CpuLibBackend(), lookahead=schedule)
     th = theta.clone().requires_grad_(True)
     nz = torch.tensor(0.1, dtype=torch.float64, requires_grad=True)
     Yt = torch.tensor(Y, requires_grad=True)
@@ -472,8 +472,9 @@ def _dist_worker(rank, world, port, so_path, n, r, block, out_q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize('schedule', [True] + (['v2'] if FULL else []))
 @pytest.mark.parametrize('world,n,r,block', [(2, 300, 1, 128)] + ([(1, 330, 2, 128), (3, 420, 1, 128)] if FULL else []))
-def test_distributed_gpr_on_the_real_kernels_under_gloo(cpu_lib, world, n, r, block):
+def test_distributed_gpr_on_the_real_kernels_under_gloo(cpu_lib, world, n, r, block, schedule):
     import socket
     import torch.multiprocessing as mp
     s = socket.socket()
@@ -482,7 +483,7 @@ def test_distributed_gpr_on_the_real_kernels_under_gloo(cpu_lib, world, n, r, bl
     s.close()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_dist_worker, args=(i, world, port, cpu_lib, n, r, block, q)) for i in range(world)]
+    procs = [ctx.Process(target=_dist_worker, args=(i, world, port, cpu_lib, n, r, block, q, schedule)) for i in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=900) for _ in range(world)]

@@ -40,7 +40,7 @@ def main():
     conv = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
     m = gpf.models.GPR(conv(X), conv(Y), kern=gpf.kernels.RBF(8, ARD=True, lengthscales=math.sqrt(8)))
     params = [p.unconstrained_tensor for p in m.parameters]
-    gpf.parallel.init(block=args.block)
+    gpf.parallel.init(block=args.block, lookahead=os.environ.get('GPSLIM_SCHEDULE', 'v2'))
 
     def step():
         obj = m.objective
