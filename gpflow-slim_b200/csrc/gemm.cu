@@ -59,7 +59,6 @@ struct GemmArgs {
   // Without it every tile of the M x N rectangle gets a CTA and the unwanted ones exit at once -- but a
   // CTA of this kernel needs a whole SM, so each of those costs an SM a few microseconds.
   const int64_t* tile_prefix;
-  int n_tiles_total;           // tiles the grid's x dimension walks (>= gridDim.x: persistent CTAs)
 };
 
 __device__ __forceinline__ void tile_coords(const GemmArgs& g, int bid, int& ti, int& tj) {
@@ -402,6 +401,25 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
 gemm_nt_tma_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmA,
                    const __grid_constant__ CUtensorMap tmB) {
   extern __shared__ __align__(16) double smem[];
+  int ti, tj;
+  tile_coords(g, blockIdx.x, ti, tj);
+  const int m0 = ti * BM, n0 = tj * BN;
+  if (g.c_uplo == C_LOWER && m0 + BM - 1 < n0) return;
+  if (g.c_uplo == C_ROWMAP && (int64_t)n0 + g.coff > g.rowlim[min(m0 + BM, g.M) - 1]) return;
+  if (g.lo_mode == 2 && (int64_t)n0 + BN - 1 + g.lo_off < g.rowlo[m0]) return;
+
+  int klo, khi;
+  k_range(g, ti, tj, klo, khi);
+  if (g.lo_mode == 1) {
+    int64_t lo = g.rowlo[m0] - g.lo_off;
+    if (lo > klo) klo = (int)(lo < khi ? lo / TBK * TBK : khi);
+  }
+  if (g.split_k > 1) {   // this CTA's slice of K; k_chunk is a multiple of TBK, so no box straddles a slice
+    klo = max(klo, (int)blockIdx.y * g.k_chunk);
+    khi = min(khi, ((int)blockIdx.y + 1) * g.k_chunk);
+  }
+  const int nk = (khi > klo) ? (khi - klo + TBK - 1) / TBK : 0;
+
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const uint32_t base = (smem_u32(smem) + 1023u) & ~1023u;
@@ -416,10 +434,34 @@ gemm_nt_tma_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmA,
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
+  if (g.split_k == 1) prefetch_c_tile(g, m0, n0, tid);
 
-  // consumers: 2 x 4 DMMA warps, warp tile 64 x 32
+  // ---------------- producer duty: lane 0 of warp 0 feeds the ring.  Load L goes to slot
+  // L % TSTAGES; it is issued in the middle of iteration L - (TSTAGES - 1), i.e. one full
+  // iteration after the slot's previous contents were consumed, so the wait on the empty
+  // barrier is normally already satisfied and never holds up DMMA issue.
+  auto issue_load = [&](int L) {
+    const int sl = L % TSTAGES;
+    const uint32_t use = (uint32_t)(L / TSTAGES);
+    mbar_wait(bar_empty + 8 * sl, (use & 1u) ^ 1u);      // first use of a slot: returns at once
+    mbar_arrive_expect_tx(bar_full + 8 * sl, TSTAGE_BYTES);
+    const int k = klo + L * TBK;
+    tma_load_2d(base + sl * TSTAGE_BYTES, &tmA, k, m0, bar_full + 8 * sl);
+    tma_load_2d(base + sl * TSTAGE_BYTES + TBOX_BYTES, &tmB, k, n0, bar_full + 8 * sl);
+  };
+  if (tid == 0) {
+    for (int L = 0; L < TSTAGES - 1 && L < nk; ++L) issue_load(L);
+  }
+
+  // ---------------- consumers: 2 x 4 DMMA warps, warp tile 64 x 32
   const int wm = warp >> 2, wn = warp & 3;
   const int lr = lane >> 2, lc = lane & 3;
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
   // byte offset of this lane's element inside a box row, for the four k-steps of a k-tile
   // A side: fragment row lr of every 8-row group reads box row pr = {0,2,4,6,1,3,5,7}[lr], so the
   // four rows a half-warp touches per 64-bit load sit in four different 32-byte bank groups of
@@ -434,115 +476,61 @@ gemm_nt_tma_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmA,
   const uint32_t a_row = (uint32_t)(wm * 64 + pr) * 128u;
   const uint32_t b_row = (uint32_t)TBOX_BYTES + (uint32_t)(wn * 32 + lr) * 128u;
 
-  // One tile per CTA normally (gridDim.x == number of tiles).  With fewer CTAs than tiles -- option
-  // "gemm_reserve_sms": the bulk updates of the distributed factorisation leave a few SMs to the
-  // latency-critical kernels of the other streams -- a CTA walks the tiles bid, bid + gridDim.x, ...;
-  // the TMA ring and its barrier phases simply run on across tiles (gl = loads issued so far).
-  uint32_t gl = 0;
-  for (int bid = blockIdx.x; bid < g.n_tiles_total; bid += gridDim.x) {
-    int ti, tj;
-    tile_coords(g, bid, ti, tj);
-    const int m0 = ti * BM, n0 = tj * BN;
-    if (g.c_uplo == C_LOWER && m0 + BM - 1 < n0) continue;
-    if (g.c_uplo == C_ROWMAP && (int64_t)n0 + g.coff > g.rowlim[min(m0 + BM, g.M) - 1]) continue;
-    if (g.lo_mode == 2 && (int64_t)n0 + BN - 1 + g.lo_off < g.rowlo[m0]) continue;
-
-    int klo, khi;
-    k_range(g, ti, tj, klo, khi);
-    if (g.lo_mode == 1) {
-      int64_t lo = g.rowlo[m0] - g.lo_off;
-      if (lo > klo) klo = (int)(lo < khi ? lo / TBK * TBK : khi);
-    }
-    if (g.split_k > 1) {   // this CTA's slice of K; k_chunk is a multiple of TBK, so no box straddles a slice
-      klo = max(klo, (int)blockIdx.y * g.k_chunk);
-      khi = min(khi, ((int)blockIdx.y + 1) * g.k_chunk);
-    }
-    const int nk = (khi > klo) ? (khi - klo + TBK - 1) / TBK : 0;
-    if (g.split_k == 1) prefetch_c_tile(g, m0, n0, tid);
-
-    // ---------------- producer duty: lane 0 of warp 0 feeds the ring.  Load L of this tile is the
-    // (gl + L)-th load of the CTA and goes to slot (gl + L) % TSTAGES; it is issued in the middle of
-    // iteration L - (TSTAGES - 1), i.e. one full iteration after the slot's previous contents were
-    // consumed, so the wait on the empty barrier is normally already satisfied and never holds up
-    // DMMA issue.
-    auto issue_load = [&](int L) {
-      const uint32_t G = gl + (uint32_t)L;
-      const int sl = (int)(G % TSTAGES);
-      const uint32_t use = G / TSTAGES;
-      mbar_wait(bar_empty + 8 * sl, (use & 1u) ^ 1u);      // first use of a slot: returns at once
-      mbar_arrive_expect_tx(bar_full + 8 * sl, TSTAGE_BYTES);
-      const int k = klo + L * TBK;
-      tma_load_2d(base + sl * TSTAGE_BYTES, &tmA, k, m0, bar_full + 8 * sl);
-      tma_load_2d(base + sl * TSTAGE_BYTES + TBOX_BYTES, &tmB, k, n0, bar_full + 8 * sl);
-    };
-    if (tid == 0) {
-      for (int L = 0; L < TSTAGES - 1 && L < nk; ++L) issue_load(L);
-    }
-
-    double acc[8][4][2];
+  double fa[2][8], fb[2][4];
+  int s = 0;
+  uint32_t ph = 0;
+  if (nk > 0) {
+    mbar_wait(bar_full, 0);
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 8; ++i) fa[0][i] = lds_f64(base + a_row + i * 1024 + koffa[0]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-    double fa[2][8], fb[2][4];
-    int s = (int)(gl % TSTAGES);
-    uint32_t ph = (gl / TSTAGES) & 1u;
-    if (nk > 0) {
-      const uint32_t sb0 = base + s * TSTAGE_BYTES;
-      mbar_wait(bar_full + 8 * s, ph);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) fa[0][i] = lds_f64(sb0 + a_row + i * 1024 + koffa[0]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) fb[0][j] = lds_f64(sb0 + b_row + j * 1024 + koff[0]);
-    }
-    for (int kt = 0; kt < nk; ++kt) {
-      const uint32_t sb = base + s * TSTAGE_BYTES;
-      int s2 = s + 1;
-      uint32_t ph2 = ph;
-      if (s2 == TSTAGES) { s2 = 0; ph2 ^= 1u; }
-#pragma unroll
-      for (int kk = 0; kk < TBK / 4; ++kk) {
-        const int cur = kk & 1, nxt = cur ^ 1;
-        // fragments of the next k-step are fetched while this one's DMMAs issue
-        if (kk + 1 < TBK / 4) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) fa[nxt][i] = lds_f64(sb + a_row + i * 1024 + koffa[kk + 1]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) fb[nxt][j] = lds_f64(sb + b_row + j * 1024 + koff[kk + 1]);
-        } else if (kt + 1 < nk) {
-          const uint32_t nb = base + s2 * TSTAGE_BYTES;
-          mbar_wait(bar_full + 8 * s2, ph2);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) fa[nxt][i] = lds_f64(nb + a_row + i * 1024 + koffa[0]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) fb[nxt][j] = lds_f64(nb + b_row + j * 1024 + koff[0]);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[cur][i], fb[cur][j]);
-        if (kk == 1 && tid == 0 && kt + TSTAGES - 1 < nk) issue_load(kt + TSTAGES - 1);
-      }
-      // every fragment of stage s has been consumed by a DMMA: hand the slot back
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_empty + 8 * s);
-      s = s2;
-      ph = ph2;
-    }
-    gl += (uint32_t)nk;
-
-    if (g.split_k > 1) {                      // partial tile of slice blockIdx.y, plain store
-      GemmArgs gs = g;
-      gs.C = g.part + (int64_t)blockIdx.y * g.part_stride;
-      gs.ldc = g.ldp;
-      gs.alpha = 1.0;
-      gs.beta = 0.0;
-      gemm_epilogue(gs, acc, m0, n0, wm, wn, pr, lc);
-    } else {
-      gemm_epilogue(g, acc, m0, n0, wm, wn, pr, lc);
-    }
+    for (int j = 0; j < 4; ++j) fb[0][j] = lds_f64(base + b_row + j * 1024 + koff[0]);
   }
+  for (int kt = 0; kt < nk; ++kt) {
+    const uint32_t sb = base + s * TSTAGE_BYTES;
+    int s2 = s + 1;
+    uint32_t ph2 = ph;
+    if (s2 == TSTAGES) { s2 = 0; ph2 ^= 1u; }
+#pragma unroll
+    for (int kk = 0; kk < TBK / 4; ++kk) {
+      const int cur = kk & 1, nxt = cur ^ 1;
+      // fragments of the next k-step are fetched while this one's DMMAs issue
+      if (kk + 1 < TBK / 4) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) fa[nxt][i] = lds_f64(sb + a_row + i * 1024 + koffa[kk + 1]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) fb[nxt][j] = lds_f64(sb + b_row + j * 1024 + koff[kk + 1]);
+      } else if (kt + 1 < nk) {
+        const uint32_t nb = base + s2 * TSTAGE_BYTES;
+        mbar_wait(bar_full + 8 * s2, ph2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) fa[nxt][i] = lds_f64(nb + a_row + i * 1024 + koffa[0]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) fb[nxt][j] = lds_f64(nb + b_row + j * 1024 + koff[0]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[cur][i], fb[cur][j]);
+      if (kk == 1 && tid == 0 && kt + TSTAGES - 1 < nk) issue_load(kt + TSTAGES - 1);
+    }
+    // every fragment of stage s has been consumed by a DMMA: hand the slot back
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+    s = s2;
+    ph = ph2;
+  }
+
+  if (g.split_k > 1) {                      // partial tile of slice blockIdx.y, plain store
+    GemmArgs gs = g;
+    gs.C = g.part + (int64_t)blockIdx.y * g.part_stride;
+    gs.ldc = g.ldp;
+    gs.alpha = 1.0;
+    gs.beta = 0.0;
+    gemm_epilogue(gs, acc, m0, n0, wm, wn, pr, lc);
+    return;
+  }
+  gemm_epilogue(g, acc, m0, n0, wm, wn, pr, lc);
 }
 
 // plain-FMA check kernel with identical semantics (gps_set_option("gemm_impl", 1)); used by
@@ -706,7 +694,6 @@ int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, M
                  ((reinterpret_cast<uintptr_t>(B.p) & 15) == 0);
     if (g.batch_y > 0 && ((g.sAy | g.sBy | g.sAz | g.sBz) & 1)) vec16 = false;
     unsigned grid = (unsigned)(g.tile_prefix ? n_tiles : (int64_t)g.tiles_m * g.tiles_n);
-    g.n_tiles_total = (int)grid;
     // gemm_impl 0: TMA kernel whenever the operands qualify; 2: force the cp.async kernel
     CUtensorMap tmA, tmB;
     bool tma = vec16 && h->gemm_impl == 0 && g.K > 0 && g.batch_y == 0 && make_tensor_map(&tmA, A) &&
@@ -717,10 +704,7 @@ int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, M
         cudaFuncSetAttribute(gemm_nt_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM);
         h->attr_tma = true;
       }
-      dim3 gridp = grid2;
-      if (h->gemm_reserve_sms > 0 && (int)grid > h->sm_count - h->gemm_reserve_sms && h->sm_count > h->gemm_reserve_sms)
-        gridp.x = (unsigned)(h->sm_count - h->gemm_reserve_sms);     // persistent CTAs, a few SMs left free
-      gemm_nt_tma_kernel<<<gridp, TMA_THREADS, TMA_SMEM, h->stream>>>(g, tmA, tmB);
+      gemm_nt_tma_kernel<<<grid2, TMA_THREADS, TMA_SMEM, h->stream>>>(g, tmA, tmB);
     } else if (vec16) {
       gemm_nt_dmma_kernel<true><<<grid2, GEMM_THREADS, GEMM_SMEM, h->stream>>>(g);
     } else {

@@ -203,11 +203,6 @@ int gps_set_option(gps_handle* h, const char* name, int64_t value) {
     h->trsm_leaf = (int)value;
     return 0;
   }
-  if (!strcmp(name, "gemm_reserve_sms")) {
-    if (value < 0 || value >= h->sm_count) return gps_fail(h, -3, "gemm_reserve_sms out of range");
-    h->gemm_reserve_sms = (int)value;
-    return 0;
-  }
   if (!strcmp(name, "gemm_splitk")) {
     h->gemm_splitk = (int)value;
     return 0;

@@ -68,8 +68,6 @@ struct gps_handle {
   int profile = 0;
   int trsm_leaf = 512; // prefix solves: aligned diagonal blocks of this size (a power-of-two multiple of 128)
                        // are solved by ONE product with their explicit inverse; 128 = strips only
-  int gemm_reserve_sms = 0;  // > 0: TMA GEMM launches with more tiles than (SMs - this) run as persistent
-                             // CTAs on (SMs - this) SMs, leaving the rest to the kernels of other streams
   int gemm_splitk = 1; // split-K for long-K products with few output tiles (0 switches it off)
   // function attributes (opt-in shared memory sizes) are per device: one flag set per handle
   bool attr_gemm = false, attr_tma = false, attr_potrf = false;

@@ -572,11 +572,6 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
         _mark('factor(lookahead)')
     else:
         _FINE = False
-        # leave a few SMs to the latency-critical kernels: a bulk update whose CTAs need a whole SM
-        # each would otherwise make every small kernel of the chain wait for a tile to finish
-        reserve = int(_os_environ().get('GPSLIM_GEMM_RESERVE_SMS', '0'))
-        if reserve and hasattr(be, 'set_option'):
-            be.set_option('gemm_reserve_sms', reserve)
         main, chain, tb, gath = streams[:4]
         # the column-(k+2) update gets its own stream: on the gather stream it would hold up the next
         # panel's solve and all-gather while it waits for the bulk update of the previous panel
@@ -707,8 +702,6 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
                     ev_rest[k] = be.record(main)
         for st in (chain, tb, gath, nar):
             be.wait(main, be.record(st))
-        if reserve and hasattr(be, 'set_option'):
-            be.set_option('gemm_reserve_sms', 0)
         if TRACE is not None and hasattr(start, 'elapsed_time'):
             end = be.record(main)
             end.synchronize()

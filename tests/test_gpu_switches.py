@@ -241,48 +241,3 @@ def test_split_k_gemm_on_the_gpu():
     finally:
         h.set_option('gemm_impl', 0)
         h.set_option('gemm_splitk', 1)
-
-
-def test_persistent_gemm_with_reserved_sms():
-    """Option "gemm_reserve_sms": launches with more tiles than (SMs - r) run as persistent CTAs that
-    walk several tiles each (the TMA ring and its barrier phases run on across tiles); plain, lower,
-    read-modify-write, triangular, ragged and the row-masked compact-grid product of the distributed
-    trailing update must all give the same numbers as one CTA per tile."""
-    from gpflowSlim._backend import ops
-    from gpflowSlim._backend.dist_gpr import CudaBackend
-    from gpflowSlim._backend.lib import TRI_LOWER, TRI_UPPER, handle_for
-    from util import dev
-    rng = np.random.default_rng(1)
-    h = handle_for(dev())
-    A, B = conv(rng.standard_normal((3000, 700))), conv(rng.standard_normal((2500, 700)))
-    C0 = conv(rng.standard_normal((3000, 2500)))
-    S = conv(rng.standard_normal((2100, 2100)))
-    be = CudaBackend(dev())
-    m, n, k, coff = 2600, 2300, 256, 130
-    Ar, Br, Cr = rng.standard_normal((m, k)), rng.standard_normal((n, k)), rng.standard_normal((m, n))
-    lim = np.sort(rng.integers(0, n + coff + 40, size=m))
-    last = lim[np.minimum(np.arange(127, m + 127, 128), m - 1)]
-    cnt = np.clip((np.minimum(last, n + coff - 1) - coff) // 128 + 1, 0, (n + 127) // 128)
-    pre = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
-
-    def run():
-        out = [ops.gemm_nt(A, B), ops.gemm_nt(A, B, alpha=-0.5, beta=2.0, out=C0.clone()),
-               ops.gemm_nt(S, S, c_uplo=1), ops.gemm_nt(torch.triu(S), torch.tril(S), a_tri=TRI_UPPER, b_tri=TRI_LOWER)]
-        Cd = conv(Cr)
-        be.gemm_rowmap_(conv(Ar), conv(Br), Cd, torch.tensor(lim, device=dev()), coff, -1.0,
-                        torch.tensor(pre, device=dev()), int(pre[-1]))
-        return out + [Cd]
-    ref = run()
-    h.set_option('gemm_reserve_sms', 20)
-    try:
-        got = run()
-    finally:
-        h.set_option('gemm_reserve_sms', 0)
-    for i, (a, b) in enumerate(zip(got, ref)):
-        assert torch.equal(a, b), 'persistent vs one CTA per tile differ in product %d' % i
-    assert_close(ref[0], A @ B.t(), 1e-12, 'gemm')
-    mask = (np.arange(n)[None, :] + coff) <= lim[:, None]
-    want = Cr.copy()
-    want[mask] -= (Ar @ Br.T)[mask]
-    assert_close(ref[4], want, 1e-12, 'compact rowmap gemm')
-
