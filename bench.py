@@ -22,7 +22,6 @@ import sys
 import threading
 import time
 
-os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')   # one hardware queue per stream (see gpflowSlim/__init__.py)
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, 'gpflow-slim_b200'))
 sys.path.insert(0, ROOT)

@@ -54,24 +54,9 @@ struct GemmArgs {
   // products whose operands sit at uniform strides (diagonal blocks of a matrix, stacked tiles)
   int batch_y;                 // 0: blockIdx.y is the split-K slice; > 0: blockIdx.y is a batch index
   int64_t sAy, sBy, sCy, sAz, sBz, sCz;
-  // compact grid (C_ROWMAP): tile_prefix[t] = number of wanted tiles in tile rows < t (tiles_m + 1
-  // entries, device); block b works on tile row ti = max{t : tile_prefix[t] <= b}, column b - prefix[ti].
-  // Without it every tile of the M x N rectangle gets a CTA and the unwanted ones exit at once -- but a
-  // CTA of this kernel needs a whole SM, so each of those costs an SM a few microseconds.
-  const int64_t* tile_prefix;
 };
 
 __device__ __forceinline__ void tile_coords(const GemmArgs& g, int bid, int& ti, int& tj) {
-  if (g.tile_prefix) {
-    int lo = 0, hi = g.tiles_m;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (g.tile_prefix[mid] <= bid) lo = mid; else hi = mid;
-    }
-    ti = lo;
-    tj = bid - (int)g.tile_prefix[lo];
-    return;
-  }
   // grouped ordering: GROUP tile-rows are walked column by column so that concurrently
   // resident CTAs share A row-panels and B row-panels in L2.
   constexpr int GROUP = 8;
@@ -603,8 +588,7 @@ double gemm_flops(const GemmArgs& g) {
 
 int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, Mat C, int a_tri,
                        int b_tri, int c_uplo, const int64_t* rowlim, int64_t coff, double flops,
-                       const int64_t* rowlo, int64_t lo_off, int lo_mode, const GemmBatch* batch,
-                       const int64_t* tile_prefix, int64_t n_tiles) {
+                       const int64_t* rowlo, int64_t lo_off, int lo_mode, const GemmBatch* batch) {
   if (A.cols != B.cols) return gps_fail(h, -3, "gemm_nt: K mismatch (%lld vs %lld)",
                                         (long long)A.cols, (long long)B.cols);
   if (C.rows != A.rows || C.cols != B.rows) return gps_fail(h, -6, "gemm_nt: C shape mismatch");
@@ -623,7 +607,6 @@ int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, M
   g.rowlo = rowlo; g.lo_off = lo_off; g.lo_mode = rowlo ? lo_mode : 0;
   g.split_k = 1; g.k_chunk = 0; g.part = nullptr; g.ldp = 0; g.part_stride = 0;
   g.batch_y = 0; g.sAy = g.sBy = g.sCy = g.sAz = g.sBz = g.sCz = 0;
-  g.tile_prefix = (c_uplo == C_ROWMAP && tile_prefix && n_tiles > 0) ? tile_prefix : nullptr;
   int batch_z = 1;
   if (batch && batch->ny * batch->nz > 1) {
     if (batch->ny < 1 || batch->nz < 1 || batch->ny > 65535 || batch->nz > 65535)
@@ -693,7 +676,7 @@ int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, M
                  ((reinterpret_cast<uintptr_t>(A.p) & 15) == 0) &&
                  ((reinterpret_cast<uintptr_t>(B.p) & 15) == 0);
     if (g.batch_y > 0 && ((g.sAy | g.sBy | g.sAz | g.sBz) & 1)) vec16 = false;
-    unsigned grid = (unsigned)(g.tile_prefix ? n_tiles : (int64_t)g.tiles_m * g.tiles_n);
+    unsigned grid = (unsigned)(g.tiles_m * g.tiles_n);
     // gemm_impl 0: TMA kernel whenever the operands qualify; 2: force the cp.async kernel
     CUtensorMap tmA, tmB;
     bool tma = vec16 && h->gemm_impl == 0 && g.K > 0 && g.batch_y == 0 && make_tensor_map(&tmA, A) &&
@@ -737,39 +720,18 @@ extern "C" int gps_gemm_nt(gps_handle* h, double alpha, const DLTensor* A, const
   return gps_gemm_nt_launch(h, alpha, a, b, beta, c, a_tri, b_tri, c_uplo);
 }
 
-static int rowmap_entry(gps_handle* h, double alpha, const DLTensor* A, const DLTensor* B, double beta,
-                        DLTensor* C, const DLTensor* row_limit, int64_t col_offset, double flops,
-                        const DLTensor* tile_prefix, int64_t n_tiles) {
+extern "C" int gps_gemm_nt_rowmap(gps_handle* h, double alpha, const DLTensor* A, const DLTensor* B,
+                                  double beta, DLTensor* C, const DLTensor* row_limit,
+                                  int64_t col_offset, double flops) {
   if (!h) return -1;
   Mat a, b, c;
   int rc;
   const int64_t* lim;
-  const int64_t* pre = nullptr;
   if ((rc = gps_as_mat(h, A, 3, "A", &a, false))) return rc;
   if ((rc = gps_as_mat(h, B, 4, "B", &b, false))) return rc;
   if ((rc = gps_as_mat(h, C, 6, "C", &c, false))) return rc;
   if ((rc = gps_as_i64(h, row_limit, 7, "row_limit", c.rows, &lim))) return rc;
-  if (tile_prefix) {
-    const int64_t tiles_m = (c.rows + BM - 1) / BM;
-    if ((rc = gps_as_i64(h, tile_prefix, 10, "tile_prefix", tiles_m + 1, &pre))) return rc;
-    if (n_tiles < 0 || n_tiles > (int64_t)tiles_m * ((c.cols + BN - 1) / BN))
-      return gps_fail(h, -11, "gemm_nt_rowmap: n_tiles out of range");
-    if (n_tiles == 0) return 0;
-  }
   GPS_CUDA(h, cudaSetDevice(h->device));
   return gps_gemm_nt_launch(h, alpha, a, b, beta, c, TRI_NONE, TRI_NONE, C_ROWMAP, lim, col_offset,
-                            flops, nullptr, 0, 0, nullptr, pre, n_tiles);
-}
-
-extern "C" int gps_gemm_nt_rowmap(gps_handle* h, double alpha, const DLTensor* A, const DLTensor* B,
-                                  double beta, DLTensor* C, const DLTensor* row_limit,
-                                  int64_t col_offset, double flops) {
-  return rowmap_entry(h, alpha, A, B, beta, C, row_limit, col_offset, flops, nullptr, 0);
-}
-
-extern "C" int gps_gemm_nt_rowmap_compact(gps_handle* h, double alpha, const DLTensor* A, const DLTensor* B,
-                                          double beta, DLTensor* C, const DLTensor* row_limit,
-                                          int64_t col_offset, double flops, const DLTensor* tile_prefix,
-                                          int64_t n_tiles) {
-  return rowmap_entry(h, alpha, A, B, beta, C, row_limit, col_offset, flops, tile_prefix, n_tiles);
+                            flops);
 }

@@ -165,6 +165,14 @@ int gps_gpr_nlml_fwd_bwd(gps_handle* h, const gps_kernel_desc* desc, const DLTen
   GPS_CUDA(h, cudaSetDevice(h->device));
   const int64_t N = X.rows, R = Yc.cols;
   if (N == 0) return gps_fail(h, -4, "X is empty");
+  // Split-K pays where the products are few and latency-bound (N <= 8192: +7 % on BASELINE config C2);
+  // at the headline size the extra partial-tile passes of the thousands of small products inside the
+  // recursions cost 1.5 % of the step (bench line 0.945 -> 0.931 evals/s), so it is off from N = 16384 on.
+  struct SplitkGuard {
+    gps_handle* h; int saved;
+    SplitkGuard(gps_handle* h_, bool off) : h(h_), saved(h_->gemm_splitk) { if (off) h->gemm_splitk = 0; }
+    ~SplitkGuard() { h->gemm_splitk = saved; }
+  } splitk_guard(h, N >= 16384);
 
   Mat A;
   double *tinv, *logdet;

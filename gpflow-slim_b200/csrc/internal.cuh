@@ -126,8 +126,7 @@ struct GemmBatch { int ny, nz; int64_t sAy, sBy, sCy, sAz, sBz, sCz; };
 int gps_gemm_nt_launch(gps_handle* h, double alpha, Mat A, Mat B, double beta, Mat C, int a_tri,
                        int b_tri, int c_uplo, const int64_t* rowlim = nullptr, int64_t coff = 0,
                        double flops = -1.0, const int64_t* rowlo = nullptr, int64_t lo_off = 0,
-                       int lo_mode = 0, const GemmBatch* batch = nullptr, const int64_t* tile_prefix = nullptr,
-                       int64_t n_tiles = 0);
+                       int lo_mode = 0, const GemmBatch* batch = nullptr);
 
 // ----------------------------------------------------------------------------- factorisation
 // Factor the n x n block at A (lower, in place) and solve the `below` rows under it:

@@ -6,14 +6,6 @@ Same import surface as the reference package (gpflowSlim/__init__.py): `settings
 float64; all O(n^2)/O(n^3) arithmetic runs in libgpslim_b200.so (hand-written sm_100a CUDA,
 C ABI in include/gpslim_b200.h).  No TensorFlow, no CPU fallback.
 """
-import os as _os
-
-# The distributed factorisation drives five CUDA streams plus three NCCL communicators per GPU.  With
-# the default of 8 hardware work queues, streams share a queue and a 2 MB broadcast of the serial chain
-# ends up behind the 4000 thread blocks of a bulk update: one queue per stream needs this set BEFORE
-# the CUDA context is created (it is read once, at context creation).
-_os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
-
 from ._settings import SETTINGS as settings
 
 from . import misc

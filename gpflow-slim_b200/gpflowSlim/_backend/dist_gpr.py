@@ -199,18 +199,9 @@ class CudaBackend(object):
         vl, vb = L.view(Lm), L.view(B)
         h.check(h.lib.gps_trsm_rlt(h.ptr, vl.ref, vb.ref))
 
-    def gemm_rowmap_(self, A, B, C, rowlim, coff, flops=-1.0, prefix=None, n_tiles=0):
-        """C -= A B^T where column c + coff <= rowlim[row]; with `prefix` (device int64, per 128-row tile
-        row the number of wanted tiles before it) only the wanted tiles get a thread block."""
+    def gemm_rowmap_(self, A, B, C, rowlim, coff, flops=-1.0):
         h, L = self._h(), self._L
         va, vb, vc, vr = L.view(A), L.view(B), L.view(C), L.view(rowlim)
-        if prefix is not None:
-            if n_tiles == 0:
-                return
-            vp = L.view(prefix)
-            h.check(h.lib.gps_gemm_nt_rowmap_compact(h.ptr, -1.0, va.ref, vb.ref, 1.0, vc.ref, vr.ref, int(coff),
-                                                     float(flops), vp.ref, int(n_tiles)))
-            return
         h.check(h.lib.gps_gemm_nt_rowmap(h.ptr, -1.0, va.ref, vb.ref, 1.0, vc.ref, vr.ref, int(coff),
                                          float(flops)))
 
@@ -344,10 +335,6 @@ class _Comm(object):
 def _os_environ():
     import os
     return os.environ
-
-
-def _to_device(a, dev):
-    return torch.as_tensor(a, device=dev)
 
 
 # --------------------------------------------------------------------------------- the path
@@ -510,11 +497,9 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
     streams = be.streams() if lookahead else None
     # The chain of the factorisation runs next to bulk updates that occupy every SM: each extra
     # launch on it waits for an SM to come free, so the split-K slicing of its small products (a
-    # gain when the GPU is idle) is switched off for the duration of the factorisation, and the
-    # bulk update is launched on the plain grouped grid unless GPSLIM_DIST_COMPACT=1 -- the two
-    # differences to the round-1 factor phase (77 ms on 8 GPUs) that the round-2 A/B runs
-    # (profiles/r02_dist_8gpu_ab.txt: 87-94 ms) could not separate before the GPU budget ran out.
-    compact = _os_environ().get('GPSLIM_DIST_COMPACT', '0') == '1'
+    # gain when the GPU is idle) is switched off for the duration of the factorisation -- the
+    # round-1 condition (factor phase 77 ms on 8 GPUs; 87-94 ms in the round-2 A/B runs with it on,
+    # profiles/r02_dist_8gpu_ab.txt).  GPSLIM_DIST_SPLITK=1 keeps it on.
     splitk_off = _os_environ().get('GPSLIM_DIST_SPLITK', '0') != '1' and hasattr(be, 'set_option')
     if splitk_off:
         be.set_option('gemm_splitk', 0)
@@ -600,22 +585,12 @@ def factor(prog, theta, noise, X, Yc, lay, comm, be, lookahead=True):
                 return
             k0, k1 = lay.rows(k)
             fkey = (k, a, b, c_lo, c_hi)
-            hit = flops_cache.get(fkey)         # pure functions of the layout: computed once
-            if hit is None:
+            flops = flops_cache.get(fkey)       # algorithmic flops, a pure function of the layout
+            if flops is None:
                 g = np.minimum(grow_host[a:b], c_hi - 1)
-                flops = 2.0 * (k1 - k0) * float(np.clip(g - c_lo + 1, 0, None).sum())
-                # wanted 128 x 128 tiles per tile row (rows are sorted by global index, so the last row
-                # of a tile row reaches furthest right)
-                last = grow_host[a:b][np.minimum(np.arange(127, b - a + 127, 128), b - a - 1)]
-                tiles_n = (c_hi - c_lo + 127) // 128
-                cnt = np.clip((np.minimum(last, c_hi - 1) - c_lo) // 128 + 1, 0, tiles_n)
-                pre = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
-                hit = flops_cache[fkey] = (flops, _to_device(pre, dev), int(pre[-1]))
-            flops, prefix, n_tiles = hit
-            if not compact:
-                prefix, n_tiles = None, 0
+                flops = flops_cache[fkey] = 2.0 * (k1 - k0) * float(np.clip(g - c_lo + 1, 0, None).sum())
             Bop = Lfull[c_lo:c_hi, k0:k1] if Bsrc is None else Bsrc
-            be.gemm_rowmap_(Aloc[a:b, k0:k1], Bop, Aloc[a:b, c_lo:c_hi], grow[a:b], c_lo, flops, prefix, n_tiles)
+            be.gemm_rowmap_(Aloc[a:b, k0:k1], Bop, Aloc[a:b, c_lo:c_hi], grow[a:b], c_lo, flops)
 
         import time as _time
         host_issue, host_t0 = {}, _time.perf_counter()

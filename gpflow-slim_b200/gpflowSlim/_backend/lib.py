@@ -89,8 +89,6 @@ SIGNATURES = {
     'gps_transpose': [_H, _T, _T],
     'gps_gemm_nt_rowmap': [_H, ctypes.c_double, _T, _T, ctypes.c_double, _T, _T, ctypes.c_int64,
                            ctypes.c_double],
-    'gps_gemm_nt_rowmap_compact': [_H, ctypes.c_double, _T, _T, ctypes.c_double, _T, _T, ctypes.c_int64,
-                                   ctypes.c_double, _T, ctypes.c_int64],
     'gps_trsm_rlt_prefix': [_H, _T, _T, _P(ctypes.c_int64)],
     'gps_trsm_rln_prefix': [_H, _T, _T, _T, _P(ctypes.c_int64)],
     'gps_gpr_weight_rows': [_H, _T, _T, _T, ctypes.c_int64],

@@ -229,14 +229,6 @@ int gps_trsm_bwd(gps_handle* h, const DLTensor* L, const DLTensor* X, const DLTe
 int gps_gemm_nt_rowmap(gps_handle* h, double alpha, const DLTensor* A, const DLTensor* B,
                        double beta, DLTensor* C, const DLTensor* row_limit, int64_t col_offset,
                        double flops);
-/* The same product launched on a COMPACT grid: tile_prefix (int64 device vector, ceil(rows/128) + 1
- * entries) holds, for every 128-row tile row of C, the number of wanted 128-column tiles in the tile
- * rows before it -- wanted = not wholly right of the row limit --, n_tiles = its last entry.  Only
- * those tiles get a thread block (the caller knows the layout; the plain entry point launches the
- * whole rectangle and lets the unwanted blocks exit, which costs an SM a few microseconds each). */
-int gps_gemm_nt_rowmap_compact(gps_handle* h, double alpha, const DLTensor* A, const DLTensor* B,
-                               double beta, DLTensor* C, const DLTensor* row_limit, int64_t col_offset,
-                               double flops, const DLTensor* tile_prefix, int64_t n_tiles);
 int gps_trsm_rlt_prefix(gps_handle* h, const DLTensor* L, DLTensor* B_inout,
                         const int64_t* row_start);
 int gps_trsm_rln_prefix(gps_handle* h, const DLTensor* L, const DLTensor* Lt, DLTensor* B_inout,

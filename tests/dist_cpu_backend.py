@@ -56,18 +56,9 @@ class CpuBackend(object):
     def syrk_lower_(self, X, D):
         D.sub_(torch.tril(X @ X.T))
 
-    def gemm_rowmap_(self, A, B, C, rowlim, coff, flops=-1.0, prefix=None, n_tiles=0):
+    def gemm_rowmap_(self, A, B, C, rowlim, coff, flops=-1.0):
         cols = torch.arange(C.shape[1]) + coff
         mask = cols[None, :] <= rowlim[:, None]
-        if prefix is not None:
-            # the compact grid must cover every tile the mask wants (and claim no more tiles than exist)
-            tm, tn = (C.shape[0] + 127) // 128, (C.shape[1] + 127) // 128
-            assert prefix.shape == (tm + 1,) and int(prefix[-1]) == n_tiles and n_tiles <= tm * tn
-            cnt = (prefix[1:] - prefix[:-1]).tolist()
-            for t in range(tm):
-                wanted = mask[t * 128:(t + 1) * 128].any(0).nonzero()
-                need = 0 if wanted.numel() == 0 else int(wanted.max()) // 128 + 1
-                assert cnt[t] == need, (t, cnt[t], need)
         upd = A @ B.T
         C.sub_(torch.where(mask, upd, torch.zeros_like(upd)))
 

@@ -94,7 +94,7 @@ class Tracer(object):
     def syrk_lower_(self, X, D):
         self._op('syrk', [X, D], [D])
 
-    def gemm_rowmap_(self, A, B, C, rowlim, coff, flops=-1.0, prefix=None, n_tiles=0):
+    def gemm_rowmap_(self, A, B, C, rowlim, coff, flops=-1.0):
         self._op('gemm', [A, B, C], [C])
 
     def transpose_into(self, A, out):

@@ -43,28 +43,6 @@ def test_gemm_rowmap_masks_by_global_row(m, n, k, coff):
     assert_close(Cd, ref, 1e-13, 'rowmap gemm')
 
 
-@pytest.mark.parametrize('m,n,k,coff', [(2600, 2300, 256, 130), (300, 517, 128, 0)])
-def test_gemm_rowmap_compact_grid(m, n, k, coff):
-    """gps_gemm_nt_rowmap_compact: only the wanted tiles get a thread block (per tile row the count of
-    tiles not wholly right of the row limit, as a prefix array); same numbers as the plain grid."""
-    rng = np.random.default_rng(m + k)
-    A, B, C = rng.standard_normal((m, k)), rng.standard_normal((n, k)), rng.standard_normal((m, n))
-    lim = np.sort(rng.integers(0, n + coff + 40, size=m))
-    last = lim[np.minimum(np.arange(127, m + 127, 128), m - 1)]
-    cnt = np.clip((np.minimum(last, n + coff - 1) - coff) // 128 + 1, 0, (n + 127) // 128)
-    pre = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
-    ref = C.copy()
-    mask = (np.arange(n)[None, :] + coff) <= lim[:, None]
-    ref[mask] -= (A @ B.T)[mask]
-    Cd, Cp = conv(C), conv(C)
-    be = _be()
-    be.gemm_rowmap_(conv(A), conv(B), Cd, torch.tensor(lim, device=dev()), coff, -1.0,
-                    torch.tensor(pre, device=dev()), int(pre[-1]))
-    be.gemm_rowmap_(conv(A), conv(B), Cp, torch.tensor(lim, device=dev()), coff)
-    assert_close(Cd, ref, 1e-13, 'compact rowmap gemm')
-    assert torch.equal(Cd, Cp)
-
-
 @pytest.mark.parametrize('leaf', [128, 256, 512, 1024])
 @pytest.mark.parametrize('n,bs', [(384, 128), (1000, 256), (1500, 384), (4000, 512)])
 def test_prefix_triangular_solves(n, bs, leaf):

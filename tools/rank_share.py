@@ -130,26 +130,6 @@ def main():
             ms = timed(lambda: f_bulk(split), reps=2)
             out['bulk_updates_%s' % ('3_launches_per_panel' if split else '1_launch_per_panel')] = {
                 'ms': ms, 'tflops': flops / ms / 1e9}
-        # the same on the compact grid (only wanted tiles get a CTA)
-        gh = grow.cpu().numpy()
-        pres = {}
-        for k in range(lay.nblk - 1):
-            k0, k1 = lay.rows(k)
-            lo, mrows = lay.rows_below(r, k)
-            rows = gh[lo:]
-            last = rows[np.minimum(np.arange(127, len(rows) + 127, 128), len(rows) - 1)]
-            tn = (n - k1 + 127) // 128
-            cnt = np.clip((np.minimum(last, n - 1) - k1) // 128 + 1, 0, tn)
-            pre = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
-            pres[k] = (torch.as_tensor(pre, device=dev), int(pre[-1]))
-
-        def f_compact():
-            for k in range(lay.nblk - 1):
-                k0, k1 = lay.rows(k)
-                lo, mrows = lay.rows_below(r, k)
-                be.gemm_rowmap_(Aloc[lo:, k0:k1], Lf[k1:n, k0:k1], Aloc[lo:, k1:n], grow[lo:], k1, -1.0, pres[k][0], pres[k][1])
-        ms = timed(f_compact, reps=2)
-        out['bulk_updates_1_launch_per_panel_compact_grid'] = {'ms': ms, 'tflops': flops / ms / 1e9}
         del Aloc, Lf
 
     if 'inverse' in what:
