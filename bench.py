@@ -426,7 +426,7 @@ def main():
         step()
     barrier()
     # GEMM launches are bracketed by CUDA events on their own stream (library option "profile").
-    # One GPU: inside the timed region.  Several GPUs: the distributed path overlaps four streams
+    # One GPU: inside the timed region.  Several GPUs: the distributed path overlaps several streams
     # and the extra event records perturb that overlap, so the timed region runs clean and the
     # roofline figures come from a separate profiled pass right after it.
     profile_in_region = (world == 1) and not args.profile_pass
@@ -523,7 +523,7 @@ def main():
         nprob = world if mode == 'independent' else 1     # problems evaluated per step, whole job
         par = {'fused': 'single GPU, fused path', 'independent': 'independent problem per GPU',
                'dist': ('one problem over %d GPU(s): block-row (block %d) distributed Cholesky + inverse; schedule %s '
-                        '(v2: four-stream look-ahead pipeline; v1: three streams); NCCL broadcasts (diagonal / top '
+                        '(v1: three-stream look-ahead; v2: five-stream pipeline); NCCL broadcasts (diagonal / top '
                         'block) + all-gather per panel on three communicators' % (world, args.block, args.schedule))}[mode]
         step_tf = nprob * float(n) ** 3 / (ms * 1e-3) / 1e12
         line = {
@@ -547,7 +547,7 @@ def main():
                          'peak_source': peak['source'], 'peak_burst': peak['burst'],
                          'gemm_share_of_step': gemm_ms / (prof_ms * prof_steps) if prof_ms > 0 else None,
                          'scope': ('rank 0, separate profiled pass of %d step(s) after the timed region%s' % (
-                             prof_steps, ' (four overlapping streams: per-launch event time includes queueing '
+                             prof_steps, ' (overlapping streams: per-launch event time includes queueing '
                              'behind the other streams)' if world > 1 else ''))
                          if not profile_in_region else 'the GPU, events inside the timed region',
                          'step_tflops_vs_n3': step_tf,

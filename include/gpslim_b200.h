@@ -113,12 +113,14 @@ int gps_version(void);
  *                      1 = plain-FMA check kernel; 2 = always the cp.async DMMA kernel;
  *          "gram_impl" 0 = register-tiled Gram kernels for a single stationary covariance where
  *                          they apply (default), 1 = the generic interpreter kernels only,
- *                          2 = EXPERIMENTAL interpreter backward with its accumulators in shared
- *                          memory (written blind at the end of round 1, not yet run on a GPU;
- *                          tests/test_gpu_experimental.py holds it to the default path);
- *          "gemm_splitk" 1 = EXPERIMENTAL split-K: products with K >= 1024 and fewer output tiles
- *                          than half the SMs are cut into up to 8 K slices (cp.async kernel + a
- *                          reduction pass); 0 (default) = off.  Not yet run on a GPU;
+ *                          2 = interpreter kernels with their slot / accumulator arrays in shared
+ *                          memory (correct, 7 % faster on the NKN config, not the default;
+ *                          tests/test_gpu_switches.py holds it to the default path);
+ *          "gemm_splitk" 1 (default) = split-K: products with fewer output tiles than SMs are cut
+ *                          into up to 32 K slices (both tensor-core kernels; partial tiles in a
+ *                          per-stream scratch + one reduction pass); 0 = off;
+ *          "trsm_leaf" 128..4096 (power of two, default 512): the prefix solves handle aligned
+ *                          diagonal blocks of this size by one product with their explicit inverse;
  *          "leaf_impl" 0 = blocked DMMA 128x128 Cholesky leaf (default), 1 = scalar check kernel;
  *          "profile"   1 = bracket every GEMM-class launch with CUDA events. */
 int gps_set_option(gps_handle* h, const char* name, int64_t value);

@@ -1,7 +1,7 @@
 """Launched under torchrun with >= 2 ranks: distributed GPR objective + gradient (composed
 Matern + Linear kernel, and the NKN topology of BASELINE config C3), distributed predict_f, the
 sharded SVGP step and the sharded SGPR objective, each against the single-GPU values computed on
-the same rank.  The GPR check is repeated (--repeat) with NaN-poisoned buffers: the four-stream
+the same rank.  The GPR check is repeated (--repeat) with NaN-poisoned buffers: the look-ahead
 schedule must give the same bits every time.  Prints DIST_CHECK_OK."""
 import argparse
 import os

@@ -9,7 +9,7 @@
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/r02_gpu_tests.log 2>&1
 tail -3 gpurun_out/r02_gpu_tests.log
-GPSLIM_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -q -s -p no:cacheprovider \
+python -m pytest tests/test_gpu_switches.py -q -s -p no:cacheprovider \
     > gpurun_out/r02_experimental.log 2>&1
 tail -8 gpurun_out/r02_experimental.log
 python tools/bench_secondary.py --what c3 > gpurun_out/r02_c3_gram_impl0.jsonl 2>&1
