@@ -1118,6 +1118,364 @@ __global__ void reduce_dx_kernel(const double* __restrict__ part, int njc, int64
   dX[i * lddx + (idx - i * xcols)] = scale * s;
 }
 
+// --------------------------------------------------------------------------- NKN fast path
+// Neural-kernel-network programs of the shape  Linear -> Product(2) -> Linear -> Product(2) -> Linear(->1)
+// over <= 7 primitives (the reference's NKN wrapper, neural_kernel_network.py / wrapper.py:100-104, BASELINE
+// config C3).  The interpreter kernels above keep slot values, slot adjoints and ~100 theta-gradient
+// accumulators per THREAD in runtime-indexed arrays (local memory): ~120 read-modify-writes per matrix
+// element.  Here a warp works on 8 matrix elements at a time ("octet"), 4 lanes per element:
+//   * lane (lr, lc) = (lane >> 2, lane & 3) belongs to element lr and evaluates primitives lc and 4 + lc;
+//   * the Linear layers are 8x8x4 FP64 tensor-core products (DMMA): rows = the 8 elements, columns =
+//     layer outputs, reduction = layer inputs; lane (lr, lc) receives outputs 2 lc, 2 lc + 1 of element
+//     lr, i.e. exactly one pair of the following Product layer;
+//   * backward: adjoint mat-vecs with the transposed weights are DMMAs too, and the WEIGHT gradients are
+//     accumulated as 8x8 DMMA tiles  dW[o][i] += sum_e dout[e][o] in[e][i]  (reduction over the 8 elements
+//     of the octet, both operands staged through 1 KB of shared memory per warp; column `n_in` of `in` is
+//     the constant 1, which makes that column of the tile the bias gradient);
+//   * primitive parameter gradients stay in <= 18 registers per lane (two primitives x (1 + 8)).
+// Everything is register resident; arithmetic per element is the interpreter's in another summation order.
+constexpr int NKN_MAXD = 8;      // active dimensions per primitive handled in registers
+
+struct NknPlan {
+  int P, n1, n2, i2, i3;         // primitives; outputs of Linear 1 / 2; inputs of Linear 2 / 3 (n1 / 2, n2 / 2)
+  int w1, b1, w2, b2, w3, b3;    // theta offsets of weights and biases
+};
+
+bool nkn_match(const gps_handle* h, const Plan& pl, NknPlan* nk) {
+  if (h->gram_impl != 0 || pl.n_ops != 5 || pl.n_prims > 7) return false;
+  const OpC* o = pl.ops;
+  if (o[0].op != GPS_OP_LINEAR || o[1].op != GPS_OP_PRODUCT || o[2].op != GPS_OP_LINEAR ||
+      o[3].op != GPS_OP_PRODUCT || o[4].op != GPS_OP_LINEAR)
+    return false;
+  const int P = pl.n_prims;
+  if (o[0].a != 0 || o[0].b != P || o[0].n < 2 || o[0].n > 8 || (o[0].n & 1)) return false;
+  if (o[1].a != o[0].dst || o[1].b != 2 || o[1].n * 2 != o[0].n) return false;
+  if (o[2].a != o[1].dst || o[2].b != o[1].n || o[2].n < 2 || o[2].n > 8 || (o[2].n & 1)) return false;
+  if (o[3].a != o[2].dst || o[3].b != 2 || o[3].n * 2 != o[2].n) return false;
+  if (o[4].a != o[3].dst || o[4].b != o[3].n || o[4].n != 1 || pl.out_slot != o[4].dst) return false;
+  for (int p = 0; p < P; ++p)
+    if (pl.prims[p].ndims > NKN_MAXD) return false;
+  nk->P = P; nk->n1 = o[0].n; nk->i2 = o[1].n; nk->n2 = o[2].n; nk->i3 = o[3].n;
+  nk->w1 = o[0].c; nk->b1 = o[0].d; nk->w2 = o[2].c; nk->b2 = o[2].d; nk->w3 = o[4].c; nk->b3 = o[4].d;
+  return true;
+}
+
+// per-lane DMMA operand fragments of the three Linear layers, zero padded to 8 x 8
+struct NknFrag {
+  double w1f[2], w2f, w3;        // B fragments (weights[out = lr][in = lc + 4 s]) of Linear 1 (two k-steps), Linear 2;
+                                 // Linear 3 weight of input lc
+  double c1[2], c2[2], b3;       // biases of outputs 2 lc, 2 lc + 1 of Linear 1 / 2; bias of Linear 3
+  double w1t[2], w2t[2];         // B fragments of the transposes (weights[out = lc + 4 s][in = lr])
+};
+
+__device__ __forceinline__ void nkn_load_frag(const NknPlan& nk, const double* __restrict__ th, int lr, int lc,
+                                              NknFrag& f) {
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int c = lc + 4 * s;
+    f.w1f[s] = (lr < nk.n1 && c < nk.P) ? th[nk.w1 + lr * nk.P + c] : 0.0;
+    f.w1t[s] = (c < nk.n1 && lr < nk.P) ? th[nk.w1 + c * nk.P + lr] : 0.0;
+    f.w2t[s] = (c < nk.n2 && lr < nk.i2) ? th[nk.w2 + c * nk.i2 + lr] : 0.0;
+    const int o = 2 * lc + s;
+    f.c1[s] = o < nk.n1 ? th[nk.b1 + o] : 0.0;
+    f.c2[s] = o < nk.n2 ? th[nk.b2 + o] : 0.0;
+  }
+  f.w2f = (lr < nk.n2 && lc < nk.i2) ? th[nk.w2 + lr * nk.i2 + lc] : 0.0;
+  f.w3 = lc < nk.i3 ? th[nk.w3 + lc] : 0.0;
+  f.b3 = th[nk.b3];
+}
+
+// forward pass of one octet.  k0 / k1: this lane's two primitive values of its element (0 where the lane
+// has no primitive).  Returns the network output of element lr (on all four lanes of the quad) and leaves
+// the layer outputs this lane owns in o1[2] (Linear 1), o2[2] (Linear 2), h1, h2 (the Product layers).
+__device__ __forceinline__ double nkn_forward(const NknFrag& f, double k0, double k1, double* o1, double* o2,
+                                              double& h1, double& h2) {
+  o1[0] = f.c1[0]; o1[1] = f.c1[1];
+  dmma884(o1[0], o1[1], k0, f.w1f[0]);
+  dmma884(o1[0], o1[1], k1, f.w1f[1]);
+  h1 = o1[0] * o1[1];
+  o2[0] = f.c2[0]; o2[1] = f.c2[1];
+  dmma884(o2[0], o2[1], h1, f.w2f);
+  h2 = o2[0] * o2[1];
+  double part = f.w3 * h2;
+  part += __shfl_xor_sync(0xffffffffu, part, 1);
+  part += __shfl_xor_sync(0xffffffffu, part, 2);
+  return part + f.b3;
+}
+
+__global__ void __launch_bounds__(GRAM_THREADS)
+gram_fwd_nkn_kernel(const Plan pl, const NknPlan nk, const double* __restrict__ theta,
+                    const double* __restrict__ FL, const double* __restrict__ FR, int64_t N, int64_t M,
+                    double diag_add, int sym, int uplo, double* __restrict__ K, int64_t ldk) {
+  extern __shared__ double sm[];
+  double* th = sm;
+  double* sl = th + pl.n_theta;
+  double* sr = sl + TILE * pl.S;
+  const int64_t i0 = (int64_t)blockIdx.y * TILE, j0 = (int64_t)blockIdx.x * TILE;
+  if (sym && uplo && j0 > i0 + TILE - 1) return;
+  const int tid = threadIdx.x;
+  for (int t = tid; t < pl.n_theta; t += GRAM_THREADS) th[t] = theta[t];
+  for (int idx = tid; idx < TILE * pl.FT; idx += GRAM_THREADS) {
+    int r = idx / pl.FT, c = idx - r * pl.FT;
+    sl[r * pl.S + c] = (i0 + r < N) ? FL[(i0 + r) * pl.FT + c] : 0.0;
+    sr[r * pl.S + c] = (j0 + r < M) ? FR[(j0 + r) * pl.FT + c] : 0.0;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
+  NknFrag f;
+  nkn_load_frag(nk, th, lr, lc, f);
+  const bool has0 = lc < nk.P, has1 = 4 + lc < nk.P;
+  const PrimC P0 = pl.prims[has0 ? lc : 0], P1 = pl.prims[has1 ? 4 + lc : 0];
+  for (int q = 0; q < TILE; ++q) {
+    const int il = warp * 8 + (q >> 3), jb = (q & 7) * 8, jl = jb + lr;
+    const int64_t gi = i0 + il, gj = j0 + jl;
+    if (gi >= N || j0 + jb >= M) continue;                        // warp uniform
+    if (sym && uplo && j0 + jb > gi) continue;
+    const double* fi = sl + il * pl.S;
+    const double* fj = sr + jl * pl.S;
+    double k0 = 0.0, k1 = 0.0;
+    if (has0) k0 = prim_eval(P0, th, fi + P0.feat_off, fj + P0.feat_off).k;
+    if (has1) k1 = prim_eval(P1, th, fi + P1.feat_off, fj + P1.feat_off).k;
+    double o1[2], o2[2], h1, h2;
+    double out = nkn_forward(f, k0, k1, o1, o2, h1, h2);
+    if (lc == 0 && gj < M && !(sym && uplo && gj > gi)) {
+      if (sym && gi == gj) out += diag_add;
+      K[gi * ldk + gj] = out;
+    }
+  }
+}
+
+// parameter gradient of one primitive at one element: acc[q] += g * d k / d theta[theta_off + q]
+__device__ __forceinline__ void nkn_prim_grad(const PrimC& P, const double* __restrict__ tinv,
+                                              const double* __restrict__ fi, const double* __restrict__ fj,
+                                              const PrimEval& ev, double g, double* acc) {
+  const double* ti = tinv + P.theta_off;
+  const int nd = P.ndims;
+  if (is_stationary(P.type)) {
+    acc[0] += g * ev.k * ti[0];
+    const double G = g * ev.dk;
+    if (P.ard) {
+#pragma unroll
+      for (int k = 0; k < NKN_MAXD; ++k)
+        if (k < nd) {
+          double df = fi[k] - fj[k];
+          acc[1 + k] += G * (-2.0) * df * df * ti[1 + k];
+        }
+    } else {
+      acc[1] += G * (-2.0) * ev.d2 * ti[1];
+    }
+  } else if (P.type == GPS_LINEAR) {
+    if (P.ard) {
+#pragma unroll
+      for (int k = 0; k < NKN_MAXD; ++k)
+        if (k < nd) acc[k] += g * fi[k] * fj[k];
+    } else {
+      double s = 0.0;
+      for (int k = 0; k < nd; ++k) s += fi[k] * fj[k];
+      acc[0] += g * s;
+    }
+  } else {
+    const double kk = ev.k, r = ev.dk, ils = ti[1], iper = ti[2];
+    acc[0] += g * kk * ti[0];
+    acc[1] += g * kk * r * ils;
+    double dcs = 0.0;
+    for (int k = 0; k < nd; ++k) {
+      double sind = fi[nd + k] * fj[k] - fi[k] * fj[nd + k];      // sin(a_i - a_j)
+      dcs += sind * (fi[2 * nd + k] - fj[2 * nd + k]);
+    }
+    acc[2] += g * kk * dcs * iper * (0.25 * ils * ils);
+  }
+}
+
+__device__ __forceinline__ int nkn_prim_nparams(const PrimC& P) {
+  return is_stationary(P.type) ? 1 + (P.ard ? P.ndims : 1) : P.type == GPS_LINEAR ? (P.ard ? P.ndims : 1) : 3;
+}
+
+__global__ void __launch_bounds__(GRAM_THREADS, 2)
+gram_bwd_nkn_kernel(const Plan pl, const NknPlan nk, const double* __restrict__ theta,
+                    const double* __restrict__ FL, const double* __restrict__ FR, int64_t N, int64_t M,
+                    const BwdArgs w, double* __restrict__ part_theta) {
+  extern __shared__ double sm[];
+  const int nacc = pl.n_theta + 1;
+  double* th = sm;                                 // [n_theta]
+  double* tinv = th + pl.n_theta;                  // [n_theta]
+  double* sl = tinv + pl.n_theta;                  // [TILE][S]
+  double* sr = sl + TILE * pl.S;                   // [TILE][S]
+  double* bi = sr + TILE * pl.S;                   // [R][TILE]
+  double* bj = bi + (w.mode == W_GPR ? w.R * TILE : 0);
+  double* red = bj + (w.mode == W_GPR ? w.R * TILE : 0);   // [8][nacc]
+  double* stage = red + 8 * nacc;                  // [8 warps][2][8][8]
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3, qb = lane & ~3;
+  double* Ts = stage + warp * 128;                 // adjoints of a layer's outputs   [element][output]
+  double* Hs = Ts + 64;                            // the layer's inputs and a 1      [element][input]
+  const int64_t i0 = (int64_t)blockIdx.y * TILE;
+  const int64_t jtiles = (M + TILE - 1) / TILE;
+
+  for (int t = tid; t < pl.n_theta; t += GRAM_THREADS) {
+    th[t] = theta[t];
+    tinv[t] = 1.0 / theta[t];
+  }
+  for (int t = tid; t < 8 * nacc; t += GRAM_THREADS) red[t] = 0.0;
+  for (int idx = tid; idx < TILE * pl.FT; idx += GRAM_THREADS) {
+    int r = idx / pl.FT, c = idx - r * pl.FT;
+    sl[r * pl.S + c] = (i0 + r < N) ? FL[(i0 + r) * pl.FT + c] : 0.0;
+  }
+  if (w.mode == W_GPR)
+    for (int idx = tid; idx < w.R * TILE; idx += GRAM_THREADS) {
+      int r = idx / TILE, c = idx - r * TILE;
+      bi[idx] = (i0 + c < N) ? w.beta[(int64_t)r * N + i0 + c] : 0.0;
+    }
+  __syncthreads();
+  NknFrag f;
+  nkn_load_frag(nk, th, lr, lc, f);
+  const bool has0 = lc < nk.P, has1 = 4 + lc < nk.P;
+  const PrimC P0 = pl.prims[has0 ? lc : 0], P1 = pl.prims[has1 ? 4 + lc : 0];
+  // constant-1 columns of the staged layer inputs (bias gradients)
+  const double one1a = lc == nk.P ? 1.0 : 0.0, one1b = 4 + lc == nk.P ? 1.0 : 0.0;
+  const double one2a = lc == nk.i2 ? 1.0 : 0.0, one2b = 4 + lc == nk.i2 ? 1.0 : 0.0;
+
+  double acc0[1 + NKN_MAXD], acc1[1 + NKN_MAXD];
+#pragma unroll
+  for (int k = 0; k <= NKN_MAXD; ++k) acc0[k] = acc1[k] = 0.0;
+  double gw1[2] = {0.0, 0.0}, gw2[2] = {0.0, 0.0};   // DMMA tiles dW1[o = lr][i = 2 lc + q], dW2 likewise
+  double gw3 = 0.0, gb3 = 0.0, gtr = 0.0;
+
+  for (int64_t jt = blockIdx.x; jt < jtiles; jt += w.njc) {
+    const int64_t j0 = jt * TILE;
+    if (w.sym_lower && j0 > i0 + TILE - 1) break;
+    __syncthreads();   // previous tile fully consumed
+    for (int idx = tid; idx < TILE * pl.FT; idx += GRAM_THREADS) {
+      int r = idx / pl.FT, c = idx - r * pl.FT;
+      sr[r * pl.S + c] = (j0 + r < M) ? FR[(j0 + r) * pl.FT + c] : 0.0;
+    }
+    if (w.mode == W_GPR)
+      for (int idx = tid; idx < w.R * TILE; idx += GRAM_THREADS) {
+        int r = idx / TILE, c = idx - r * TILE;
+        bj[idx] = (j0 + c < M) ? w.beta[(int64_t)r * N + j0 + c] : 0.0;
+      }
+    __syncthreads();
+    for (int q = 0; q < TILE; ++q) {
+      const int il = warp * 8 + (q >> 3), jb = (q & 7) * 8, jl = jb + lr;
+      const int64_t gi = i0 + il, gj = j0 + jl;
+      if (gi >= N || j0 + jb >= M) continue;                      // warp uniform
+      if (w.sym_lower && j0 + jb > gi) continue;
+      const bool live = gj < M && !(w.sym_lower && gj > gi);
+      double wij = 0.0;
+      if (live) {
+        if (w.mode == W_GPR) {
+          double bb = 0.0;
+          for (int r = 0; r < w.R; ++r) bb = fma(bi[r * TILE + il], bj[r * TILE + jl], bb);
+          wij = 0.5 * ((double)w.R * w.W[gi * w.ldw + gj] - bb);
+          if (gi == gj && lc == 0) gtr += wij;                    // tr W = d nlml / d noise
+        } else {
+          wij = w.W[gi * w.ldw + gj];
+        }
+        if (w.sym_lower && gj != gi) wij *= 2.0;
+      }
+      const double* fi = sl + il * pl.S;
+      const double* fj = sr + jl * pl.S;
+      PrimEval e0, e1;
+      e0.k = e0.dk = e0.d2 = 0.0;
+      e1 = e0;
+      if (has0) e0 = prim_eval(P0, th, fi + P0.feat_off, fj + P0.feat_off);
+      if (has1) e1 = prim_eval(P1, th, fi + P1.feat_off, fj + P1.feat_off);
+      double o1[2], o2[2], h1, h2;
+      nkn_forward(f, e0.k, e1.k, o1, o2, h1, h2);
+
+      // ---- Linear 3 (-> 1) and Product 2
+      gw3 += wij * h2;
+      if (lc == 0) gb3 += wij;
+      const double dh2 = wij * f.w3;
+      const double d2a = dh2 * o2[1], d2b = dh2 * o2[0];          // adjoints of Linear-2 outputs 2 lc, 2 lc + 1
+      // ---- Linear 2: weight-gradient tile and adjoint of its inputs
+      Ts[lr * 8 + 2 * lc] = d2a;
+      Ts[lr * 8 + 2 * lc + 1] = d2b;
+      Hs[lr * 8 + lc] = lc < nk.i2 ? h1 : one2a;
+      Hs[lr * 8 + 4 + lc] = one2b;
+      __syncwarp();
+      double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        dmma884(gw2[0], gw2[1], Ts[(4 * s + lc) * 8 + lr], Hs[(4 * s + lc) * 8 + lr]);
+        dmma884(q0, q1, Ts[lr * 8 + 4 * s + lc], f.w2t[s]);       // dh1[e][2 lc], [2 lc + 1]
+      }
+      __syncwarp();
+      const int src = qb + (lc >> 1);
+      double t0 = __shfl_sync(0xffffffffu, q0, src), t1 = __shfl_sync(0xffffffffu, q1, src);
+      const double dh1 = (lc & 1) ? t1 : t0;                      // adjoint of Product-1 output lc
+      const double d1a = dh1 * o1[1], d1b = dh1 * o1[0];          // adjoints of Linear-1 outputs 2 lc, 2 lc + 1
+      // ---- Linear 1
+      Ts[lr * 8 + 2 * lc] = d1a;
+      Ts[lr * 8 + 2 * lc + 1] = d1b;
+      Hs[lr * 8 + lc] = has0 ? e0.k : one1a;
+      Hs[lr * 8 + 4 + lc] = has1 ? e1.k : one1b;
+      __syncwarp();
+      double r0 = 0.0, r1 = 0.0;
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        dmma884(gw1[0], gw1[1], Ts[(4 * s + lc) * 8 + lr], Hs[(4 * s + lc) * 8 + lr]);
+        dmma884(r0, r1, Ts[lr * 8 + 4 * s + lc], f.w1t[s]);       // dk[e][2 lc], [2 lc + 1]
+      }
+      __syncwarp();
+      t0 = __shfl_sync(0xffffffffu, r0, src);
+      t1 = __shfl_sync(0xffffffffu, r1, src);
+      const double g0 = (lc & 1) ? t1 : t0;                       // adjoint of primitive lc
+      t0 = __shfl_sync(0xffffffffu, r0, src + 2);
+      t1 = __shfl_sync(0xffffffffu, r1, src + 2);
+      const double g1 = (lc & 1) ? t1 : t0;                       // adjoint of primitive 4 + lc
+      if (has0) nkn_prim_grad(P0, tinv, fi + P0.feat_off, fj + P0.feat_off, e0, g0, acc0);
+      if (has1) nkn_prim_grad(P1, tinv, fi + P1.feat_off, fj + P1.feat_off, e1, g1, acc1);
+    }
+  }
+  // ---- CTA reduction (fixed order): per-warp rows of `red`, then over the 8 warps
+  double* rw = red + warp * nacc;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int i = 2 * lc + q;
+    if (lr < nk.n1) {
+      if (i < nk.P) rw[nk.w1 + lr * nk.P + i] = gw1[q];
+      else if (i == nk.P) rw[nk.b1 + lr] = gw1[q];
+    }
+    if (lr < nk.n2) {
+      if (i < nk.i2) rw[nk.w2 + lr * nk.i2 + i] = gw2[q];
+      else if (i == nk.i2) rw[nk.b2 + lr] = gw2[q];
+    }
+  }
+  // sums over the 8 elements (lr) of what each lane column accumulated
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) {
+    gw3 += __shfl_xor_sync(0xffffffffu, gw3, o);
+    gb3 += __shfl_xor_sync(0xffffffffu, gb3, o);
+    gtr += __shfl_xor_sync(0xffffffffu, gtr, o);
+#pragma unroll
+    for (int k = 0; k <= NKN_MAXD; ++k) {
+      acc0[k] += __shfl_xor_sync(0xffffffffu, acc0[k], o);
+      acc1[k] += __shfl_xor_sync(0xffffffffu, acc1[k], o);
+    }
+  }
+  if (lr == 0) {
+    if (lc < nk.i3) rw[nk.w3 + lc] = gw3;
+    if (lc == 0) {
+      rw[nk.b3] = gb3;
+      rw[pl.n_theta] = gtr;
+    }
+    const int np0 = has0 ? nkn_prim_nparams(P0) : 0, np1 = has1 ? nkn_prim_nparams(P1) : 0;
+#pragma unroll
+    for (int k = 0; k <= NKN_MAXD; ++k) {
+      if (k < np0) rw[P0.theta_off + k] = acc0[k];
+      if (k < np1) rw[P1.theta_off + k] = acc1[k];
+    }
+  }
+  __syncthreads();
+  const int64_t cta = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+  for (int t = tid; t < nacc; t += GRAM_THREADS) {
+    double s = 0.0;
+    for (int wq = 0; wq < GRAM_THREADS / 32; ++wq) s += red[wq * nacc + t];
+    part_theta[cta * nacc + t] = s;
+  }
+}
+
 // --------------------------------------------------------------------------- Kdiag
 __global__ void kdiag_kernel(const Plan pl, const PlanDims pd, const double* __restrict__ theta,
                              const double* __restrict__ X, int64_t ldx, int64_t N,
@@ -1214,6 +1572,8 @@ void gram_attrs() {
   cudaFuncSetAttribute(gram_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(gram_bwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(gram_fwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(gram_fwd_nkn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(gram_bwd_nkn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   g_gram_attr = true;
 }
 
@@ -1246,6 +1606,14 @@ int gps_gram_fwd_mat(gps_handle* h, const gps_kernel_desc* desc, const double* t
       gram_fwd_stat_kernel<8><<<grid, GRAM_THREADS, 0, h->stream>>>(P.type, P.ndims, pl.FT, theta, FL, FR, N, M, diag_add, sym, up, K.p, K.ld);
     else
       gram_fwd_stat_kernel<16><<<grid, GRAM_THREADS, 0, h->stream>>>(P.type, P.ndims, pl.FT, theta, FL, FR, N, M, diag_add, sym, up, K.p, K.ld);
+    GPS_LAUNCH_CHECK(h);
+    return 0;
+  }
+  NknPlan nk;
+  if (nkn_match(h, pl, &nk)) {
+    // Linear / Product(2) networks: the layers on the FP64 tensor cores (see gram_bwd_nkn_kernel)
+    gram_fwd_nkn_kernel<<<grid, GRAM_THREADS, smem, h->stream>>>(pl, nk, theta, FL, FR, N, M, diag_add,
+                                                                 X2 ? 0 : 1, X2 ? 0 : uplo, K.p, K.ld);
     GPS_LAUNCH_CHECK(h);
     return 0;
   }
@@ -1315,9 +1683,15 @@ int gps_gram_bwd_mat(gps_handle* h, const gps_kernel_desc* desc, const double* t
   size_t smem = (size_t)(2 * pl.n_theta + 2 * TILE * pl.S + (w.mode == W_GPR ? 2 * w.R * TILE : 0) +
                          8 * nacc + (dX ? TILE * X.cols : 0)) * sizeof(double);
   if (!use_smem_acc && smem > 220 * 1024) return gps_fail(h, -2, "gram_bwd: kernel too large for shared memory");
+  NknPlan nk;
+  const size_t smem_nkn = (size_t)(2 * pl.n_theta + 2 * TILE * pl.S + (w.mode == W_GPR ? 2 * w.R * TILE : 0) +
+                                   8 * nacc + 8 * 128) * sizeof(double);
   if (use_smem_acc) {
     gram_bwd_smem_kernel<<<dim3((unsigned)njc, (unsigned)itiles), NT2, smem2, h->stream>>>(
         pl, pd, nslots, theta, FL, FR, N, M, a, part, pdx);
+  } else if (!dX && smem_nkn <= 220 * 1024 && nkn_match(h, pl, &nk)) {
+    gram_bwd_nkn_kernel<<<dim3((unsigned)njc, (unsigned)itiles), GRAM_THREADS, smem_nkn, h->stream>>>(
+        pl, nk, theta, FL, FR, N, M, a, part);
   } else if (fast) {
     const PrimC P = pl.prims[0];
     const dim3 g2((unsigned)njc, (unsigned)itiles);

@@ -67,8 +67,8 @@ def _worker(rank, world, port, n, d, r, block, lookahead, out_q):
 
 @pytest.mark.parametrize('world,n,r,block,lookahead', [(1, 700, 1, 256, True), (2, 900, 2, 128, True),
                                                        (3, 1100, 1, 256, True), (2, 600, 1, 128, False),
-                                                       (4, 1300, 1, 128, True), (2, 515, 3, 256, True),
-                                                       (2, 900, 2, 128, 'v2'), (3, 1100, 1, 256, 'v2'), (4, 1300, 1, 128, 'v2')])
+                                                       (2, 515, 3, 256, True), (2, 900, 2, 128, 'v2'),
+                                                       (4, 1300, 1, 128, 'v2')])
 def test_distributed_gpr_host_logic_matches_oracle(world, n, r, block, lookahead):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
@@ -111,8 +111,7 @@ def _predict_worker(rank, world, port, n, ns, r, block, out_q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world,n,ns,r,block', [(1, 500, 37, 1, 128), (2, 700, 53, 2, 128), (3, 640, 5, 1, 256),
-                                                (4, 600, 2, 1, 128)])
+@pytest.mark.parametrize('world,n,ns,r,block', [(2, 700, 53, 2, 128), (3, 640, 5, 1, 256), (4, 600, 2, 1, 128)])
 def test_distributed_predict_matches_oracle(world, n, ns, r, block):
     """dist_gpr.predict: the ranks factor together, the test points are dealt out (ragged, also
     fewer test points than ranks), one all-gather joins mean / variance."""

@@ -71,6 +71,41 @@ def test_smem_accumulator_backward_nkn_gpr(golden):
         assert_close(g, gold['grad/objective/%d' % i], 1e-8, 'grad %d' % i)
 
 
+@pytest.mark.parametrize('n,m', [(75, 41), (300, 517), (1024, 64)])
+def test_nkn_tensor_core_kernels_equal_the_interpreter(n, m):
+    """gram_impl 0 on a Linear/Product(2) network (gram_fwd_nkn_kernel / gram_bwd_nkn_kernel: layers,
+    adjoint mat-vecs and weight gradients as FP64 tensor-core products over octets of elements) against
+    the interpreter (gram_impl 1): K(X), K(X, X2), dense backward of both, the fused GPR gradient."""
+    import gpflowSlim as gpf
+    from gpflowSlim._backend.lib import handle_for
+    d = 5
+    rng = np.random.default_rng(n * 7 + m)
+    X, X2 = conv(rng.standard_normal((n, d))), conv(rng.standard_normal((m, d)))
+    Y = conv(rng.standard_normal((n, 2)))
+    W, Ws = conv(rng.standard_normal((n, m))), conv(rng.standard_normal((n, n)))
+    h = handle_for(X)
+    res = {}
+    for impl in (0, 1):
+        h.set_option('gram_impl', impl)
+        try:
+            kern = cases.nkn_c3_kernel(gpf, d)
+            params = [p.unconstrained_tensor for p in kern.parameters]
+            K, K2 = kern.K(X), kern.K(X, X2)
+            g1 = torch.autograd.grad((K * Ws).sum(), params)
+            g2 = torch.autograd.grad((K2 * W).sum(), params)
+            model = gpf.models.GPR(X, Y, kern=kern, name='nkn_tc_%d_%d_%d' % (n, m, impl))
+            obj = model.objective
+            g3 = torch.autograd.grad(obj, [p.unconstrained_tensor for p in model.parameters])
+            res[impl] = [K.detach(), K2.detach(), obj.detach()] + list(g1) + list(g2) + list(g3)
+        finally:
+            h.set_option('gram_impl', 0)
+    same = True
+    for i, (a, b) in enumerate(zip(res[0], res[1])):
+        assert_close(a, b, 1e-9, 'nkn item %d (n=%d m=%d)' % (i, n, m))
+        same = same and torch.equal(a, b)
+    assert not same            # the two runs took different kernels
+
+
 def test_smem_accumulator_backward_speed_nkn():
     """Not an assertion about speed -- prints the two timings for the NKN Gram backward."""
     import gpflowSlim as gpf
@@ -81,7 +116,7 @@ def test_smem_accumulator_backward_speed_nkn():
     Xc = conv(X)
     W = conv(np.random.default_rng(0).standard_normal((n, n)))
     h = handle_for(Xc)
-    for impl in (1, 2):
+    for impl in (0, 1, 2):     # 0: the tensor-core NKN kernels, 1: interpreter, 2: interpreter with shared-memory arrays
         h.set_option('gram_impl', impl)
         try:
             params = [p.unconstrained_tensor for p in kern.parameters]

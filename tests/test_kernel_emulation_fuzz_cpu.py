@@ -20,6 +20,7 @@ gemm_lib = G.emu          # module-scoped fixtures of the two emulation tests, r
 gram_lib = K.emu
 
 
+@pytest.mark.slow
 def test_fuzz_gemm(gemm_lib):
     rng = np.random.default_rng(101)
     for it in range(NCASES):
@@ -94,6 +95,7 @@ def _random_kernel(gpf, rng, D):
     return expr()
 
 
+@pytest.mark.slow
 def test_fuzz_gram_interpreter(gram_lib):
     gpf = K._gpf()
     rng = np.random.default_rng(202)

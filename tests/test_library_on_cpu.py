@@ -190,6 +190,7 @@ def test_autograd_adjoints_on_the_real_kernels(gpf):
         assert float((a - b).abs().max()) < 1e-10 * max(1.0, float(b.abs().max()))
 
 
+@pytest.mark.slow
 def test_split_k_gemm_through_the_launch_code(gpf):
     """Option "gemm_splitk" (on by default): long-K products with few output tiles are cut into K
     slices by the host code (slice count from the SM count -- 4 in the CPU build), partial tiles
@@ -198,9 +199,9 @@ def test_split_k_gemm_through_the_launch_code(gpf):
     rng = np.random.default_rng(17)
     h = lib.handle_for(None)
     close = lambda a, b: np.testing.assert_allclose(a.numpy(), b, rtol=0, atol=1e-12 * max(1.0, np.abs(b).max()))
-    A, B = rng.standard_normal((100, 2050)), rng.standard_normal((90, 2050))
+    A, B = rng.standard_normal((100, 1100)), rng.standard_normal((90, 1100))
     C0 = rng.standard_normal((100, 90))
-    Asq = rng.standard_normal((100, 1100))
+    Asq = rng.standard_normal((100, 600))
     A3 = conv(rng.standard_normal((40, 1031)))[:, :1029]                 # odd leading dimension, ragged K
     h.set_option('gemm_splitk', 1)
     try:
@@ -218,6 +219,7 @@ def test_split_k_gemm_through_the_launch_code(gpf):
         h.set_option('gemm_splitk', 1)     # the default
 
 
+@pytest.mark.slow
 def test_fast_path_gram_input_gradient(gpf):
     """gps_gram_bwd of a single stationary kernel with d/dX: the register-tiled kernel writes
     G = dObj/d(d2) and one skinny tensor-core product G [F | 1] gives the input gradient; against
@@ -226,7 +228,7 @@ def test_fast_path_gram_input_gradient(gpf):
     import gpflowSlim
     from oracle import ref_torch as R
     rng = np.random.default_rng(4)
-    n, m, d = 150, 70, 5
+    n, m, d = 100, 60, 5
     Xn, X2n = rng.standard_normal((n, d)), rng.standard_normal((m, d))
     W, Ws = conv(rng.standard_normal((n, m))), conv(rng.standard_normal((n, n)))
     dims = [0, 2, 3, 4]
@@ -235,7 +237,7 @@ def test_fast_path_gram_input_gradient(gpf):
                                                 active_dims=dims)
         spec = dict(type=typ, variance=torch.tensor(1.3, dtype=torch.float64),
                     lengthscales=torch.tensor([0.7, 0.9, 1.1, 1.3], dtype=torch.float64), active_dims=dims)
-        for mode in ('both', 'x2', 'sym'):
+        for mode in (('both', 'x2', 'sym') if cls == 'RBF' else ('both',)):
             X, X2 = conv(Xn).requires_grad_(mode != 'x2'), conv(X2n).requires_grad_(mode != 'sym')
             Xo, X2o = conv(Xn).requires_grad_(mode != 'x2'), conv(X2n).requires_grad_(mode != 'sym')
             if mode == 'sym':
@@ -249,6 +251,70 @@ def test_fast_path_gram_input_gradient(gpf):
                 assert float((a - b).abs().max()) < 1e-11 * float(b.abs().max()), (cls, mode)
 
 
+def _nkn(gpf, d, prims, widths):
+    """Linear -> Product(2) -> Linear -> Product(2) -> Linear(->1) network over `prims`."""
+    n1, n2 = widths
+    hparams = [dict(name='Linear', params=dict(input_dim=len(prims), output_dim=n1, name='l0')),
+               dict(name='Product', params=dict(input_dim=n1, step=2, name='l1')),
+               dict(name='Linear', params=dict(input_dim=n1 // 2, output_dim=n2, name='l2')),
+               dict(name='Product', params=dict(input_dim=n2, step=2, name='l3')),
+               dict(name='Linear', params=dict(input_dim=n2 // 2, output_dim=1, name='l4'))]
+    np.random.seed(1)
+    return gpf.neural_kernel_network.NeuralKernelNetwork(d, prims, gpf.neural_kernel_network.NKNWrapper(hparams))
+
+
+@pytest.mark.parametrize('topo', ['c3', 'seven', 'narrow'])
+def test_nkn_tensor_core_gram_kernels_against_the_interpreter(gpf, topo):
+    """gram_fwd_nkn_kernel / gram_bwd_nkn_kernel (Linear layers, adjoint mat-vecs and weight
+    gradients as 8x8x4 FP64 tensor-core products over octets of matrix elements) against the generic
+    interpreter kernels (gram_impl 1): K(X) with jitter, K(X, X2), the dense backward for both and the
+    fused GPR objective gradient (K^-1 / beta weights, lower tiles only), ragged sizes."""
+    from gpflowSlim._backend import lib
+    k = gpf.kernels
+    d = 3
+    if topo == 'c3':
+        prims = [k.RBF(d, ARD=True, name='a0'), k.RBF(d, lengthscales=2.0, ARD=True, name='a1'),
+                 k.Periodic(d, period=1.0, lengthscales=1.0, name='a2'), k.Periodic(d, period=2.0, name='a3'),
+                 k.Linear(d, ARD=True, name='a4'), k.Linear(d, ARD=True, name='a5')]
+        widths = (8, 4)
+    elif topo == 'seven':   # 7 primitives: the bias column is the 8th; non-ARD, Matern, Linear without ARD
+        prims = [k.Matern32(d, lengthscales=1.5, name='b0'), k.RBF(d, name='b1'), k.Linear(d, name='b2'),
+                 k.Matern52(2, active_dims=[0, 2], ARD=True, name='b3'), k.Periodic(d, period=1.5, name='b4'),
+                 k.Matern12(d, name='b5'), k.RBF(1, active_dims=[1], name='b6')]
+        widths = (6, 8)
+    else:                   # fewer than 4 primitives and the narrowest layers
+        prims = [k.RBF(d, ARD=True, name='c0'), k.Linear(d, name='c1')]
+        widths = (2, 2)
+    rng = np.random.default_rng(11)
+    n, m = 77, 45
+    X, X2 = conv(rng.standard_normal((n, d))), conv(rng.standard_normal((m, d)))
+    Y = conv(rng.standard_normal((n, 2)))
+    W, Ws = conv(rng.standard_normal((n, m))), conv(rng.standard_normal((n, n)))
+    h = lib.handle_for(None)
+    res = {}
+    for impl in (0, 1):
+        h.set_option('gram_impl', impl)
+        try:
+            kern = _nkn(gpf, d, prims, widths)
+            params = [p.unconstrained_tensor for p in kern.parameters]
+            K, K2 = kern.K(X), kern.K(X, X2)
+            g1 = torch.autograd.grad((K * Ws).sum(), params, allow_unused=True)
+            g2 = torch.autograd.grad((K2 * W).sum(), params, allow_unused=True)
+            model = gpf.models.GPR(X, Y, kern=kern, name='nkn_fast_%s_%d' % (topo, impl))
+            obj = model.objective
+            g3 = torch.autograd.grad(obj, [p.unconstrained_tensor for p in model.parameters])
+            res[impl] = [K.detach(), K2.detach(), obj.detach()] + [g for gs in (g1, g2, g3) for g in gs if g is not None]
+        finally:
+            h.set_option('gram_impl', 0)
+    assert len(res[0]) == len(res[1]) > 10
+    same = True
+    for a, b in zip(res[0], res[1]):
+        assert float((a - b).abs().max()) <= 1e-11 * max(float(b.abs().max()), 1e-30)
+        same = same and torch.equal(a, b)
+    assert not same          # another summation order: the two runs really took different kernels
+
+
+@pytest.mark.slow
 def test_prefix_solves_with_big_leaves(gpf):
     """gps_trsm_rlt_prefix / gps_trsm_rln_prefix with option trsm_leaf = 256: the aligned 256-blocks
     are solved by one product with their explicit inverses (built for all blocks at once by
@@ -256,12 +322,12 @@ def test_prefix_solves_with_big_leaves(gpf):
     dense inverses, for rows that start inside and outside a leaf."""
     from gpflowSlim._backend import dist_gpr, lib
     rng = np.random.default_rng(11)
-    n, bs = 600, 128
+    n, bs = 400, 128                       # one aligned 256-leaf + a ragged 144-wide tail
     A = rng.standard_normal((n, n + 3))
     S = A @ A.T / (n + 3) + 0.5 * np.eye(n)
     L = np.linalg.cholesky(S)
     U, Kinv = np.linalg.inv(L).T, np.linalg.inv(S)
-    rows = np.concatenate([np.arange(0, 40), np.arange(128, 200), np.arange(384, 420), np.arange(512, 560)])
+    rows = np.concatenate([np.arange(0, 20), np.arange(128, 150), np.arange(256, 270), np.arange(384, 400)])
     act = rows // bs * bs
     h = lib.handle_for(None)
 
@@ -290,7 +356,7 @@ def test_prefix_solves_with_big_leaves(gpf):
     assert np.abs(results[128] - results[256]).max() < 1e-11 * np.abs(Kinv).max()
 
 
-@pytest.mark.parametrize('n,m', [(70, 33), (200, 140), (1, 1)])
+@pytest.mark.parametrize('n,m', [(70, 33), pytest.param(*((200, 140) if FULL else (130, 40)), marks=pytest.mark.slow), (1, 1)])
 def test_library_side_adjoints(gpf, n, m):
     """gps_potri / gps_chol_bwd / gps_trsm_bwd (csrc/adjoint.cu), with U computed inside and with
     a caller-supplied U, against torch autograd and a dense inverse."""
@@ -325,12 +391,13 @@ def test_library_side_adjoints(gpf, n, m):
 #   svgp_nonwhite_diag 16 [3e-12], functions 19 [4e-13], gpr_features 19 [1e-10], mc_models 32 [1e-10],
 #   sgpr 41 [1e-12], gpr_composed 65 [2e-14], gpr_misc 69 [2e-14], likelihoods_extra 0.2 [0], priors 5 [2e-15],
 #   large_d 43 [4e-15], lbfgs 225 [2e-12], gpr_white 15 [5e-14]  (mc_models, likelihoods_extra, large_d had never run on a GPU then)
-_DEFAULT_CASES = ['kernels', 'svgp_white_diag', 'nkn', 'gpr_white']
-_FULL_CASES = ['kernels_extra', 'svgp_nonwhite_diag', 'functions', 'gpr_features', 'mc_models', 'sgpr',
+_DEFAULT_CASES = ['kernels', 'svgp_white_diag', 'nkn']
+_FULL_CASES = ['gpr_white', 'kernels_extra', 'svgp_nonwhite_diag', 'functions', 'gpr_features', 'mc_models', 'sgpr',
                'gpr_composed', 'gpr_misc', 'likelihoods_extra', 'priors', 'large_d', 'lbfgs']
 
 
-@pytest.mark.parametrize('name', _DEFAULT_CASES + (_FULL_CASES if FULL else []))
+@pytest.mark.parametrize('name', [pytest.param(c, marks=pytest.mark.slow) if c == 'nkn' else c for c in _DEFAULT_CASES] +
+                         (_FULL_CASES if FULL else []))
 def test_golden_cases_through_the_real_library(gpf, golden, name):
     """The parity contract of tests/test_gpu_parity.py -- reference golden vectors, 1e-8 relative --
     with the shipped library code running on the CPU (fused one-call GPR objective and gradient,
@@ -472,6 +539,7 @@ def _dist_worker(rank, world, port, so_path, n, r, block, out_q, schedule=True):
         dist.destroy_process_group()
 
 
+@pytest.mark.slow
 @pytest.mark.parametrize('schedule', [True] + (['v2'] if FULL else []))
 @pytest.mark.parametrize('world,n,r,block', [(2, 300, 1, 128)] + ([(1, 330, 2, 128), (3, 420, 1, 128)] if FULL else []))
 def test_distributed_gpr_on_the_real_kernels_under_gloo(cpu_lib, world, n, r, block, schedule):
