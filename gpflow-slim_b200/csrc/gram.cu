@@ -20,6 +20,7 @@
 // of X), recomputing K tile by tile; W is either a dense matrix or, for the fused GPR
 // objective, formed on the fly as 1/2 (R K^-1 - beta beta^T) from the lower triangle of K^-1.
 // Reductions are deterministic (per-CTA partials + a fixed-order second pass).
+#include <algorithm>
 #include <math.h>
 #include <string.h>
 
@@ -1160,6 +1161,17 @@ bool nkn_match(const gps_handle* h, const Plan& pl, NknPlan* nk) {
   return true;
 }
 
+// Shared-memory row stride of the feature tiles for the NKN kernels: the 8 elements of an octet read 8
+// consecutive rows at the same column, and the lanes of two primitives of the same type run together,
+// so rows must land in distinct 8-byte banks of a half warp: stride = +-1 (mod 16).  (The first version
+// used the interpreter's odd stride, 83 for the C3 network: ncu counted 1.1e8 bank conflicts at N=4096,
+// profiles/r02_nkn_bwd_ncu_full.json.)
+int nkn_row_stride(int ft) {
+  int s = ft;
+  while (s % 16 != 1 && s % 16 != 15) ++s;
+  return s;
+}
+
 // per-lane DMMA operand fragments of the three Linear layers, zero padded to 8 x 8
 struct NknFrag {
   double w1f[2], w2f, w3;        // B fragments (weights[out = lr][in = lc + 4 s]) of Linear 1 (two k-steps), Linear 2;
@@ -1183,6 +1195,65 @@ __device__ __forceinline__ void nkn_load_frag(const NknPlan& nk, const double* _
   f.w2f = (lr < nk.n2 && lc < nk.i2) ? th[nk.w2 + lr * nk.i2 + lc] : 0.0;
   f.w3 = lc < nk.i3 ? th[nk.w3 + lc] : 0.0;
   f.b3 = th[nk.b3];
+}
+
+// A primitive's descriptor in registers (PrimC packs int16 fields in constant memory: fetched by a
+// per-lane index inside the octet loop, every use was a constant load + a sign extension -- 6.6 % of
+// the first version's instructions).
+struct PrimR {
+  int type, ard, ndims, theta_off, feat_off;
+};
+__device__ __forceinline__ PrimR nkn_prim(const Plan& pl, int p) {
+  const PrimC c = pl.prims[p];
+  PrimR r;
+  r.type = c.type; r.ard = c.ard; r.ndims = c.ndims; r.theta_off = c.theta_off; r.feat_off = c.feat_off;
+  return r;
+}
+
+// prim_eval for the NKN kernels: the loops over the (<= NKN_MAXD) active dimensions are unrolled under a
+// guard (the generic loops spend half of their instructions on counters, selects and branches) and the
+// periodic kernel multiplies by 1 / lengthscale^2 where prim_eval divides.
+__device__ __forceinline__ PrimEval nkn_prim_eval(const PrimR& P, const double* __restrict__ th,
+                                                  const double* __restrict__ tinv,
+                                                  const double* __restrict__ fi, const double* __restrict__ fj) {
+  PrimEval e;
+  e.k = 0; e.dk = 0; e.d2 = 0;
+  const double* t = th + P.theta_off;
+  const int nd = P.ndims;
+  if (is_stationary(P.type)) {
+    double dot = 0.0;
+#pragma unroll
+    for (int k = 0; k < NKN_MAXD; ++k)
+      if (k < nd) dot = fma(fi[k], fj[k], dot);
+    double raw = -2.0 * dot + (fi[nd] + fj[nd]);
+    bool live = raw >= 0.0;
+    double d2 = live ? raw : 0.0;
+    e.d2 = d2;
+    stat_body(P.type, t[0], d2, live, e.k, e.dk);
+  } else if (P.type == GPS_LINEAR) {
+    double dot = 0.0;
+    if (P.ard) {
+#pragma unroll
+      for (int k = 0; k < NKN_MAXD; ++k)
+        if (k < nd) dot = fma(fi[k] * t[k], fj[k], dot);
+    } else {
+      const double v = t[0];
+#pragma unroll
+      for (int k = 0; k < NKN_MAXD; ++k)
+        if (k < nd) dot = fma(fi[k] * v, fj[k], dot);
+    }
+    e.k = dot;
+  } else {
+    double cs = 0.0;
+#pragma unroll
+    for (int k = 0; k < NKN_MAXD; ++k)
+      if (k < nd) cs += fi[k] * fj[k] + fi[nd + k] * fj[nd + k];
+    const double ils = tinv[P.theta_off + 1];
+    double r = 0.5 * ((double)nd - cs) * (ils * ils);
+    e.k = t[0] * exp(-0.5 * r);
+    e.dk = r;
+  }
+  return e;
 }
 
 // forward pass of one octet.  k0 / k1: this lane's two primitive values of its element (0 where the lane
@@ -1209,12 +1280,16 @@ gram_fwd_nkn_kernel(const Plan pl, const NknPlan nk, const double* __restrict__ 
                     double diag_add, int sym, int uplo, double* __restrict__ K, int64_t ldk) {
   extern __shared__ double sm[];
   double* th = sm;
-  double* sl = th + pl.n_theta;
+  double* tinv = th + pl.n_theta;
+  double* sl = tinv + pl.n_theta;
   double* sr = sl + TILE * pl.S;
   const int64_t i0 = (int64_t)blockIdx.y * TILE, j0 = (int64_t)blockIdx.x * TILE;
   if (sym && uplo && j0 > i0 + TILE - 1) return;
   const int tid = threadIdx.x;
-  for (int t = tid; t < pl.n_theta; t += GRAM_THREADS) th[t] = theta[t];
+  for (int t = tid; t < pl.n_theta; t += GRAM_THREADS) {
+    th[t] = theta[t];
+    tinv[t] = 1.0 / theta[t];
+  }
   for (int idx = tid; idx < TILE * pl.FT; idx += GRAM_THREADS) {
     int r = idx / pl.FT, c = idx - r * pl.FT;
     sl[r * pl.S + c] = (i0 + r < N) ? FL[(i0 + r) * pl.FT + c] : 0.0;
@@ -1225,7 +1300,7 @@ gram_fwd_nkn_kernel(const Plan pl, const NknPlan nk, const double* __restrict__ 
   NknFrag f;
   nkn_load_frag(nk, th, lr, lc, f);
   const bool has0 = lc < nk.P, has1 = 4 + lc < nk.P;
-  const PrimC P0 = pl.prims[has0 ? lc : 0], P1 = pl.prims[has1 ? 4 + lc : 0];
+  const PrimR P0 = nkn_prim(pl, has0 ? lc : 0), P1 = nkn_prim(pl, has1 ? 4 + lc : 0);
   for (int q = 0; q < TILE; ++q) {
     const int il = warp * 8 + (q >> 3), jb = (q & 7) * 8, jl = jb + lr;
     const int64_t gi = i0 + il, gj = j0 + jl;
@@ -1234,8 +1309,8 @@ gram_fwd_nkn_kernel(const Plan pl, const NknPlan nk, const double* __restrict__ 
     const double* fi = sl + il * pl.S;
     const double* fj = sr + jl * pl.S;
     double k0 = 0.0, k1 = 0.0;
-    if (has0) k0 = prim_eval(P0, th, fi + P0.feat_off, fj + P0.feat_off).k;
-    if (has1) k1 = prim_eval(P1, th, fi + P1.feat_off, fj + P1.feat_off).k;
+    if (has0) k0 = nkn_prim_eval(P0, th, tinv, fi + P0.feat_off, fj + P0.feat_off).k;
+    if (has1) k1 = nkn_prim_eval(P1, th, tinv, fi + P1.feat_off, fj + P1.feat_off).k;
     double o1[2], o2[2], h1, h2;
     double out = nkn_forward(f, k0, k1, o1, o2, h1, h2);
     if (lc == 0 && gj < M && !(sym && uplo && gj > gi)) {
@@ -1246,23 +1321,24 @@ gram_fwd_nkn_kernel(const Plan pl, const NknPlan nk, const double* __restrict__ 
 }
 
 // parameter gradient of one primitive at one element: acc[q] += g * d k / d theta[theta_off + q]
-__device__ __forceinline__ void nkn_prim_grad(const PrimC& P, const double* __restrict__ tinv,
-                                              const double* __restrict__ fi, const double* __restrict__ fj,
-                                              const PrimEval& ev, double g, double* acc) {
-  const double* ti = tinv + P.theta_off;
+__device__ __forceinline__ void nkn_prim_grad(const PrimR& P, const double* __restrict__ fi,
+                                              const double* __restrict__ fj, const PrimEval& ev, double g,
+                                              double* acc) {
+  // the factors that depend on theta only (1 / variance, 1 / lengthscale ...) are applied once per lane
+  // after the loop over the matrix elements: nkn_prim_scale
   const int nd = P.ndims;
   if (is_stationary(P.type)) {
-    acc[0] += g * ev.k * ti[0];
-    const double G = g * ev.dk;
+    acc[0] += g * ev.k;
+    const double G = -2.0 * g * ev.dk;
     if (P.ard) {
 #pragma unroll
       for (int k = 0; k < NKN_MAXD; ++k)
         if (k < nd) {
           double df = fi[k] - fj[k];
-          acc[1 + k] += G * (-2.0) * df * df * ti[1 + k];
+          acc[1 + k] += G * df * df;
         }
     } else {
-      acc[1] += G * (-2.0) * ev.d2 * ti[1];
+      acc[1] += G * ev.d2;
     }
   } else if (P.type == GPS_LINEAR) {
     if (P.ard) {
@@ -1271,23 +1347,47 @@ __device__ __forceinline__ void nkn_prim_grad(const PrimC& P, const double* __re
         if (k < nd) acc[k] += g * fi[k] * fj[k];
     } else {
       double s = 0.0;
-      for (int k = 0; k < nd; ++k) s += fi[k] * fj[k];
+#pragma unroll
+      for (int k = 0; k < NKN_MAXD; ++k)
+        if (k < nd) s = fma(fi[k], fj[k], s);
       acc[0] += g * s;
     }
   } else {
-    const double kk = ev.k, r = ev.dk, ils = ti[1], iper = ti[2];
-    acc[0] += g * kk * ti[0];
-    acc[1] += g * kk * r * ils;
+    const double gk = g * ev.k;
+    acc[0] += gk;
+    acc[1] += gk * ev.dk;
     double dcs = 0.0;
-    for (int k = 0; k < nd; ++k) {
-      double sind = fi[nd + k] * fj[k] - fi[k] * fj[nd + k];      // sin(a_i - a_j)
-      dcs += sind * (fi[2 * nd + k] - fj[2 * nd + k]);
-    }
-    acc[2] += g * kk * dcs * iper * (0.25 * ils * ils);
+#pragma unroll
+    for (int k = 0; k < NKN_MAXD; ++k)
+      if (k < nd) {
+        double sind = fi[nd + k] * fj[k] - fi[k] * fj[nd + k];    // sin(a_i - a_j)
+        dcs += sind * (fi[2 * nd + k] - fj[2 * nd + k]);
+      }
+    acc[2] += gk * dcs;
   }
 }
 
-__device__ __forceinline__ int nkn_prim_nparams(const PrimC& P) {
+// theta-only factors of the sums nkn_prim_grad accumulated (same formulas as gram_bwd_kernel)
+__device__ __forceinline__ void nkn_prim_scale(const PrimR& P, const double* __restrict__ tinv, double* acc) {
+  const double* ti = tinv + P.theta_off;
+  if (is_stationary(P.type)) {
+    acc[0] *= ti[0];
+    if (P.ard) {
+#pragma unroll
+      for (int k = 0; k < NKN_MAXD; ++k)
+        if (k < P.ndims) acc[1 + k] *= ti[1 + k];
+    } else {
+      acc[1] *= ti[1];
+    }
+  } else if (P.type == GPS_PERIODIC) {
+    const double ils = ti[1], iper = ti[2];
+    acc[0] *= ti[0];
+    acc[1] *= ils;
+    acc[2] *= iper * (0.25 * ils * ils);
+  }
+}
+
+__device__ __forceinline__ int nkn_prim_nparams(const PrimR& P) {
   return is_stationary(P.type) ? 1 + (P.ard ? P.ndims : 1) : P.type == GPS_LINEAR ? (P.ard ? P.ndims : 1) : 3;
 }
 
@@ -1299,24 +1399,26 @@ gram_bwd_nkn_kernel(const Plan pl, const NknPlan nk, const double* __restrict__ 
   const int nacc = pl.n_theta + 1;
   double* th = sm;                                 // [n_theta]
   double* tinv = th + pl.n_theta;                  // [n_theta]
-  double* sl = tinv + pl.n_theta;                  // [TILE][S]
-  double* sr = sl + TILE * pl.S;                   // [TILE][S]
-  double* bi = sr + TILE * pl.S;                   // [R][TILE]
+  double* bi = tinv + pl.n_theta;                  // [R][TILE]
   double* bj = bi + (w.mode == W_GPR ? w.R * TILE : 0);
-  double* red = bj + (w.mode == W_GPR ? w.R * TILE : 0);   // [8][nacc]
-  double* stage = red + 8 * nacc;                  // [8 warps][2][8][8]
+  double* stage = bj + (w.mode == W_GPR ? w.R * TILE : 0);   // [8 warps][2][8][8]
+  double* sl = stage + 8 * 128;                    // [TILE][S]
+  double* sr = sl + TILE * pl.S;                   // [TILE][S]
+  double* red = sl;                                // [8][nacc], after the main loop (the host sizes the
+                                                   // region as max(2 TILE S, 8 nacc))
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3, qb = lane & ~3;
   double* Ts = stage + warp * 128;                 // adjoints of a layer's outputs   [element][output]
   double* Hs = Ts + 64;                            // the layer's inputs and a 1      [element][input]
-  const int64_t i0 = (int64_t)blockIdx.y * TILE;
+  // row tiles in descending order: with lower-triangular weights the last row tile has the most
+  // column tiles, and the hardware hands out CTAs in grid order -- heavy ones first, light ones fill the tail
+  const int64_t i0 = (int64_t)(gridDim.y - 1 - blockIdx.y) * TILE;
   const int64_t jtiles = (M + TILE - 1) / TILE;
 
   for (int t = tid; t < pl.n_theta; t += GRAM_THREADS) {
     th[t] = theta[t];
     tinv[t] = 1.0 / theta[t];
   }
-  for (int t = tid; t < 8 * nacc; t += GRAM_THREADS) red[t] = 0.0;
   for (int idx = tid; idx < TILE * pl.FT; idx += GRAM_THREADS) {
     int r = idx / pl.FT, c = idx - r * pl.FT;
     sl[r * pl.S + c] = (i0 + r < N) ? FL[(i0 + r) * pl.FT + c] : 0.0;
@@ -1330,7 +1432,7 @@ gram_bwd_nkn_kernel(const Plan pl, const NknPlan nk, const double* __restrict__ 
   NknFrag f;
   nkn_load_frag(nk, th, lr, lc, f);
   const bool has0 = lc < nk.P, has1 = 4 + lc < nk.P;
-  const PrimC P0 = pl.prims[has0 ? lc : 0], P1 = pl.prims[has1 ? 4 + lc : 0];
+  const PrimR P0 = nkn_prim(pl, has0 ? lc : 0), P1 = nkn_prim(pl, has1 ? 4 + lc : 0);
   // constant-1 columns of the staged layer inputs (bias gradients)
   const double one1a = lc == nk.P ? 1.0 : 0.0, one1b = 4 + lc == nk.P ? 1.0 : 0.0;
   const double one2a = lc == nk.i2 ? 1.0 : 0.0, one2b = 4 + lc == nk.i2 ? 1.0 : 0.0;
@@ -1355,7 +1457,17 @@ gram_bwd_nkn_kernel(const Plan pl, const NknPlan nk, const double* __restrict__ 
         bj[idx] = (j0 + c < M) ? w.beta[(int64_t)r * N + j0 + c] : 0.0;
       }
     __syncthreads();
+    // the weight of octet q + 1 is requested while octet q is computed (the first version loaded it
+    // where it was used: 8 % of all stall samples sat on the instruction after that load)
+    auto w_load = [&](int q) -> double {
+      const int64_t gi = i0 + warp * 8 + (q >> 3), gj = j0 + (q & 7) * 8 + lr;
+      if (gi >= N || gj >= M || (w.sym_lower && gj > gi)) return 0.0;
+      return w.W[gi * w.ldw + gj];
+    };
+    double w_next = w_load(0);
     for (int q = 0; q < TILE; ++q) {
+      const double w_raw = w_next;
+      w_next = q + 1 < TILE ? w_load(q + 1) : 0.0;
       const int il = warp * 8 + (q >> 3), jb = (q & 7) * 8, jl = jb + lr;
       const int64_t gi = i0 + il, gj = j0 + jl;
       if (gi >= N || j0 + jb >= M) continue;                      // warp uniform
@@ -1366,10 +1478,10 @@ gram_bwd_nkn_kernel(const Plan pl, const NknPlan nk, const double* __restrict__ 
         if (w.mode == W_GPR) {
           double bb = 0.0;
           for (int r = 0; r < w.R; ++r) bb = fma(bi[r * TILE + il], bj[r * TILE + jl], bb);
-          wij = 0.5 * ((double)w.R * w.W[gi * w.ldw + gj] - bb);
+          wij = 0.5 * ((double)w.R * w_raw - bb);
           if (gi == gj && lc == 0) gtr += wij;                    // tr W = d nlml / d noise
         } else {
-          wij = w.W[gi * w.ldw + gj];
+          wij = w_raw;
         }
         if (w.sym_lower && gj != gi) wij *= 2.0;
       }
@@ -1378,8 +1490,8 @@ gram_bwd_nkn_kernel(const Plan pl, const NknPlan nk, const double* __restrict__ 
       PrimEval e0, e1;
       e0.k = e0.dk = e0.d2 = 0.0;
       e1 = e0;
-      if (has0) e0 = prim_eval(P0, th, fi + P0.feat_off, fj + P0.feat_off);
-      if (has1) e1 = prim_eval(P1, th, fi + P1.feat_off, fj + P1.feat_off);
+      if (has0) e0 = nkn_prim_eval(P0, th, tinv, fi + P0.feat_off, fj + P0.feat_off);
+      if (has1) e1 = nkn_prim_eval(P1, th, tinv, fi + P1.feat_off, fj + P1.feat_off);
       double o1[2], o2[2], h1, h2;
       nkn_forward(f, e0.k, e1.k, o1, o2, h1, h2);
 
@@ -1424,11 +1536,16 @@ gram_bwd_nkn_kernel(const Plan pl, const NknPlan nk, const double* __restrict__ 
       t0 = __shfl_sync(0xffffffffu, r0, src + 2);
       t1 = __shfl_sync(0xffffffffu, r1, src + 2);
       const double g1 = (lc & 1) ? t1 : t0;                       // adjoint of primitive 4 + lc
-      if (has0) nkn_prim_grad(P0, tinv, fi + P0.feat_off, fj + P0.feat_off, e0, g0, acc0);
-      if (has1) nkn_prim_grad(P1, tinv, fi + P1.feat_off, fj + P1.feat_off, e1, g1, acc1);
+      if (has0) nkn_prim_grad(P0, fi + P0.feat_off, fj + P0.feat_off, e0, g0, acc0);
+      if (has1) nkn_prim_grad(P1, fi + P1.feat_off, fj + P1.feat_off, e1, g1, acc1);
     }
   }
-  // ---- CTA reduction (fixed order): per-warp rows of `red`, then over the 8 warps
+  if (has0) nkn_prim_scale(P0, tinv, acc0);
+  if (has1) nkn_prim_scale(P1, tinv, acc1);
+  // ---- CTA reduction (fixed order): per-warp rows of `red` (on top of the feature tiles), then over the 8 warps
+  __syncthreads();
+  for (int t = tid; t < 8 * nacc; t += GRAM_THREADS) red[t] = 0.0;
+  __syncthreads();
   double* rw = red + warp * nacc;
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
@@ -1612,8 +1729,12 @@ int gps_gram_fwd_mat(gps_handle* h, const gps_kernel_desc* desc, const double* t
   NknPlan nk;
   if (nkn_match(h, pl, &nk)) {
     // Linear / Product(2) networks: the layers on the FP64 tensor cores (see gram_bwd_nkn_kernel)
-    gram_fwd_nkn_kernel<<<grid, GRAM_THREADS, smem, h->stream>>>(pl, nk, theta, FL, FR, N, M, diag_add,
-                                                                 X2 ? 0 : 1, X2 ? 0 : uplo, K.p, K.ld);
+    Plan pn = pl;
+    pn.S = nkn_row_stride(pl.FT);
+    size_t smem_n = (size_t)(2 * pl.n_theta + 2 * TILE * pn.S) * sizeof(double);
+    if (smem_n > 200 * 1024) { pn.S = pl.S; smem_n = smem + (size_t)pl.n_theta * sizeof(double); }
+    gram_fwd_nkn_kernel<<<grid, GRAM_THREADS, smem_n, h->stream>>>(pn, nk, theta, FL, FR, N, M, diag_add,
+                                                                   X2 ? 0 : 1, X2 ? 0 : uplo, K.p, K.ld);
     GPS_LAUNCH_CHECK(h);
     return 0;
   }
@@ -1670,6 +1791,23 @@ int gps_gram_bwd_mat(gps_handle* h, const gps_kernel_desc* desc, const double* t
   a.mode = w.mode; a.W = w.W.p; a.ldw = w.W.ld; a.beta = w.beta; a.R = w.R;
   a.sym_lower = w.sym_lower; a.want_dx = dX ? 1 : 0; a.xcols = (int)X.cols;
   a.dx_scale = X2 ? 1.0 : 2.0; a.njc = (int)njc;
+  NknPlan nk;
+  Plan pn = pl;
+  pn.S = nkn_row_stride(pl.FT);
+  const size_t nkn_fixed = (size_t)(2 * pl.n_theta + (w.mode == W_GPR ? 2 * w.R * TILE : 0) + 8 * 128);
+  auto nkn_bytes = [&](int S) { return (nkn_fixed + std::max<size_t>(2 * TILE * S, 8 * nacc)) * sizeof(double); };
+  size_t smem_nkn = nkn_bytes(pn.S);
+  if (smem_nkn > 113 * 1024 && nkn_bytes(pl.S) <= 113 * 1024) {   // two CTAs per SM (228 KB, 1 KB reserved each) first
+    pn.S = pl.S;
+    smem_nkn = nkn_bytes(pn.S);
+  }
+  const bool nkn = !use_smem_acc && !dX && smem_nkn <= 220 * 1024 && nkn_match(h, pl, &nk);
+  if (nkn) {
+    // two CTAs per SM and uneven work per CTA (lower tiles only): many more CTAs than slots
+    njc = (16 * h->sm_count + itiles - 1) / itiles;
+    if (njc > jtiles) njc = jtiles;
+    a.njc = (int)njc;
+  }
   const int64_t nctas = itiles * njc;
   double* part = (double*)gps_ws(h, WS_PARTIAL, (size_t)nctas * nacc * sizeof(double));
   if (!part) return -102;
@@ -1683,15 +1821,12 @@ int gps_gram_bwd_mat(gps_handle* h, const gps_kernel_desc* desc, const double* t
   size_t smem = (size_t)(2 * pl.n_theta + 2 * TILE * pl.S + (w.mode == W_GPR ? 2 * w.R * TILE : 0) +
                          8 * nacc + (dX ? TILE * X.cols : 0)) * sizeof(double);
   if (!use_smem_acc && smem > 220 * 1024) return gps_fail(h, -2, "gram_bwd: kernel too large for shared memory");
-  NknPlan nk;
-  const size_t smem_nkn = (size_t)(2 * pl.n_theta + 2 * TILE * pl.S + (w.mode == W_GPR ? 2 * w.R * TILE : 0) +
-                                   8 * nacc + 8 * 128) * sizeof(double);
   if (use_smem_acc) {
     gram_bwd_smem_kernel<<<dim3((unsigned)njc, (unsigned)itiles), NT2, smem2, h->stream>>>(
         pl, pd, nslots, theta, FL, FR, N, M, a, part, pdx);
-  } else if (!dX && smem_nkn <= 220 * 1024 && nkn_match(h, pl, &nk)) {
+  } else if (nkn) {
     gram_bwd_nkn_kernel<<<dim3((unsigned)njc, (unsigned)itiles), GRAM_THREADS, smem_nkn, h->stream>>>(
-        pl, nk, theta, FL, FR, N, M, a, part);
+        pn, nk, theta, FL, FR, N, M, a, part);
   } else if (fast) {
     const PrimC P = pl.prims[0];
     const dim3 g2((unsigned)njc, (unsigned)itiles);

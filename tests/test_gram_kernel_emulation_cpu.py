@@ -39,6 +39,11 @@ def emu(tmp_path_factory):
     start = src.index('#include "internal.cuh"') + len('#include "internal.cuh"')
     end = src.index('int features(gps_handle* h')          # everything up to the host launch code
     region = src[start:end]
+    # the tensor-core NKN kernels need the warp-level mma emulation of the whole-library CPU build
+    # (tests/test_library_on_cpu.py::test_nkn_tensor_core_gram_kernels_against_the_interpreter covers them)
+    n0, n1_ = region.index('// --------------------------------------------------------------------------- NKN fast path'), \
+        region.index('// --------------------------------------------------------------------------- Kdiag')
+    region = region[:n0] + region[n1_:]
     region, n1 = re.subn(r'extern __shared__ double sm\[\];', 'double* sm = emu_smem;', region)
     region, n2 = re.subn(r'__syncthreads\(\)', 'emu_barrier()', region)
     region, n3 = re.subn(r'__shfl_xor_sync\(0xffffffffu, (\w+), (\d+)\)', r'emu_shfl_xor(\1, \2)', region)

@@ -1,5 +1,5 @@
-"""Profiling driver: one warm-up and one profiled fused GPR NLML+grad evaluation (or a bare
-GEMM / POTRF) so that `ncu --profile-from-start off` captures exactly one step."""
+"""Profiling driver: one warm-up and one profiled fused GPR NLML+grad evaluation (ARD-RBF, or the
+NKN network of config C3 with --what nkn; or a bare GEMM / POTRF) so that `ncu --profile-from-start off` captures exactly one step."""
 import argparse
 import math
 import os
@@ -27,6 +27,16 @@ def main():
         X, Y = synth_gpr(n, d)
         kern = gpf.kernels.RBF(d, ARD=True, lengthscales=math.sqrt(d))
         m = gpf.models.GPR(torch.tensor(X, device=dev), torch.tensor(Y, device=dev), kern=kern)
+        params = [p.unconstrained_tensor for p in m.parameters]
+
+        def step():
+            obj = m.objective
+            torch.autograd.grad(obj, params)
+    elif args.what == 'nkn':
+        # the BASELINE C3 network through the fused GPR objective: gram_fwd_nkn_kernel / gram_bwd_nkn_kernel
+        from bench import nkn_c3_kernel
+        X, Y = synth_gpr(n, d)
+        m = gpf.models.GPR(torch.tensor(X, device=dev), torch.tensor(Y, device=dev), kern=nkn_c3_kernel(gpf, d))
         params = [p.unconstrained_tensor for p in m.parameters]
 
         def step():
