@@ -1165,7 +1165,7 @@ bool nkn_match(const gps_handle* h, const Plan& pl, NknPlan* nk) {
 // consecutive rows at the same column, and the lanes of two primitives of the same type run together,
 // so rows must land in distinct 8-byte banks of a half warp: stride = +-1 (mod 16).  (The first version
 // used the interpreter's odd stride, 83 for the C3 network: ncu counted 1.1e8 bank conflicts at N=4096,
-// profiles/r02_nkn_bwd_ncu_full.json.)
+// profiles/r02_nkn_bwd_first_ncu_full.json.)
 int nkn_row_stride(int ft) {
   int s = ft;
   while (s % 16 != 1 && s % 16 != 15) ++s;
@@ -1197,9 +1197,12 @@ __device__ __forceinline__ void nkn_load_frag(const NknPlan& nk, const double* _
   f.b3 = th[nk.b3];
 }
 
-// A primitive's descriptor in registers (PrimC packs int16 fields in constant memory: fetched by a
-// per-lane index inside the octet loop, every use was a constant load + a sign extension -- 6.6 % of
-// the first version's instructions).
+// A primitive's descriptor as plain ints.  PrimC packs int16 fields in constant memory, fetched by a per-lane
+// index: in the first version every use inside the octet loop was a constant load + a sign extension (6.6 %
+// of its instructions).  MEASURED AFTERWARDS (profiles/r02_nkn_bwd_source_hotspots.txt): under the
+// 128-register cap of two CTAs per SM the compiler still re-fetches the fields inside the loop (13 % of the
+// tuned version's instructions sit on nkn_prim) -- the next step is one packed 32-bit word per primitive,
+// or the descriptors of the CTA in shared memory.
 struct PrimR {
   int type, ard, ndims, theta_off, feat_off;
 };

@@ -63,7 +63,7 @@ struct gps_handle {
   std::string err;
   int gemm_impl = 0;
   int leaf_impl = 0;   // 0 = blocked DMMA leaf, 1 = simple check kernel
-  int gram_impl = 0;   // 0 = register-tiled fast path for single stationary kernels, 1 = interpreter only,
+  int gram_impl = 0;   // 0 = specialised kernels where they apply (single stationary kernel; NKN networks), 1 = interpreter only,
                        // 2 = experimental shared-memory-accumulator interpreter backward
   int profile = 0;
   int trsm_leaf = 512; // prefix solves: aligned diagonal blocks of this size (a power-of-two multiple of 128)

@@ -111,8 +111,10 @@ int gps_version(void);
 /* options: "gemm_impl" 0 = DMMA tensor-core GEMM, operands staged by TMA when they are 16-byte
  *                          aligned with even leading dimensions, else by cp.async (default);
  *                      1 = plain-FMA check kernel; 2 = always the cp.async DMMA kernel;
- *          "gram_impl" 0 = register-tiled Gram kernels for a single stationary covariance where
- *                          they apply (default), 1 = the generic interpreter kernels only,
+ *          "gram_impl" 0 = specialised Gram kernels where they apply (default): register-tiled for a
+ *                          single stationary covariance, tensor-core (mma.sync f64) kernels for
+ *                          Linear/Product(2) neural-kernel networks; interpreter otherwise,
+ *                          1 = the generic interpreter kernels only,
  *                          2 = interpreter kernels with their slot / accumulator arrays in shared
  *                          memory (correct, 7 % faster on the NKN config, not the default;
  *                          tests/test_gpu_switches.py holds it to the default path);
