@@ -77,7 +77,7 @@ def test_abi_of_the_cpu_build_matches_the_header(cpu_lib):
     assert cdll.gps_version() == 100
 
 
-@pytest.mark.parametrize('n', [1, 31, 129, 200, 256])    # 256: the level-batched triangular inverse
+@pytest.mark.parametrize('n', [1, 31, 129, pytest.param(200, marks=pytest.mark.slow), 256])    # 256: the level-batched triangular inverse
 def test_cholesky_solve_inverse_through_the_host_recursion(gpf, n):
     """gps_potrf (recursive blocked, leaves + strip TRSMs + lower-masked GEMM updates),
     gps_trsm_rlt, gps_tri_inv_t, gps_sum_log_diag, gps_row_sumsq, gps_transpose."""
