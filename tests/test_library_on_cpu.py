@@ -314,6 +314,59 @@ def test_nkn_tensor_core_gram_kernels_against_the_interpreter(gpf, topo):
     assert not same          # another summation order: the two runs really took different kernels
 
 
+def test_networks_outside_the_tensor_core_shape_keep_the_interpreter(gpf):
+    """nkn_match (gram.cu) must hand anything but Linear -> Product(2) -> Linear -> Product(2) -> Linear(->1)
+    over <= 7 primitives of <= 8 active dimensions to the interpreter: for such programs gram_impl 0 and 1
+    run the SAME kernels, so the results are bit-identical (the specialised kernels sum in another order,
+    see the `not same` assertion of the test above)."""
+    from gpflowSlim._backend import lib
+    k = gpf.kernels
+    nn = gpf.neural_kernel_network
+
+    def net(prims, hparams, d):
+        np.random.seed(2)
+        return nn.NeuralKernelNetwork(d, prims, nn.NKNWrapper(hparams))
+
+    def lin(i, o, name):
+        return dict(name='Linear', params=dict(input_dim=i, output_dim=o, name=name))
+
+    def prod(i, name, step=2):
+        return dict(name='Product', params=dict(input_dim=i, step=step, name=name))
+    cases_ = {
+        # 8 primitives: no free column for the bias in the first 8 x 8 tile
+        'eight': (3, lambda: net([k.RBF(3, name='e%d' % i) for i in range(8)],
+                                 [lin(8, 4, 'l0'), prod(4, 'l1'), lin(2, 2, 'l2'), prod(2, 'l3'), lin(1, 1, 'l4')], 3)),
+        # three layers only
+        'short': (3, lambda: net([k.RBF(3, name='s0'), k.Linear(3, name='s1')],
+                                 [lin(2, 4, 'l0'), prod(4, 'l1'), lin(2, 1, 'l2')], 3)),
+        # a primitive with 9 active dimensions
+        'wide': (9, lambda: net([k.RBF(9, ARD=True, name='w0'), k.Linear(9, name='w1')],
+                                [lin(2, 4, 'l0'), prod(4, 'l1'), lin(2, 2, 'l2'), prod(2, 'l3'), lin(1, 1, 'l4')], 9)),
+        # Product over 4 inputs at a time
+        'step4': (3, lambda: net([k.RBF(3, name='p0'), k.Matern32(3, name='p1')],
+                                 [lin(2, 8, 'l0'), prod(8, 'l1', step=4), lin(2, 2, 'l2'), prod(2, 'l3'), lin(1, 1, 'l4')], 3)),
+    }
+    h = lib.handle_for(None)
+    rng = np.random.default_rng(5)
+    for name, (d, make) in cases_.items():
+        X, X2 = conv(rng.standard_normal((40, d))), conv(rng.standard_normal((21, d)))
+        W = conv(rng.standard_normal((40, 21)))
+        res = {}
+        for impl in (0, 1):
+            h.set_option('gram_impl', impl)
+            try:
+                kern = make()
+                params = [p.unconstrained_tensor for p in kern.parameters]
+                K, K2 = kern.K(X), kern.K(X, X2)
+                g = torch.autograd.grad((K2 * W).sum(), params, allow_unused=True)
+                res[impl] = [K.detach(), K2.detach()] + [x for x in g if x is not None]
+            finally:
+                h.set_option('gram_impl', 0)
+        assert len(res[0]) == len(res[1]) > 4, name
+        for a, b in zip(res[0], res[1]):
+            assert torch.equal(a, b), name
+
+
 @pytest.mark.slow
 def test_prefix_solves_with_big_leaves(gpf):
     """gps_trsm_rlt_prefix / gps_trsm_rln_prefix with option trsm_leaf = 256: the aligned 256-blocks
