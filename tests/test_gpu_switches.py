@@ -3,6 +3,10 @@ module flags, each held to the default path (or to torch) on the GPU.  Written b
 round 1, first run (all green) on a B200 at the start of round 2 (profiles/r02_experimental_switches_gpu.txt);
 since then part of the regular `pytest -m gpu` run.
 
+gram_impl = 0 on Linear/Product(2) neural-kernel networks: the tensor-core kernels gram_fwd_nkn_kernel /
+gram_bwd_nkn_kernel (csrc/gram.cu) against the interpreter (gram_impl = 1), Gram, dense backward and the
+fused GPR gradient; the timing test prints all three implementations.
+
 gram_impl = 2: interpreter Gram forward / backward with the slot values, slot adjoints and
 theta-gradient accumulators in shared memory ([index][thread] layout) instead of local memory
 (csrc/gram.cu: gram_fwd_smem_kernel, gram_bwd_smem_kernel).  Must reproduce the default interpreter
