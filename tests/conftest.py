@@ -14,17 +14,10 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
-    config.addinivalue_line('markers', 'slow: heavy CUDA-source-on-the-CPU emulation cases; run with GPSLIM_SLOW_TESTS=1 '
-                                       '(the default CPU suite stays within a few minutes)')
 
 
 def pytest_collection_modifyitems(config, items):
     import torch
-    if os.environ.get('GPSLIM_SLOW_TESTS') != '1':
-        slow = pytest.mark.skip(reason='slow emulation case: set GPSLIM_SLOW_TESTS=1')
-        for item in items:
-            if 'slow' in item.keywords:
-                item.add_marker(slow)
     if torch.cuda.is_available():
         return
     skip = pytest.mark.skip(reason='no CUDA device')

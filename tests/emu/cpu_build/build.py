@@ -90,7 +90,7 @@ def build(outdir):
         open(cpp, 'w').write(src)
         obj = cpp.replace('.cpp', '.o')
         cmd = ['g++', '-std=c++17', '-O1', '-fPIC', '-pthread', '-Wno-attributes', '-Wno-unused-function',
-               '-Wno-unused-variable', '-I', HERE, '-I', CSRC, '-I', os.path.join(ROOT, 'include'), '-c', cpp, '-o', obj]
+               '-Wno-unused-variable', '-I', HERE, '-I', os.path.dirname(HERE), '-I', CSRC, '-I', os.path.join(ROOT, 'include'), '-c', cpp, '-o', obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode:
             raise RuntimeError('%s:\n%s' % (f, res.stderr[-5000:]))

@@ -4,10 +4,11 @@
 //   * device memory is host memory; streams do not exist: every launch runs to completion at its
 //     call site, which is one legal serialisation of the stream order;
 //   * a kernel launch `k<<<grid, block, smem, stream>>>(args)` is rewritten textually into
-//     EMU_LAUNCH(grid, block, smem, k(args)) by the build script: one std::thread per CUDA thread
-//     of a block, blocks one after the other, __syncthreads = block barrier, warp collectives =
-//     per-warp barriers + exchange buffer, mma.sync.m8n8k4.f64 emulated per the PTX fragment
-//     layout, cp.async = copy with zero fill;
+//     EMU_LAUNCH(grid, block, smem, k(args)) by the build script and executed by ../emu_fibers.h:
+//     one OS thread per WARP of a block, the 32 lanes of a warp as cooperative fibers of that
+//     thread, blocks one after the other, __syncthreads = warp gather + pthread barrier across
+//     the warps, warp collectives = warp barriers + exchange buffer, mma.sync.m8n8k4.f64 emulated
+//     per the PTX fragment layout, cp.async = copy with zero fill;
 //   * the TMA / mbarrier GEMM kernel is cut out (inline PTX): the cp.async tensor-core kernel
 //     serves every product, as it does on the GPU for operands TMA cannot address.
 // Nothing here is shipped or used by the product.
@@ -19,6 +20,7 @@
 #include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 
 #include <algorithm>
@@ -26,6 +28,8 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+
+#include "emu_fibers.h"
 
 using std::max;
 using std::min;
@@ -83,20 +87,11 @@ inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSucces
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 
-// ---------------------------------------------------------------- execution model
-struct EmuIdx { unsigned x = 0, y = 0, z = 0; };
-inline thread_local EmuIdx threadIdx, blockIdx;
-inline thread_local unsigned emu_ltid = 0;                // linear thread id inside the block
+// ---------------------------------------------------------------- execution model: ../emu_fibers.h
 inline dim3 gridDim, blockDim;
 inline double* emu_smem = nullptr;
 inline double* emu_wx = nullptr;                          // [2][nthreads] exchange slots
-inline unsigned emu_nthreads = 0;
-inline pthread_barrier_t emu_bar;
-inline pthread_barrier_t emu_wbar[32];
 inline std::mutex emu_atomic_mutex;
-
-inline void emu_barrier() { pthread_barrier_wait(&emu_bar); }
-inline void emu_warp_barrier() { pthread_barrier_wait(&emu_wbar[emu_ltid >> 5]); }
 #define __syncthreads() emu_barrier()
 #define __syncwarp() emu_warp_barrier()
 
@@ -159,38 +154,15 @@ inline int64_t emu_launch_count = 0;
 template <class Body>
 void emu_launch(dim3 grid, dim3 block, size_t smem_bytes, Body body) {
   ++emu_launch_count;
-  const unsigned nthreads = block.x * block.y * block.z;
   gridDim = grid;
   blockDim = block;
-  emu_nthreads = nthreads;
+  const unsigned nthreads = block.x * block.y * block.z;
   std::vector<double> smem(smem_bytes / sizeof(double) + 8), wx(2 * (size_t)nthreads + 64);
   emu_smem = smem.data();
   emu_wx = wx.data();
-  pthread_barrier_init(&emu_bar, nullptr, nthreads);
-  const unsigned nwarps = (nthreads + 31) / 32;
-  for (unsigned w = 0; w < nwarps; ++w)
-    pthread_barrier_init(&emu_wbar[w], nullptr, std::min(32u, nthreads - 32 * w));
-  std::vector<std::thread> pool;
-  pool.reserve(nthreads);
-  for (unsigned t = 0; t < nthreads; ++t)
-    pool.emplace_back([=, &smem]() {
-      emu_ltid = t;
-      threadIdx.x = t % block.x;
-      threadIdx.y = (t / block.x) % block.y;
-      threadIdx.z = t / (block.x * block.y);
-      for (unsigned bz = 0; bz < grid.z; ++bz)
-        for (unsigned by = 0; by < grid.y; ++by)
-          for (unsigned bx = 0; bx < grid.x; ++bx) {
-            blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
-            if (t == 0)
-              for (auto& v : smem) v = NAN;            // fresh block: stale shared memory cannot help
-            emu_barrier();
-            body();
-            emu_barrier();
-          }
-    });
-  for (auto& th : pool) th.join();
-  pthread_barrier_destroy(&emu_bar);
-  for (unsigned w = 0; w < nwarps; ++w) pthread_barrier_destroy(&emu_wbar[w]);
+  EmuIdx g, b;
+  g.x = grid.x; g.y = grid.y; g.z = grid.z;
+  b.x = block.x; b.y = block.y; b.z = block.z;
+  emu_run_grid(g, b, &smem, body);
 }
 #define EMU_LAUNCH(grid, block, smem, call) emu_launch((grid), (block), (size_t)(smem), [&]() { call; })

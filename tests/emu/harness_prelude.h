@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE ONLY: a host emulation layer just wide enough to execute the SOURCE TEXT
-// of the interpreter Gram kernels of gpflow-slim_b200/csrc/gram.cu on the CPU (one std::thread
-// per CUDA thread of a block, blocks run one after the other, __syncthreads / warp shuffles
-// emulated with barriers).  tests/test_gram_kernel_emulation_cpu.py generates a translation unit
+// of the interpreter Gram kernels of gpflow-slim_b200/csrc/gram.cu on the CPU (one OS thread
+// per warp of a block with its 32 lanes as cooperative fibers, blocks run one after the other,
+// __syncthreads / warp shuffles emulated with barriers).  tests/test_gram_kernel_emulation_cpu.py generates a translation unit
 // = this prelude + the kernel region of gram.cu (textually, with four mechanical substitutions
 // listed there) + harness_driver.inc, compiles it with g++ and compares the kernels with the
 // oracle.  Nothing here is shipped or used by the product.
@@ -14,12 +14,15 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <functional>
 #include <string>
 #include <thread>
 #include <vector>
 
+#include "emu_fibers.h"
 #include "gpslim_b200.h"
 
 #define __global__
@@ -34,20 +37,31 @@
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
-struct EmuDim3 { unsigned x = 1, y = 1, z = 1; };
-static thread_local EmuDim3 threadIdx, blockIdx;
+// ---- execution model: emu_fibers.h (one OS thread per warp, its lanes as cooperative fibers)
+typedef EmuIdx EmuDim3;
 static EmuDim3 gridDim, blockDim;
 static double* emu_smem = nullptr;          // dynamic shared memory of the running block
 static double* emu_xchg = nullptr;          // one slot per thread for the shuffle emulation
-static pthread_barrier_t emu_bar;
+static double* emu_wx = nullptr;            // [2][nthreads] exchange slots for warp collectives
 
-static inline void emu_barrier() { pthread_barrier_wait(&emu_bar); }
-// valid because every thread of the block executes the same sequence of shuffles in these kernels
+// all blocks of a (gx, gy) grid of `nthreads`-thread (1-D) blocks, one after the other
+template <class Body>
+static void emu_run(unsigned gx, unsigned gy, unsigned nthreads, size_t smem_doubles, Body body) {
+  gridDim.x = gx; gridDim.y = gy; gridDim.z = 1;
+  blockDim.x = nthreads; blockDim.y = blockDim.z = 1;
+  std::vector<double> smem(smem_doubles + 8), xchg(nthreads), wx(2 * (size_t)nthreads);
+  emu_smem = smem.data();
+  emu_xchg = xchg.data();
+  emu_wx = wx.data();
+  emu_run_grid(gridDim, blockDim, &smem, body);
+}
+
+// shuffles exchange inside one warp (lane masks below 32)
 static inline double emu_shfl_xor(double v, int lanemask) {
   emu_xchg[threadIdx.x] = v;
-  emu_barrier();
+  emu_warp_barrier();
   double r = emu_xchg[threadIdx.x ^ (unsigned)lanemask];
-  emu_barrier();
+  emu_warp_barrier();
   return r;
 }
 static inline double warp_sum(double v) {

@@ -2,7 +2,7 @@
 // diverge (the Cholesky leaf: warp 0 factors the next diagonal block while the other warps run
 // DMMA updates).  Warp collectives -- __syncwarp, __shfl_sync, __shfl_xor_sync and the FP64
 // tensor-core instruction mma.sync.m8n8k4 (dmma884) -- synchronise the 32 threads of ONE warp
-// through a per-warp barrier and exchange buffer.  Fragment layout of m8n8k4.f64 (PTX ISA):
+// through the warp barrier of harness_prelude.h (fiber switches inside the warp's OS thread) and an exchange buffer.  Fragment layout of m8n8k4.f64 (PTX ISA):
 //   A (8x4, row):  lane holds A[lane >> 2][lane & 3]
 //   B (4x8, col):  lane holds B[lane & 3][lane >> 2]
 //   C/D (8x8):     lane holds C[lane >> 2][2 (lane & 3) + {0, 1}]
@@ -15,12 +15,8 @@
 using std::max;
 using std::min;
 
-static pthread_barrier_t emu_wbar[32];
-static double* emu_wx = nullptr;            // [2][nthreads] exchange slots for warp collectives
-static unsigned emu_nthreads = 0;
 static std::mutex emu_atomic_mutex;
 
-static inline void emu_warp_barrier() { pthread_barrier_wait(&emu_wbar[threadIdx.x >> 5]); }
 #define __syncwarp() emu_warp_barrier()
 
 static inline double emu_shfl(double v, int src_lane) {

@@ -65,8 +65,7 @@ def _worker(rank, world, port, n, d, r, block, lookahead, out_q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world,n,r,block,lookahead', [pytest.param(1, 700, 1, 256, True, marks=pytest.mark.slow),
-                                                       pytest.param(2, 900, 2, 128, True, marks=pytest.mark.slow),
+@pytest.mark.parametrize('world,n,r,block,lookahead', [(1, 700, 1, 256, True), (2, 900, 2, 128, True),
                                                        (3, 1100, 1, 256, True), (2, 600, 1, 128, False),
                                                        (2, 515, 3, 256, True), (2, 900, 2, 128, 'v2'),
                                                        (4, 1300, 1, 128, 'v2')])

@@ -150,7 +150,6 @@ def test_rowmap_mask_of_the_block_row_distribution(emu):
     close(got, np.where(mask, C0 - A @ B.T, C0))
 
 
-@pytest.mark.slow
 def test_per_row_start_modes_of_the_prefix_solves(emu):
     """lo_mode 1: A[r][k] == 0 for lo_off + k < rowlo[r] (K range of a tile starts later);
     lo_mode 2: C[r][c] is not wanted for lo_off + c < rowlo[r] (tiles wholly left are skipped)."""

@@ -6,7 +6,7 @@ reductions that needs no GPU.
 How: the region of gram.cu between `#include "internal.cuh"` and the first host launch function
 (all kernels: interpreter, experimental shared-memory variants, register-tiled fast path, Kdiag) is copied
 verbatim into a host translation unit between tests/emu/harness_prelude.h (CUDA keywords defined
-away, threadIdx / blockIdx as thread-locals, one std::thread per CUDA thread, __syncthreads and
+away, one host thread per warp with its 32 lanes as cooperative fibers (emu/emu_fibers.h), __syncthreads and
 warp shuffles as barriers) and tests/emu/harness_driver.inc (launch loops + the fixed-order
 second-pass reductions of the host code), with exactly three textual substitutions:
     extern __shared__ double sm[];   ->  double* sm = emu_smem;

@@ -20,7 +20,6 @@ gemm_lib = G.emu          # module-scoped fixtures of the two emulation tests, r
 gram_lib = K.emu
 
 
-@pytest.mark.slow
 def test_fuzz_gemm(gemm_lib):
     rng = np.random.default_rng(101)
     for it in range(NCASES):
@@ -95,7 +94,6 @@ def _random_kernel(gpf, rng, D):
     return expr()
 
 
-@pytest.mark.slow
 def test_fuzz_gram_interpreter(gram_lib):
     gpf = K._gpf()
     rng = np.random.default_rng(202)

@@ -4,8 +4,9 @@ and driven through the package's own ctypes binding and autograd layer.
 `tests/emu/cpu_build/build.py` transforms the five unmodified .cu files textually (kernel launches
 -> EMU_LAUNCH, dynamic shared memory, one cache-hint asm, the TMA/mbarrier kernel cut out so that
 the cp.async tensor-core kernel serves every GEMM, DLPack device type) and compiles them with g++
-against a stand-in <cuda_runtime.h>: one host thread per CUDA thread, barriers for
-__syncthreads / warp collectives, an emulation of mma.sync.m8n8k4.f64.  The resulting shared
+against a stand-in <cuda_runtime.h>: one host thread per warp with its lanes as cooperative fibers
+(tests/emu/emu_fibers.h), barriers for __syncthreads / warp collectives, an emulation of
+mma.sync.m8n8k4.f64.  The resulting shared
 library exports the same C ABI; here it replaces the GPU library under `gpflowSlim._backend.lib`,
 so everything above it is the shipped code: DLTensor marshaling, argument checks, workspace
 management, the recursive blocked Cholesky / triangular inverse, the fused one-call GPR
@@ -14,8 +15,7 @@ objective + gradient, the Gram kernels, the autograd adjoints.
 What this cannot see: the TMA + mbarrier main loop of the default GEMM kernel, stream
 concurrency (launches run to completion in issue order), and anything about speed.
 
-Default selection runs in about a minute; GPSLIM_CPU_LIB_FULL=1 adds the larger golden cases
-(all of which were run clean when this was written, see the table in the test)."""
+The whole selection runs in about a minute; GPSLIM_CPU_LIB_FULL=0 keeps only the short one."""
 import os
 
 import numpy as np
@@ -24,7 +24,7 @@ import torch
 
 from oracle import cases
 
-FULL = os.environ.get('GPSLIM_CPU_LIB_FULL') == '1'
+FULL = os.environ.get('GPSLIM_CPU_LIB_FULL', '1') == '1'      # GPSLIM_CPU_LIB_FULL=0: the short selection
 
 
 def conv(a):
@@ -77,7 +77,7 @@ def test_abi_of_the_cpu_build_matches_the_header(cpu_lib):
     assert cdll.gps_version() == 100
 
 
-@pytest.mark.parametrize('n', [1, 31, 129, pytest.param(200, marks=pytest.mark.slow), 256])    # 256: the level-batched triangular inverse
+@pytest.mark.parametrize('n', [1, 31, 129, 200, 256])    # 256: the level-batched triangular inverse
 def test_cholesky_solve_inverse_through_the_host_recursion(gpf, n):
     """gps_potrf (recursive blocked, leaves + strip TRSMs + lower-masked GEMM updates),
     gps_trsm_rlt, gps_tri_inv_t, gps_sum_log_diag, gps_row_sumsq, gps_transpose."""
@@ -190,7 +190,6 @@ def test_autograd_adjoints_on_the_real_kernels(gpf):
         assert float((a - b).abs().max()) < 1e-10 * max(1.0, float(b.abs().max()))
 
 
-@pytest.mark.slow
 def test_split_k_gemm_through_the_launch_code(gpf):
     """Option "gemm_splitk" (on by default): long-K products with few output tiles are cut into K
     slices by the host code (slice count from the SM count -- 4 in the CPU build), partial tiles
@@ -199,9 +198,9 @@ def test_split_k_gemm_through_the_launch_code(gpf):
     rng = np.random.default_rng(17)
     h = lib.handle_for(None)
     close = lambda a, b: np.testing.assert_allclose(a.numpy(), b, rtol=0, atol=1e-12 * max(1.0, np.abs(b).max()))
-    A, B = rng.standard_normal((100, 1100)), rng.standard_normal((90, 1100))
+    A, B = rng.standard_normal((100, 2050)), rng.standard_normal((90, 2050))
     C0 = rng.standard_normal((100, 90))
-    Asq = rng.standard_normal((100, 600))
+    Asq = rng.standard_normal((100, 1100))
     A3 = conv(rng.standard_normal((40, 1031)))[:, :1029]                 # odd leading dimension, ragged K
     h.set_option('gemm_splitk', 1)
     try:
@@ -219,7 +218,6 @@ def test_split_k_gemm_through_the_launch_code(gpf):
         h.set_option('gemm_splitk', 1)     # the default
 
 
-@pytest.mark.slow
 def test_fast_path_gram_input_gradient(gpf):
     """gps_gram_bwd of a single stationary kernel with d/dX: the register-tiled kernel writes
     G = dObj/d(d2) and one skinny tensor-core product G [F | 1] gives the input gradient; against
@@ -228,7 +226,7 @@ def test_fast_path_gram_input_gradient(gpf):
     import gpflowSlim
     from oracle import ref_torch as R
     rng = np.random.default_rng(4)
-    n, m, d = 100, 60, 5
+    n, m, d = 150, 70, 5
     Xn, X2n = rng.standard_normal((n, d)), rng.standard_normal((m, d))
     W, Ws = conv(rng.standard_normal((n, m))), conv(rng.standard_normal((n, n)))
     dims = [0, 2, 3, 4]
@@ -237,7 +235,7 @@ def test_fast_path_gram_input_gradient(gpf):
                                                 active_dims=dims)
         spec = dict(type=typ, variance=torch.tensor(1.3, dtype=torch.float64),
                     lengthscales=torch.tensor([0.7, 0.9, 1.1, 1.3], dtype=torch.float64), active_dims=dims)
-        for mode in (('both', 'x2', 'sym') if cls == 'RBF' else ('both',)):
+        for mode in ('both', 'x2', 'sym'):
             X, X2 = conv(Xn).requires_grad_(mode != 'x2'), conv(X2n).requires_grad_(mode != 'sym')
             Xo, X2o = conv(Xn).requires_grad_(mode != 'x2'), conv(X2n).requires_grad_(mode != 'sym')
             if mode == 'sym':
@@ -314,6 +312,33 @@ def test_nkn_tensor_core_gram_kernels_against_the_interpreter(gpf, topo):
     assert not same          # another summation order: the two runs really took different kernels
 
 
+def test_nkn_tensor_core_backward_with_several_column_tiles_per_block(gpf):
+    """The column-tile loop of gram_bwd_nkn_kernel (a CTA walks tiles jt, jt + njc, ...; feature tiles and
+    beta rows are reloaded between two barriers; the reduction scratch aliases the feature tiles): N = 520
+    gives 9 row tiles and -- with the 4 SMs of the CPU build -- 8 column chunks, so the last row tiles have
+    CTAs with two tiles.  Fused GPR gradient (lower tiles, K^-1 / beta weights, R = 2) against the interpreter."""
+    from gpflowSlim._backend import lib
+    k = gpf.kernels
+    d, n = 3, 520
+    rng = np.random.default_rng(12)
+    X, Y = conv(rng.standard_normal((n, d))), conv(rng.standard_normal((n, 2)))
+    h = lib.handle_for(None)
+    res = {}
+    for impl in (0, 1):
+        h.set_option('gram_impl', impl)
+        try:
+            kern = _nkn(gpf, d, [k.RBF(d, ARD=True, name='m0'), k.Periodic(d, period=1.3, name='m1'),
+                                 k.Linear(d, ARD=True, name='m2'), k.Matern32(d, name='m3'), k.RBF(d, name='m4')], (8, 4))
+            model = gpf.models.GPR(X, Y, kern=kern, name='nkn_tiles_%d' % impl)
+            obj = model.objective
+            res[impl] = [obj.detach()] + list(torch.autograd.grad(obj, [p.unconstrained_tensor for p in model.parameters]))
+        finally:
+            h.set_option('gram_impl', 0)
+    for a, b in zip(res[0], res[1]):
+        assert float((a - b).abs().max()) <= 1e-10 * max(float(b.abs().max()), 1e-30)
+    assert not all(torch.equal(a, b) for a, b in zip(res[0], res[1]))
+
+
 def test_networks_outside_the_tensor_core_shape_keep_the_interpreter(gpf):
     """nkn_match (gram.cu) must hand anything but Linear -> Product(2) -> Linear -> Product(2) -> Linear(->1)
     over <= 7 primitives of <= 8 active dimensions to the interpreter: for such programs gram_impl 0 and 1
@@ -367,7 +392,6 @@ def test_networks_outside_the_tensor_core_shape_keep_the_interpreter(gpf):
             assert torch.equal(a, b), name
 
 
-@pytest.mark.slow
 def test_prefix_solves_with_big_leaves(gpf):
     """gps_trsm_rlt_prefix / gps_trsm_rln_prefix with option trsm_leaf = 256: the aligned 256-blocks
     are solved by one product with their explicit inverses (built for all blocks at once by
@@ -375,12 +399,12 @@ def test_prefix_solves_with_big_leaves(gpf):
     dense inverses, for rows that start inside and outside a leaf."""
     from gpflowSlim._backend import dist_gpr, lib
     rng = np.random.default_rng(11)
-    n, bs = 400, 128                       # one aligned 256-leaf + a ragged 144-wide tail
+    n, bs = 600, 128                       # two aligned 256-leaves + a ragged 88-wide tail
     A = rng.standard_normal((n, n + 3))
     S = A @ A.T / (n + 3) + 0.5 * np.eye(n)
     L = np.linalg.cholesky(S)
     U, Kinv = np.linalg.inv(L).T, np.linalg.inv(S)
-    rows = np.concatenate([np.arange(0, 20), np.arange(128, 150), np.arange(256, 270), np.arange(384, 400)])
+    rows = np.concatenate([np.arange(0, 40), np.arange(128, 200), np.arange(384, 420), np.arange(512, 560)])
     act = rows // bs * bs
     h = lib.handle_for(None)
 
@@ -409,7 +433,7 @@ def test_prefix_solves_with_big_leaves(gpf):
     assert np.abs(results[128] - results[256]).max() < 1e-11 * np.abs(Kinv).max()
 
 
-@pytest.mark.parametrize('n,m', [(70, 33), pytest.param(*((200, 140) if FULL else (130, 40)), marks=pytest.mark.slow), (1, 1)])
+@pytest.mark.parametrize('n,m', [(70, 33), (200, 140), (1, 1)])
 def test_library_side_adjoints(gpf, n, m):
     """gps_potri / gps_chol_bwd / gps_trsm_bwd (csrc/adjoint.cu), with U computed inside and with
     a caller-supplied U, against torch autograd and a dense inverse."""
@@ -449,7 +473,7 @@ _FULL_CASES = ['gpr_white', 'kernels_extra', 'svgp_nonwhite_diag', 'functions', 
                'gpr_composed', 'gpr_misc', 'likelihoods_extra', 'priors', 'large_d', 'lbfgs']
 
 
-@pytest.mark.parametrize('name', [pytest.param(c, marks=pytest.mark.slow) if c == 'nkn' else c for c in _DEFAULT_CASES] +
+@pytest.mark.parametrize('name', _DEFAULT_CASES +
                          (_FULL_CASES if FULL else []))
 def test_golden_cases_through_the_real_library(gpf, golden, name):
     """The parity contract of tests/test_gpu_parity.py -- reference golden vectors, 1e-8 relative --
@@ -487,7 +511,7 @@ def test_fused_gpr_objective_gradient_and_prediction(gpf):
     assert max(errs) < 1e-9, errs
 
 
-@pytest.mark.skipif(not FULL, reason='GPSLIM_CPU_LIB_FULL=1')
+@pytest.mark.skipif(not FULL, reason='GPSLIM_CPU_LIB_FULL=0')
 def test_experimental_switches_through_the_real_dispatch_code(gpf, golden):
     """The switches with an alternative implementation (tests/test_gpu_switches.py), through the
     shipped host code on the CPU build: gram_impl = 2 (shared-memory interpreter kernels: their
@@ -592,9 +616,8 @@ def _dist_worker(rank, world, port, so_path, n, r, block, out_q, schedule=True):
         dist.destroy_process_group()
 
 
-@pytest.mark.slow
-@pytest.mark.parametrize('schedule', [True] + (['v2'] if FULL else []))
-@pytest.mark.parametrize('world,n,r,block', [(2, 300, 1, 128)] + ([(1, 330, 2, 128), (3, 420, 1, 128)] if FULL else []))
+@pytest.mark.parametrize('world,n,r,block,schedule', [(2, 300, 1, 128, True)] + (
+    [(1, 330, 2, 128, 'v2'), (2, 300, 1, 128, 'v2'), (3, 420, 1, 128, True)] if FULL else []))
 def test_distributed_gpr_on_the_real_kernels_under_gloo(cpu_lib, world, n, r, block, schedule):
     import socket
     import torch.multiprocessing as mp
