@@ -173,6 +173,8 @@ inline void emu_run_grid(EmuIdx grid, EmuIdx block, std::vector<double>* smem, c
     emu_stacks = (char*)mmap(nullptr, 1024 * EMU_STACK, PROT_READ | PROT_WRITE,
                              MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
     if (emu_stacks == (char*)MAP_FAILED) { perror("emulation: mmap of the lane stacks"); abort(); }
+    for (size_t t = 0; t < 1024; ++t)       // guard page below every stack: an overflow faults instead of
+      mprotect(emu_stacks + t * EMU_STACK, 4096, PROT_NONE);   // scribbling over the neighbouring lane
   }
   emu_nthreads = nthreads;
   emu_nwarps = (nthreads + 31) / 32;
