@@ -2,9 +2,9 @@
 random GEMM shapes / leading dimensions / alignments / triangular flags against numpy, and random
 kernel EXPRESSIONS (primitives on random active dimensions, nested Sum / Product with constants,
 small NKNs) through the interpreter Gram kernels -- validated and experimental variants --
-against torch autograd through the oracle.  Seeded and bounded (about half a minute); set
-GPSLIM_FUZZ=<n> for n cases per family (500 Gram and 280 GEMM cases were run clean when this was
-written; the only deviations seen were the known 1e-8-level rounding noise of Matern-type kernels
+against torch autograd through the oracle.  Seeded and bounded (100 cases per family, about ten
+seconds on the fiber emulation); set GPSLIM_FUZZ=<n> for n cases per family (500 Gram and 280 GEMM
+cases were run clean when this was written, 400 + 400 again on the final code of round 2; the only deviations seen were the known 1e-8-level rounding noise of Matern-type kernels
 at nearly coincident 1-D points, which the reference's own distance formula has as well)."""
 import os
 
@@ -14,7 +14,7 @@ import pytest
 import test_gemm_kernel_emulation_cpu as G
 import test_gram_kernel_emulation_cpu as K
 
-NCASES = int(os.environ.get('GPSLIM_FUZZ', '16'))
+NCASES = int(os.environ.get('GPSLIM_FUZZ', '100'))
 
 gemm_lib = G.emu          # module-scoped fixtures of the two emulation tests, re-exported
 gram_lib = K.emu

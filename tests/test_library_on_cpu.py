@@ -339,6 +339,70 @@ def test_nkn_tensor_core_backward_with_several_column_tiles_per_block(gpf):
     assert not all(torch.equal(a, b) for a, b in zip(res[0], res[1]))
 
 
+def test_fuzz_nkn_tensor_core_kernels(gpf):
+    """Randomised differential test of gram_fwd_nkn_kernel / gram_bwd_nkn_kernel against the interpreter:
+    random numbers of primitives (1-7) of random types / ARD / active dimensions (1-8 of them), random
+    layer widths, ragged sizes; K(X), K(X, X2), both dense backward passes and, every third case, the fused
+    GPR gradient.  GPSLIM_FUZZ=<n> cases (default 24; 600 were run clean when this was written)."""
+    from gpflowSlim._backend import lib
+    k = gpf.kernels
+    ncases = int(os.environ.get('GPSLIM_FUZZ', '24'))
+    rng = np.random.default_rng(2024)
+    h = lib.handle_for(None)
+    for it in range(ncases):
+        D = int(rng.integers(1, 10))
+        P = int(rng.integers(1, 8))
+        specs = []
+        for p in range(P):
+            nd = int(rng.integers(1, min(D, 8) + 1))
+            dims = sorted(rng.choice(D, size=nd, replace=False).tolist())
+            typ = str(rng.choice(['RBF', 'Matern12', 'Matern32', 'Matern52', 'Exponential', 'Linear', 'Periodic']))
+            ard = bool(rng.integers(0, 2)) and typ != 'Periodic'
+            specs.append((typ, nd, dims, ard, float(rng.uniform(0.5, 2.0)), rng.uniform(0.7, 2.5, size=nd if ard else 1)))
+        widths = (2 * int(rng.integers(1, 5)), 2 * int(rng.integers(1, 5)))
+        n, m = int(rng.integers(1, 150)), int(rng.integers(1, 100))
+
+        def make(tag):
+            prims = []
+            for p, (typ, nd, dims, ard, var, ls) in enumerate(specs):
+                kw = dict(active_dims=dims, name='f%d_%d_%s' % (it, p, tag))
+                if typ == 'Linear':
+                    prims.append(k.Linear(nd, variance=(ls if ard else float(ls[0])), ARD=ard, **kw))
+                elif typ == 'Periodic':
+                    prims.append(k.Periodic(nd, period=float(ls[0]) + 0.5, variance=var, lengthscales=1.2, **kw))
+                else:
+                    prims.append(getattr(k, typ)(nd, variance=var, lengthscales=(ls if ard else float(ls[0])), ARD=ard, **kw))
+            return _nkn(gpf, D, prims, widths)
+        X, X2 = conv(rng.standard_normal((n, D))), conv(rng.standard_normal((m, D)))
+        W, Ws = conv(rng.standard_normal((n, m))), conv(rng.standard_normal((n, n)))
+        Y = conv(rng.standard_normal((n, int(rng.integers(1, 4)))))
+        res = {}
+        for impl in (0, 1):
+            h.set_option('gram_impl', impl)
+            try:
+                kern = make(str(impl))
+                params = [p.unconstrained_tensor for p in kern.parameters]
+                K, K2 = kern.K(X), kern.K(X, X2)
+                out = [K.detach(), K2.detach()]
+                out += [g for g in torch.autograd.grad((K * Ws).sum(), params, allow_unused=True) if g is not None]
+                out += [g for g in torch.autograd.grad((K2 * W).sum(), params, allow_unused=True) if g is not None]
+                if it % 3 == 0:
+                    model = gpf.models.GPR(X, Y, kern=kern, name='fz%d_%d' % (it, impl))
+                    obj = model.objective
+                    out += [obj.detach()] + list(torch.autograd.grad(obj, [p.unconstrained_tensor for p in model.parameters]))
+                res[impl] = out
+            finally:
+                h.set_option('gram_impl', 0)
+        assert len(res[0]) == len(res[1])
+        # the parameter gradients of one objective are sums of the same large terms with different signs: a
+        # small one is a cancelled sum, so errors are measured against the largest gradient of the case too
+        gmax = max(float(b.abs().max()) for b in res[1][2:])
+        for j, (a, b) in enumerate(zip(res[0], res[1])):
+            scale = max(float(b.abs().max()), 1e-4 * gmax if j >= 2 else 0.0, 1e-30)
+            err = float((a - b).abs().max()) / scale
+            assert err <= 1e-9, (it, j, err, specs, widths, n, m)
+
+
 def test_networks_outside_the_tensor_core_shape_keep_the_interpreter(gpf):
     """nkn_match (gram.cu) must hand anything but Linear -> Product(2) -> Linear -> Product(2) -> Linear(->1)
     over <= 7 primitives of <= 8 active dimensions to the interpreter: for such programs gram_impl 0 and 1
