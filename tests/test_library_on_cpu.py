@@ -100,6 +100,70 @@ def test_cholesky_solve_inverse_through_the_host_recursion(gpf, n):
     assert torch.equal(ops.transpose(B), B.t().contiguous())
 
 
+def test_fuzz_factorisation_solves_and_inverses_on_padded_buffers(gpf):
+    """Randomised differential test of the host recursion + kernels behind gps_potrf, gps_trsm_rlt,
+    gps_tri_inv_t, gps_potri, gps_chol_bwd and gps_trsm_bwd against LAPACK / torch autograd: random orders
+    1..520 (every leaf / strip / GEMM-tile raggedness), operands that are column slices of wider NaN-filled
+    buffers (leading dimension != width: nothing outside the view may be read or written), split-K on and
+    off.  GPSLIM_FUZZ=<n> cases (default 12; 150 were run clean when this was written)."""
+    import ctypes
+    from gpflowSlim._backend import lib, ops
+    ncases = int(os.environ.get('GPSLIM_FUZZ', '12'))
+    rng = np.random.default_rng(77)
+    h = lib.handle_for(None)
+
+    def padded(a, pad):
+        buf = torch.full((a.shape[0], a.shape[1] + pad), float('nan'), dtype=torch.float64)
+        v = buf[:, :a.shape[1]]
+        v.copy_(a)
+        return buf, v
+    for it in range(ncases):
+        n = int(rng.choice([int(rng.integers(1, 40)), int(rng.integers(100, 300)), int(rng.integers(300, 521))]))
+        m = int(rng.integers(1, 200))
+        pad = int(rng.choice([0, 1, 2, 5, 16]))
+        h.set_option('gemm_splitk', int(rng.integers(0, 2)))
+        try:
+            A = rng.standard_normal((n, n + 2))
+            S = conv(A @ A.T / (n + 2) + 0.3 * np.eye(n))
+            ref = torch.linalg.cholesky(S)
+            bufL, L = padded(S, pad)
+            info = ctypes.c_int(0)
+            h.check(h.lib.gps_potrf(h.ptr, lib.view(L).ref, 1, ctypes.byref(info)))
+            assert info.value == 0
+            assert float((L - ref).abs().max()) < 1e-12 * float(ref.abs().max()), (it, n, pad)
+            assert float(torch.triu(L, 1).abs().max()) == 0.0 and bool(torch.isnan(bufL[:, n:]).all())
+            B = conv(rng.standard_normal((m, n)))
+            bufB, Bv = padded(B, pad)
+            h.check(h.lib.gps_trsm_rlt(h.ptr, lib.view(L).ref, lib.view(Bv).ref))
+            want = torch.linalg.solve_triangular(ref, B.t(), upper=False).t()
+            assert float((Bv - want).abs().max()) < 1e-10 * max(1.0, float(want.abs().max())), (it, n, m, pad)
+            assert bool(torch.isnan(bufB[:, n:]).all())
+            bufU, U = padded(torch.zeros(n, n, dtype=torch.float64), pad)
+            U.fill_(float('nan'))
+            h.check(h.lib.gps_tri_inv_t(h.ptr, lib.view(L).ref, lib.view(U).ref))
+            Ti = torch.linalg.inv(ref).t()
+            assert float((U - Ti).abs().max()) < 1e-10 * float(Ti.abs().max()), (it, n, pad)
+            Kinv = ops.potri(L)
+            Ki = torch.linalg.inv(S)
+            assert float((torch.tril(Kinv) - torch.tril(Ki)).abs().max()) < 1e-9 * float(Ki.abs().max()), (it, n, pad)
+            # adjoints against torch autograd
+            Lbar = conv(np.tril(rng.standard_normal((n, n))))
+            Sg = S.clone().requires_grad_(True)
+            (torch.linalg.cholesky(Sg) * Lbar).sum().backward()
+            Sbar = ops.chol_bwd(L, Lbar)
+            wantS = 0.5 * (Sg.grad + Sg.grad.t())
+            gotS = torch.tril(Sbar) + torch.tril(Sbar, -1).t()
+            assert float((gotS - wantS).abs().max()) < 1e-9 * max(1.0, float(wantS.abs().max())), (it, n, pad)
+            Xbar = conv(rng.standard_normal((m, n)))
+            Lg, Bg = ref.clone().requires_grad_(True), B.clone().requires_grad_(True)
+            (torch.linalg.solve_triangular(Lg, Bg.t(), upper=False).t() * Xbar).sum().backward()
+            Bbar, Lb = ops.trsm_bwd(L, Bv, Xbar)
+            assert float((Bbar - Bg.grad).abs().max()) < 1e-9 * max(1.0, float(Bg.grad.abs().max())), (it, n, m, pad)
+            assert float((torch.tril(Lb) - torch.tril(Lg.grad)).abs().max()) < 1e-9 * max(1.0, float(Lg.grad.abs().max())), (it, n, m)
+        finally:
+            h.set_option('gemm_splitk', 1)
+
+
 def test_not_positive_definite_is_reported_through_the_abi(gpf):
     from gpflowSlim._backend import ops
     S = torch.eye(150, dtype=torch.float64)
