@@ -639,6 +639,38 @@ def test_fused_gpr_objective_gradient_and_prediction(gpf):
     assert max(errs) < 1e-9, errs
 
 
+def test_fuzz_fused_gpr_against_the_op_by_op_path(gpf):
+    """gps_gpr_nlml_fwd_bwd / gps_gpr_predict (one library call: Gram, factorisation, ride-along solves,
+    fused weight formation + Gram backward) against the same model evaluated one autograd op at a time
+    (`fused=False`: gram, cholesky, triangular solves with their hand-written adjoints), for every kernel of
+    the zoo and the NKN network, random sizes 2..330, 1..4 output columns, random noise.  Both paths run on
+    the CPU build; they share kernels but not orchestration, adjoint formulas or summation order.
+    GPSLIM_FUZZ=<n> cases (default 10; 150 were run clean when this was written)."""
+    ncases = int(os.environ.get('GPSLIM_FUZZ', '10'))
+    rng = np.random.default_rng(31)
+    d = 3
+    zoo = cases._kernel_zoo(gpf, d) + [('nkn', lambda: cases.nkn_c3_kernel(gpf, d))]
+    for it in range(ncases):
+        name, make = zoo[int(rng.integers(0, len(zoo)))]
+        n, r, ns = int(rng.integers(2, 331)), int(rng.integers(1, 5)), int(rng.integers(1, 40))
+        X, Y = conv(rng.standard_normal((n, d))), conv(rng.standard_normal((n, r)))
+        Xs = conv(rng.standard_normal((ns, d)))
+        noise = float(rng.uniform(0.05, 1.0))
+        out = {}
+        for fused in (True, False):
+            m = gpf.models.GPR(X, Y, kern=make(), obs_var=noise, fused=fused, name='fz_gpr_%d_%d' % (it, fused))
+            obj = m.objective
+            gr = torch.autograd.grad(obj, [p.unconstrained_tensor for p in m.parameters])
+            with torch.no_grad():
+                mu, var = m.predict_f(Xs)
+            out[fused] = [obj.detach()] + [g.detach() for g in gr] + [mu, var]
+        gmax = max(float(b.abs().max()) for b in out[False][1:-2])
+        for j, (a, b) in enumerate(zip(out[True], out[False])):
+            scale = max(float(b.abs().max()), 1e-4 * gmax if 1 <= j < len(out[True]) - 2 else 0.0, 1e-30)
+            err = float((a - b).abs().max()) / scale
+            assert err < 1e-8, (it, name, n, r, j, err)
+
+
 @pytest.mark.skipif(not FULL, reason='GPSLIM_CPU_LIB_FULL=0')
 def test_experimental_switches_through_the_real_dispatch_code(gpf, golden):
     """The switches with an alternative implementation (tests/test_gpu_switches.py), through the
