@@ -671,6 +671,60 @@ def test_fuzz_fused_gpr_against_the_op_by_op_path(gpf):
             assert err < 1e-8, (it, name, n, r, j, err)
 
 
+def test_fuzz_svgp_bound_against_the_torch_double(gpf, monkeypatch):
+    """The SVGP bound (svgp.py:94-125: Kuu / Kuf Gram kernels incl. the inducing-input gradient, the
+    conditional with its triangular-aware products, the KL term, the Gaussian expectations) with its
+    gradients w.r.t. every parameter AND the inducing inputs: the CPU build of the library against the
+    torch-CPU double of the ops layer (plain torch autograd), random batch 20..260, 4..130 inducing points,
+    1..2 latents, whitened or not, diagonal or full q_sqrt, every kernel of the zoo.
+    GPSLIM_FUZZ=<n> cases (default 8; 150 were run clean when this was written)."""
+    import cpu_ops_double
+    ncases = int(os.environ.get('GPSLIM_FUZZ', '8'))
+    rng = np.random.default_rng(53)
+    d = 3
+    # (the bare Linear kernels are left out: Kuu of rank 3 + jitter has condition 1e8, and the two
+    # implementations then differ by rounding x condition = 1e-5, as any two would)
+    zoo = [z for z in cases._kernel_zoo(gpf, d) if not z[0].startswith('lin_')]
+    specs = []
+    for it in range(ncases):
+        specs.append(dict(kern=int(rng.integers(0, len(zoo))), n=int(rng.integers(20, 261)), m=int(rng.integers(4, 131)),
+                          lat=int(rng.integers(1, 3)), whiten=bool(rng.integers(0, 2)), q_diag=bool(rng.integers(0, 2)),
+                          seed=int(rng.integers(0, 1 << 30))))
+
+    def run(sp, tag):
+        r = np.random.default_rng(sp['seed'])
+        X = r.standard_normal((sp['n'], d))
+        Y = np.sin(X.sum(1, keepdims=True)) + 0.1 * r.standard_normal((sp['n'], sp['lat']))
+        Z = r.standard_normal((sp['m'], d))
+        m = gpf.models.SVGP(conv(X), conv(Y), zoo[sp['kern']][1](), gpf.likelihoods.Gaussian(var=0.2), Z=Z,
+                            whiten=sp['whiten'], q_diag=sp['q_diag'], num_data=5 * sp['n'], name='fz_svgp_' + tag)
+        with torch.no_grad():
+            qm = m._q_mu.unconstrained_tensor
+            qm.copy_(torch.as_tensor(0.3 * r.standard_normal(tuple(qm.shape))).to(qm))
+            qs = m._q_sqrt.unconstrained_tensor
+            qs.add_(torch.as_tensor(0.05 * r.standard_normal(tuple(qs.shape))).to(qs))
+        params = [p.unconstrained_tensor for p in m.parameters] + [m.feature._Z.unconstrained_tensor]
+        obj = m.objective
+        with torch.no_grad():
+            sp['cond'] = float(np.linalg.cond(m.feature.Kuu(m.kern, jitter=gpf.settings.numerics.jitter_level).numpy()))
+        return [obj.detach()] + [g.detach() for g in torch.autograd.grad(obj, params)]
+    got = [run(sp, 'lib%d' % i) for i, sp in enumerate(specs)]
+    cpu_ops_double.install(monkeypatch)
+    want = [run(sp, 'dbl%d' % i) for i, sp in enumerate(specs)]
+    for i, (g, w) in enumerate(zip(got, want)):
+        gmax = max(float(b.abs().max()) for b in w[1:])
+        # the north-star tolerance (1e-8; Matern-type kernels reach a few 1e-9 through sqrt(d2 + 1e-12) at the
+        # coincident points of Kuu's diagonal); beyond that two correct implementations differ by rounding x
+        # condition of Kuu (inducing points are random here, so Kuu + 1e-6 I reaches 1e7)
+        tol = max(1e-8, 1e-14 * specs[i]['cond'])
+        for j, (a, b) in enumerate(zip(g, w)):
+            scale = max(float(b.abs().max()), 1e-4 * gmax if j else 0.0, 1e-30)
+            err = float((a - b).abs().max()) / scale
+            assert err < tol, (i, zoo[specs[i]['kern']][0], specs[i], j, err, tol)
+    # two implementations really ran: rounding differs somewhere
+    assert not all(torch.equal(a, b) for g, w in zip(got, want) for a, b in zip(g, w))
+
+
 @pytest.mark.skipif(not FULL, reason='GPSLIM_CPU_LIB_FULL=0')
 def test_experimental_switches_through_the_real_dispatch_code(gpf, golden):
     """The switches with an alternative implementation (tests/test_gpu_switches.py), through the
