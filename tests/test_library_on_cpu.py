@@ -830,6 +830,68 @@ def _dist_worker(rank, world, port, so_path, n, r, block, out_q, schedule=True):
         dist.destroy_process_group()
 
 
+def test_fuzz_distributed_path_at_world_1_against_the_fused_call(gpf):
+    """dist_gpr.nlml_and_grad with one rank (every block row local, no collective) on the CPU build: the
+    block-row factorisation in all three schedules, the row-map GEMM, the prefix solves for the big-leaf
+    sizes, the inverse rows and gps_gpr_weight_rows -- against the fused single-call path
+    (gps_gpr_nlml_fwd_bwd), random orders 2..700, 1..3 output columns, block 128 / 256 / 512, kernels of the
+    zoo (any program takes this path).  The multi-rank layouts are the gloo test below.
+    GPSLIM_FUZZ=<n> cases (default 6; 80 were run clean when this was written)."""
+    import contextlib
+    from gpflowSlim._backend import dist_gpr, lib, ops
+    ncases = int(os.environ.get('GPSLIM_FUZZ', '6'))
+    rng = np.random.default_rng(91)
+    d = 3
+
+    class Be(dist_gpr.CudaBackend):
+        poison = True
+
+        def __init__(self):
+            self._L, self.device = lib, torch.device('cpu')
+
+        def streams(self):
+            return 'main', 'chain', 'tb', 'gather', 'narrow'
+
+        def on(self, stream):
+            return contextlib.nullcontext()
+
+        def record(self, stream):
+            return None
+
+        def wait(self, stream, event):
+            pass
+    zoo = cases._kernel_zoo(gpf, d) + [('nkn', lambda: cases.nkn_c3_kernel(gpf, d))]
+    h = lib.handle_for(None)
+    for it in range(ncases):
+        name, make = zoo[int(rng.integers(0, len(zoo)))]
+        n, r = int(rng.choice([int(rng.integers(2, 130)), int(rng.integers(130, 701))])), int(rng.integers(1, 4))
+        block = int(rng.choice([128, 256, 512]))
+        schedule = [True, 'v2', False][int(rng.integers(0, 3))]
+        leaf = int(rng.choice([128, 256, 512]))
+        noise = float(rng.uniform(0.05, 0.8))
+        X, Y = conv(rng.standard_normal((n, d))), conv(rng.standard_normal((n, r)))
+        kern = make()
+        prog = kern.program()
+        theta = prog.theta('cpu').detach()
+        h.set_option('trsm_leaf', leaf)
+        try:
+            nlml, dth, dnz, dY = dist_gpr.nlml_and_grad(prog, theta, noise, X, Y, block=block, backend=Be(),
+                                                        lookahead=schedule)
+        finally:
+            h.set_option('trsm_leaf', 512)
+        th = theta.clone().requires_grad_(True)
+        nz = torch.tensor(noise, dtype=torch.float64, requires_grad=True)
+        Yt = Y.clone().requires_grad_(True)
+        # fused path through its autograd Function (theta is the program's own parameter vector there)
+        obj = -ops._GprLogLik.apply(th, nz, Yt, X, prog)
+        g = torch.autograd.grad(obj, [th, nz, Yt])
+        gmax = max(float(x.abs().max()) for x in g[:2])
+        for j, (a, b) in enumerate(zip([nlml, dth, dnz, dY], [obj.detach()] + list(g))):
+            scale = max(float(b.abs().max()), 1e-4 * gmax if j in (1, 2) else 0.0, 1e-30)
+            err = float((a - b).abs().max()) / scale
+            assert err < 1e-8, (it, name, n, r, block, schedule, leaf, j, err)
+
+
 @pytest.mark.parametrize('world,n,r,block,schedule', [(2, 300, 1, 128, True)] + (
     [(1, 330, 2, 128, 'v2'), (2, 300, 1, 128, 'v2'), (3, 420, 1, 128, True)] if FULL else []))
 def test_distributed_gpr_on_the_real_kernels_under_gloo(cpu_lib, world, n, r, block, schedule):
