@@ -892,6 +892,160 @@ def test_fuzz_distributed_path_at_world_1_against_the_fused_call(gpf):
             assert err < 1e-8, (it, name, n, r, block, schedule, leaf, j, err)
 
 
+class _ThreadComm(object):
+    """The communicator interface of dist_gpr._Comm for P ranks that are THREADS of this process: a
+    collective is a rendezvous at a barrier around a shared slot.  Every rank issues its collectives in the
+    same order (what NCCL requires, and what the gloo tests already rely on), so one barrier serves all
+    three channels.  Lets the randomised test below run dozens of multi-rank configurations without
+    spawning processes."""
+
+    def __init__(self, world, rank, shared):
+        self.world, self.rank, self.sh = world, rank, shared
+
+    def _sync(self):
+        self.sh['bar'].wait(timeout=600)
+
+    def broadcast(self, t, src, which='chain'):
+        if self.rank == src:
+            self.sh['slot'] = t
+        self._sync()
+        if self.rank != src:
+            t.copy_(self.sh['slot'])
+        self._sync()
+
+    def all_gather(self, out, inp):
+        self.sh['parts'][self.rank] = inp
+        self._sync()
+        out.copy_(torch.cat([p.reshape(-1) for p in self.sh['parts']]).reshape(out.shape))
+        self._sync()
+
+    def all_reduce_sum(self, t):
+        self.sh['parts'][self.rank] = t.clone()
+        self._sync()
+        total = sum(self.sh['parts'][1:], self.sh['parts'][0].clone())      # fixed order on every rank
+        self._sync()
+        t.copy_(total)
+
+
+def test_fuzz_distributed_path_with_ranks_as_threads(gpf, monkeypatch):
+    """dist_gpr.nlml_and_grad and dist_gpr.predict at world sizes 2..5 with the ranks as threads of this
+    process (_ThreadComm), every rank on the real kernels of the CPU build with NaN-poisoned buffers:
+    snake block-row layouts with ragged last blocks and more ranks than block rows, all three schedules,
+    1..3 output columns, fewer test points than ranks -- against the fused single-call path.  The emulated
+    library is not re-entrant, so its calls are serialised by a lock; each rank has its own handle.
+    GPSLIM_FUZZ=<n> cases (default 5; 60 were run clean when this was written)."""
+    import contextlib
+    import ctypes
+    import threading
+    from gpflowSlim._backend import dist_gpr, lib, ops
+    ncases = int(os.environ.get('GPSLIM_FUZZ', '5'))
+    rng = np.random.default_rng(123)
+    d = 3
+    lock = threading.RLock()
+
+    class LockedLib(object):
+        def __init__(self, cdll):
+            self._cdll = cdll
+
+        def __getattr__(self, name):
+            fn = getattr(self._cdll, name)
+
+            def call(*a):
+                with lock:
+                    return fn(*a)
+            return call
+
+    class RankHandle(lib.Handle):
+        def __init__(self):
+            lib.Handle.__init__(self, 0)
+            self.lib = LockedLib(self.lib)
+
+        def sync_stream(self):
+            pass
+    tls = threading.local()
+    main_handle = lib.handle_for(None)
+
+    def handle_for(_):
+        if threading.current_thread() is threading.main_thread():
+            return main_handle
+        if not hasattr(tls, 'h'):
+            with lock:
+                tls.h = RankHandle()
+        return tls.h
+    monkeypatch.setattr(lib, 'handle_for', handle_for)
+    monkeypatch.setattr(ops, 'handle_for', handle_for)
+    monkeypatch.setattr(dist_gpr, '_Comm', lambda g: g)
+
+    class Be(dist_gpr.CudaBackend):
+        poison = True
+
+        def __init__(self):
+            self._L, self.device = lib, torch.device('cpu')
+
+        def streams(self):
+            return 'main', 'chain', 'tb', 'gather', 'narrow'
+
+        def on(self, stream):
+            return contextlib.nullcontext()
+
+        def record(self, stream):
+            return None
+
+        def wait(self, stream, event):
+            pass
+    zoo = [z for z in cases._kernel_zoo(gpf, d) if z[0] in ('rbf_ard', 'm32_ard', 'sum', 'product', 'periodic')]
+    for it in range(ncases):
+        name, make = zoo[int(rng.integers(0, len(zoo)))]
+        world = int(rng.integers(2, 6))
+        n, r = int(rng.integers(2, 560)), int(rng.integers(1, 4))
+        ns = int(rng.integers(1, 30))
+        block = int(rng.choice([128, 256]))
+        schedule = [True, 'v2', False][int(rng.integers(0, 3))]
+        noise = float(rng.uniform(0.05, 0.8))
+        X, Y = conv(rng.standard_normal((n, d))), conv(rng.standard_normal((n, r)))
+        Xs = conv(rng.standard_normal((ns, d)))
+        kern = make()
+        prog = kern.program()
+        theta = prog.theta('cpu').detach()
+        kd = kern.Kdiag(Xs).detach()
+        shared = dict(bar=threading.Barrier(world), slot=None, parts=[None] * world)
+        results, errors = [None] * world, []
+
+        def rank_main(rank):
+            try:
+                comm = _ThreadComm(world, rank, shared)
+                be = Be()
+                out = dist_gpr.nlml_and_grad(prog, theta, noise, X, Y, block=block, group=comm, backend=be,
+                                             lookahead=schedule)
+                mu, var = dist_gpr.predict(prog, theta, noise, X, Y, Xs, kd, block=block, group=comm, backend=be,
+                                           lookahead=schedule)
+                results[rank] = list(out) + [mu, var]
+            except BaseException as e:      # noqa: a failing rank must not leave the others at the barrier
+                errors.append((rank, repr(e)))
+                shared['bar'].abort()
+        threads = [threading.Thread(target=rank_main, args=(q,)) for q in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors, (it, name, world, n, r, block, schedule, errors[:2])
+        th = theta.clone().requires_grad_(True)
+        nz = torch.tensor(noise, dtype=torch.float64, requires_grad=True)
+        Yt = Y.clone().requires_grad_(True)
+        obj = -ops._GprLogLik.apply(th, nz, Yt, X, prog)
+        g = torch.autograd.grad(obj, [th, nz, Yt])
+        mu0, var0 = ops.gpr_predict(prog, X, Y, torch.tensor(noise, dtype=torch.float64), Xs)
+        want = [obj.detach()] + list(g) + [mu0, var0]
+        gmax = max(float(x.abs().max()) for x in g[:2])
+        for rank in range(world):
+            for j, (a, b) in enumerate(zip(results[rank], want)):
+                scale = max(float(b.abs().max()), 1e-4 * gmax if j in (1, 2) else 0.0, 1e-30)
+                err = float((a.reshape(b.shape) - b).abs().max()) / scale
+                assert err < 1e-8, (it, name, world, rank, n, r, ns, block, schedule, j, err)
+            for a, b in zip(results[rank], results[0]):
+                assert torch.equal(a, b)          # every rank returns the same bits
+
+
 @pytest.mark.parametrize('world,n,r,block,schedule', [(2, 300, 1, 128, True)] + (
     [(1, 330, 2, 128, 'v2'), (2, 300, 1, 128, 'v2'), (3, 420, 1, 128, True)] if FULL else []))
 def test_distributed_gpr_on_the_real_kernels_under_gloo(cpu_lib, world, n, r, block, schedule):
