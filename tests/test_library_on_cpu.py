@@ -105,10 +105,10 @@ def test_fuzz_factorisation_solves_and_inverses_on_padded_buffers(gpf):
     gps_tri_inv_t, gps_potri, gps_chol_bwd and gps_trsm_bwd against LAPACK / torch autograd: random orders
     1..520 (every leaf / strip / GEMM-tile raggedness), operands that are column slices of wider NaN-filled
     buffers (leading dimension != width: nothing outside the view may be read or written), split-K on and
-    off.  GPSLIM_FUZZ=<n> cases (default 12; 150 were run clean when this was written)."""
+    off.  GPSLIM_FUZZ=<n> cases (default 6; 150 were run clean when this was written)."""
     import ctypes
     from gpflowSlim._backend import lib, ops
-    ncases = int(os.environ.get('GPSLIM_FUZZ', '12'))
+    ncases = int(os.environ.get('GPSLIM_FUZZ', '6'))
     rng = np.random.default_rng(77)
     h = lib.handle_for(None)
 
@@ -407,10 +407,10 @@ def test_fuzz_nkn_tensor_core_kernels(gpf):
     """Randomised differential test of gram_fwd_nkn_kernel / gram_bwd_nkn_kernel against the interpreter:
     random numbers of primitives (1-7) of random types / ARD / active dimensions (1-8 of them), random
     layer widths, ragged sizes; K(X), K(X, X2), both dense backward passes and, every third case, the fused
-    GPR gradient.  GPSLIM_FUZZ=<n> cases (default 24; 600 were run clean when this was written)."""
+    GPR gradient.  GPSLIM_FUZZ=<n> cases (default 16; 600 were run clean when this was written)."""
     from gpflowSlim._backend import lib
     k = gpf.kernels
-    ncases = int(os.environ.get('GPSLIM_FUZZ', '24'))
+    ncases = int(os.environ.get('GPSLIM_FUZZ', '16'))
     rng = np.random.default_rng(2024)
     h = lib.handle_for(None)
     for it in range(ncases):
@@ -645,8 +645,8 @@ def test_fuzz_fused_gpr_against_the_op_by_op_path(gpf):
     (`fused=False`: gram, cholesky, triangular solves with their hand-written adjoints), for every kernel of
     the zoo and the NKN network, random sizes 2..330, 1..4 output columns, random noise.  Both paths run on
     the CPU build; they share kernels but not orchestration, adjoint formulas or summation order.
-    GPSLIM_FUZZ=<n> cases (default 10; 150 were run clean when this was written)."""
-    ncases = int(os.environ.get('GPSLIM_FUZZ', '10'))
+    GPSLIM_FUZZ=<n> cases (default 6; 150 were run clean when this was written)."""
+    ncases = int(os.environ.get('GPSLIM_FUZZ', '6'))
     rng = np.random.default_rng(31)
     d = 3
     zoo = cases._kernel_zoo(gpf, d) + [('nkn', lambda: cases.nkn_c3_kernel(gpf, d))]
@@ -677,9 +677,9 @@ def test_fuzz_svgp_bound_against_the_torch_double(gpf, monkeypatch):
     gradients w.r.t. every parameter AND the inducing inputs: the CPU build of the library against the
     torch-CPU double of the ops layer (plain torch autograd), random batch 20..260, 4..130 inducing points,
     1..2 latents, whitened or not, diagonal or full q_sqrt, every kernel of the zoo.
-    GPSLIM_FUZZ=<n> cases (default 8; 150 were run clean when this was written)."""
+    GPSLIM_FUZZ=<n> cases (default 5; 150 were run clean when this was written)."""
     import cpu_ops_double
-    ncases = int(os.environ.get('GPSLIM_FUZZ', '8'))
+    ncases = int(os.environ.get('GPSLIM_FUZZ', '5'))
     rng = np.random.default_rng(53)
     d = 3
     # (the bare Linear kernels are left out: Kuu of rank 3 + jitter has condition 1e8, and the two
@@ -836,10 +836,10 @@ def test_fuzz_distributed_path_at_world_1_against_the_fused_call(gpf):
     sizes, the inverse rows and gps_gpr_weight_rows -- against the fused single-call path
     (gps_gpr_nlml_fwd_bwd), random orders 2..700, 1..3 output columns, block 128 / 256 / 512, kernels of the
     zoo (any program takes this path).  The multi-rank layouts are the gloo test below.
-    GPSLIM_FUZZ=<n> cases (default 6; 80 were run clean when this was written)."""
+    GPSLIM_FUZZ=<n> cases (default 3; 80 were run clean when this was written)."""
     import contextlib
     from gpflowSlim._backend import dist_gpr, lib, ops
-    ncases = int(os.environ.get('GPSLIM_FUZZ', '6'))
+    ncases = int(os.environ.get('GPSLIM_FUZZ', '3'))
     rng = np.random.default_rng(91)
     d = 3
 
@@ -933,12 +933,12 @@ def test_fuzz_distributed_path_with_ranks_as_threads(gpf, monkeypatch):
     snake block-row layouts with ragged last blocks and more ranks than block rows, all three schedules,
     1..3 output columns, fewer test points than ranks -- against the fused single-call path.  The emulated
     library is not re-entrant, so its calls are serialised by a lock; each rank has its own handle.
-    GPSLIM_FUZZ=<n> cases (default 5; 60 were run clean when this was written)."""
+    GPSLIM_FUZZ=<n> cases (default 3; 60 were run clean when this was written)."""
     import contextlib
     import ctypes
     import threading
     from gpflowSlim._backend import dist_gpr, lib, ops
-    ncases = int(os.environ.get('GPSLIM_FUZZ', '5'))
+    ncases = int(os.environ.get('GPSLIM_FUZZ', '3'))
     rng = np.random.default_rng(123)
     d = 3
     lock = threading.RLock()
