@@ -118,7 +118,8 @@ def test_fuzz_factorisation_solves_and_inverses_on_padded_buffers(gpf):
         v.copy_(a)
         return buf, v
     for it in range(ncases):
-        n = int(rng.choice([int(rng.integers(1, 40)), int(rng.integers(100, 300)), int(rng.integers(300, 521))]))
+        n = int(rng.choice([int(rng.integers(1, 40)), int(rng.integers(100, 300)), int(rng.integers(300, 521)),
+                            int(rng.choice([128, 256, 384, 512]))]))      # powers of two: the level-batched inverse
         m = int(rng.integers(1, 200))
         pad = int(rng.choice([0, 1, 2, 5, 16]))
         h.set_option('gemm_splitk', int(rng.integers(0, 2)))
