@@ -7,8 +7,10 @@ Transformations (all mechanical):
   1. k<<<grid, block, smem, stream>>>(args);  ->  EMU_LAUNCH(grid, block, smem, k(args));
   2. extern __shared__ [__align__(16)] double NAME[];  ->  double* NAME = emu_smem;
   3. asm volatile("prefetch.global.L2 ...");   ->  (void)0;      (a cache hint)
-  4. gemm.cu: the TMA + mbarrier kernel (inline PTX) and the tensor-map encoder are cut out;
-     make_tensor_map() returns false, so every product takes the cp.async tensor-core kernel
+  4. gemm.cu: the six inline-PTX helper functions of the TMA + mbarrier kernel (mbarrier init / arrive /
+     expect_tx / wait, cp.async.bulk.tensor.2d, ld.shared) are replaced by the functional stand-ins of
+     tma_emulation.inc and the tensor-map encoder by a plain description of the operand view: the
+     kernel's own main loop runs; gemm_impl 2 still selects the cp.async tensor-core kernel
   5. handle.cu: DLPack device_type 2 (kDLCUDA) -> 1 (kDLCPU) in the argument checks
 """
 import os
@@ -67,13 +69,18 @@ def transform(name, src):
     src = re.sub(r'extern __shared__ (?:__align__\(16\) )?double (\w+)\[\];', r'double* \1 = emu_smem;', src)
     src = re.sub(r'asm volatile\("prefetch\.global\.L2.*?\)\);', '(void)0;', src, flags=re.S)
     if name == 'gemm.cu':
-        a = src.index('// ------------------------------------------------------------------ TMA + mbarrier variant')
-        b = src.index('__global__ void gemm_nt_naive_kernel')
-        src = src[:a] + ('constexpr int TMA_THREADS = GEMM_THREADS, TMA_SMEM = 0;\n'
-                         'void gemm_nt_tma_kernel(const GemmArgs, const CUtensorMap, const CUtensorMap) {}\n\n') + src[b:]
+        # the six PTX helpers of the TMA kernel -> functional stand-ins; the kernel body stays
+        a = src.index('__device__ __forceinline__ void mbar_init(')
+        b = src.index('__global__ void __launch_bounds__(TMA_THREADS, 1)')
+        assert src[a:b].count('asm volatile') == 6
+        src = src[:a] + open(os.path.join(HERE, 'tma_emulation.inc')).read() + '\n' + src[b:]
+        src, k = re.subn(r'asm volatile\("fence\.mbarrier_init\.release\.cluster;\\n" ::: "memory"\);', '(void)0;', src)
+        assert k == 1, k
         a = src.index('typedef CUresult (*EncodeTiledFn)')
         b = src.index('double gemm_flops(const GemmArgs& g) {', a)
-        src = src[:a] + 'bool make_tensor_map(CUtensorMap*, const Mat&) { return false; }\n\n' + src[b:]
+        src = src[:a] + ('bool make_tensor_map(CUtensorMap* tm, const Mat& X) {\n'
+                         '  tm->p = X.p; tm->cols = (uint64_t)X.cols; tm->rows = (uint64_t)X.rows; tm->ld = (uint64_t)X.ld;\n'
+                         '  return true;\n}\n\n') + src[b:]
     if name == 'handle.cu':
         src, k = re.subn(r'device_type != 2', 'device_type != 1', src)
         assert k == 2, k

@@ -1,4 +1,8 @@
-// TEST INFRASTRUCTURE ONLY -- stand-in for <cuda.h> in the CPU build of the library: the TMA
-// kernel and its tensor-map encoder are cut out of gemm.cu there (see cuda_runtime.h).
+// TEST INFRASTRUCTURE ONLY -- stand-in for <cuda.h> in the CPU build of the library: the tensor map
+// of the TMA GEMM kernel as a plain description of the row-major operand view (tma_emulation.inc reads it).
 #pragma once
-struct CUtensorMap { char opaque[128]; };
+#include <stdint.h>
+struct CUtensorMap {
+  const double* p;
+  uint64_t cols, rows, ld;        // dims (K, rows), row stride in elements
+};

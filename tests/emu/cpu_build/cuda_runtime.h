@@ -9,8 +9,10 @@
 //     thread, blocks one after the other, __syncthreads = warp gather + pthread barrier across
 //     the warps, warp collectives = warp barriers + exchange buffer, mma.sync.m8n8k4.f64 emulated
 //     per the PTX fragment layout, cp.async = copy with zero fill;
-//   * the TMA / mbarrier GEMM kernel is cut out (inline PTX): the cp.async tensor-core kernel
-//     serves every product, as it does on the GPU for operands TMA cannot address.
+//   * the TMA / mbarrier GEMM kernel keeps its own main loop; only its six PTX helper functions
+//     (mbarrier init / arrive / wait, the tensor copy with the 128-byte swizzle, ld.shared) are
+//     replaced by the functional stand-ins of tma_emulation.inc, and the tensor-map encoder by a
+//     plain description of the operand view.
 // Nothing here is shipped or used by the product.
 #pragma once
 #ifndef _GNU_SOURCE
@@ -18,6 +20,7 @@
 #endif
 #include <math.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <stdio.h>
@@ -43,6 +46,7 @@ using std::min;
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))
+#define __grid_constant__
 
 // ---------------------------------------------------------------- runtime API
 typedef int cudaError_t;
@@ -125,6 +129,8 @@ inline void dmma884(double& c0, double& c1, double a, double b) {
   c0 = s0;
   c1 = s1;
 }
+inline uint32_t smem_u32(const void* p) { return (uint32_t)((const char*)p - (const char*)emu_smem); }   // byte offset
+inline void __trap() { abort(); }
 inline double rsqrt(double x) { return 1.0 / sqrt(x); }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 inline int atomicCAS(int* addr, int cmp, int val) {

@@ -98,6 +98,17 @@ inline void emu_yield() {
   w->cur = to;
   emu_ctx_switch(w->fib[from].ctx, w->fib[to].ctx);
 }
+// the same for a lane that polls something another warp will change (an mbarrier): false if no other lane
+// of this warp can run, and the caller should give up the OS thread instead
+inline bool emu_yield_if_possible() {
+  EmuWarp* w = emu_w;
+  for (int l = 0; l < w->n; ++l)
+    if (l != w->cur && !w->fib[l].done) {
+      emu_yield();
+      return true;
+    }
+  return false;
+}
 inline void emu_warp_barrier() {
   EmuWarp* w = emu_w;
   const unsigned g = w->gen;

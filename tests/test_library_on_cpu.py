@@ -2,8 +2,8 @@
 and driven through the package's own ctypes binding and autograd layer.
 
 `tests/emu/cpu_build/build.py` transforms the five unmodified .cu files textually (kernel launches
--> EMU_LAUNCH, dynamic shared memory, one cache-hint asm, the TMA/mbarrier kernel cut out so that
-the cp.async tensor-core kernel serves every GEMM, DLPack device type) and compiles them with g++
+-> EMU_LAUNCH, dynamic shared memory, one cache-hint asm, the six PTX helper functions of the
+TMA/mbarrier GEMM kernel -> functional stand-ins (its main loop is the kernel's own), DLPack device type) and compiles them with g++
 against a stand-in <cuda_runtime.h>: one host thread per warp with its lanes as cooperative fibers
 (tests/emu/emu_fibers.h), barriers for __syncthreads / warp collectives, an emulation of
 mma.sync.m8n8k4.f64.  The resulting shared
@@ -12,7 +12,8 @@ so everything above it is the shipped code: DLTensor marshaling, argument checks
 management, the recursive blocked Cholesky / triangular inverse, the fused one-call GPR
 objective + gradient, the Gram kernels, the autograd adjoints.
 
-What this cannot see: the TMA + mbarrier main loop of the default GEMM kernel, stream
+What this cannot see: that the hardware's 128-byte swizzle and mbarrier semantics ARE what the stand-ins
+implement (the GPU tests do), stream
 concurrency (launches run to completion in issue order), and anything about speed.
 
 The whole selection runs in about a minute; GPSLIM_CPU_LIB_FULL=0 keeps only the short one."""
@@ -225,6 +226,48 @@ def test_gemm_flags_through_the_launch_code(gpf):
     close(ops.gemm_nt(conv(G), conv(G), alpha=-0.5, beta=1.0, out=conv(C0.copy())), C0 - 0.5 * G @ G.T)
     A3 = conv(rng.standard_normal((33, 7)))[:, :5]                    # odd leading dimension: 8-byte staging
     close(ops.gemm_nt(A3, A3), A3.numpy() @ A3.numpy().T)
+
+
+def test_tma_kernel_main_loop_against_the_cp_async_kernel_and_numpy(gpf):
+    """gemm_nt_tma_kernel -- the kernel that does 95 % of a GPR step -- with its OWN main loop on the CPU
+    (build.py swaps only its six PTX helpers for the functional stand-ins of emu/cpu_build/tma_emulation.inc):
+    the 6-stage ring with more k-tiles than stages (barrier phases flip several times), fewer k-tiles than
+    stages, K not a multiple of the 16-wide box (zero-filled edge), ragged M / N, triangular operands (K ranges
+    per tile), lower-only output, alpha / beta, and the K-sliced launch of few-tile products -- against numpy
+    and against the cp.async tensor-core kernel (gemm_impl 2), which the same launch code selects for
+    operands TMA cannot address."""
+    from gpflowSlim._backend import lib, ops
+    rng = np.random.default_rng(21)
+    h = lib.handle_for(None)
+    shapes = [(150, 140, 400), (129, 260, 97), (5, 3, 2), (130, 131, 16), (300, 70, 1100), (257, 257, 40)]
+    for (m, n, k) in shapes:
+        A, B = rng.standard_normal((m, k)), rng.standard_normal((n, k))
+        C0 = rng.standard_normal((m, n))
+        variants = [dict(), dict(alpha=-0.7, beta=0.3)]
+        if m == n:
+            Lo, Up = np.tril(rng.standard_normal((m, m))), np.triu(rng.standard_normal((m, m)))
+            variants += [dict(sq=(Lo, Lo, 1, 1, 1)), dict(sq=(Up, Up, 2, 2, 0)), dict(sq=(Lo, Up, 1, 2, 0))]
+        for v in variants:
+            out = {}
+            for impl in (0, 2):
+                h.set_option('gemm_impl', impl)
+                try:
+                    if 'sq' in v:
+                        a, b, ta, tb, cu = v['sq']
+                        got = ops.gemm_nt(conv(a), conv(b), a_tri=ta, b_tri=tb, c_uplo=cu)
+                        want = np.tril(a @ b.T) if cu else a @ b.T
+                    elif 'alpha' in v:
+                        got = ops.gemm_nt(conv(A), conv(B), alpha=v['alpha'], beta=v['beta'], out=conv(C0.copy()))
+                        want = v['alpha'] * (A @ B.T) + v['beta'] * C0
+                    else:
+                        got = ops.gemm_nt(conv(A), conv(B))
+                        want = A @ B.T
+                finally:
+                    h.set_option('gemm_impl', 0)
+                out[impl] = got
+                assert np.abs(got.numpy() - want).max() < 1e-12 * max(1.0, np.abs(want).max()), (m, n, k, list(v), impl)
+            # same tile order, K ranges and per-lane accumulation order in both kernels
+            assert torch.equal(out[0], out[2]), (m, n, k, list(v))
 
 
 def test_autograd_adjoints_on_the_real_kernels(gpf):
