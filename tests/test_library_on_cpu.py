@@ -270,6 +270,60 @@ def test_tma_kernel_main_loop_against_the_cp_async_kernel_and_numpy(gpf):
             assert torch.equal(out[0], out[2]), (m, n, k, list(v))
 
 
+def test_fuzz_gemm_through_the_shipped_launch_code(gpf):
+    """gps_gemm_nt with random shapes (K up to 1300: the stage ring wraps many times, few-tile products are
+    K-sliced), leading-dimension paddings and 8-byte misalignments (the launch code picks the TMA kernel, the
+    16-byte or the 8-byte cp.async staging), triangular operands, lower output, alpha / beta, output views
+    inside wider buffers whose padding columns must stay untouched -- against numpy.
+    GPSLIM_FUZZ=<n> cases (default 25; 300 were run clean when this was written)."""
+    from gpflowSlim._backend import lib
+    ncases = int(os.environ.get('GPSLIM_FUZZ', '25'))
+    rng = np.random.default_rng(404)
+    h = lib.handle_for(None)
+
+    def tri(a, t):
+        return a if t == 0 else (np.tril(a) if t == 1 else np.triu(a))
+    for it in range(ncases):
+        a_tri = b_tri = c_uplo = 0
+        if rng.random() < 0.5:
+            M = N = Kd = int(rng.integers(1, 300))
+            a_tri, b_tri, c_uplo = int(rng.integers(0, 3)), int(rng.integers(0, 3)), int(rng.integers(0, 2))
+            if rng.random() < 0.3:
+                Kd, a_tri, b_tri = int(rng.integers(1, 1300)), 0, 0
+        else:
+            M, N = int(rng.integers(1, 300)), int(rng.integers(1, 300))
+            Kd = int(rng.choice([int(rng.integers(1, 70)), int(rng.integers(70, 1300))]))
+        pa, pb, pc = (int(rng.integers(0, 4)) for _ in range(3))
+        oa, ob = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+        An = rng.standard_normal(M * (Kd + pa) + 1)[oa:oa + M * (Kd + pa)].reshape(M, Kd + pa)[:, :Kd]
+        Bn = rng.standard_normal(N * (Kd + pb) + 1)[ob:ob + N * (Kd + pb)].reshape(N, Kd + pb)[:, :Kd]
+        An[...] = tri(An.copy(), a_tri)
+        Bn[...] = tri(Bn.copy(), b_tri)
+        C0 = rng.standard_normal((M, N))
+        beta, alpha = float(rng.choice([0.0, 1.0, -0.4])), float(rng.choice([1.0, -1.0, 0.6]))
+        Cfull = np.full((M, N + pc), 777.0)
+        Cfull[:, :N] = C0 if beta else np.nan
+        A, B, Cf = torch.from_numpy(An), torch.from_numpy(Bn), torch.from_numpy(Cfull)     # share memory: same strides / alignment
+        h.set_option('gemm_splitk', int(rng.random() < 0.7))
+        try:
+            h.check(h.lib.gps_gemm_nt(h.ptr, alpha, lib.view(A).ref, lib.view(B).ref, beta, lib.view(Cf[:, :N]).ref,
+                                      a_tri, b_tri, c_uplo))
+        finally:
+            h.set_option('gemm_splitk', 1)
+        got = Cfull[:, :N]
+        want = alpha * An @ Bn.T + (beta * C0 if beta else 0.0)
+        tol = 5e-13 * max(1.0, np.abs(want).max())
+        what = dict(it=it, M=M, N=N, K=Kd, a_tri=a_tri, b_tri=b_tri, c_uplo=c_uplo, pad=(pa, pb, pc), off=(oa, ob),
+                    alpha=alpha, beta=beta)
+        if c_uplo:
+            assert np.abs(np.tril(got) - np.tril(want)).max() < tol, what
+            iu = np.triu_indices(M, 1)
+            assert (got[iu] == C0[iu]).all() if beta else np.isnan(got[iu]).all(), what
+        else:
+            assert np.abs(got - want).max() < tol, what
+        assert (Cfull[:, N:] == 777.0).all(), what
+
+
 def test_autograd_adjoints_on_the_real_kernels(gpf):
     """The check of tests/test_gpu_kernels.py::test_autograd_ops_match_torch, on the CPU build."""
     from gpflowSlim._backend import ops
