@@ -750,7 +750,8 @@ def test_fuzz_fused_gpr_against_the_op_by_op_path(gpf):
     zoo = cases._kernel_zoo(gpf, d) + [('nkn', lambda: cases.nkn_c3_kernel(gpf, d))]
     for it in range(ncases):
         name, make = zoo[int(rng.integers(0, len(zoo)))]
-        n, r, ns = int(rng.integers(2, 331)), int(rng.integers(1, 5)), int(rng.integers(1, 40))
+        n, r, ns = int(rng.integers(2, 331)), int(rng.choice([1, 1, 2, 3, 4, 9, 16, 17])), int(rng.integers(1, 40))
+        # (17 output columns: beyond the fused call's 16, GPR falls back to the op-by-op path by itself)
         X, Y = conv(rng.standard_normal((n, d))), conv(rng.standard_normal((n, r)))
         Xs = conv(rng.standard_normal((ns, d)))
         noise = float(rng.uniform(0.05, 1.0))
