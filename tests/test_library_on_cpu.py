@@ -1096,7 +1096,7 @@ def test_fuzz_distributed_path_with_ranks_as_threads(gpf, monkeypatch):
     for it in range(ncases):
         name, make = zoo[int(rng.integers(0, len(zoo)))]
         world = int(rng.integers(2, 6))
-        n, r = int(rng.integers(2, 560)), int(rng.integers(1, 4))
+        n, r = int(rng.integers(2, int(os.environ.get('GPSLIM_FUZZ_MAXN', '560')))), int(rng.choice([1, 1, 2, 3, 16]))
         ns = int(rng.integers(1, 30))
         block = int(rng.choice([128, 256]))
         schedule = [True, 'v2', False][int(rng.integers(0, 3))]
